@@ -1,0 +1,427 @@
+// c5_api.cu — the C ABI of include/c5gpu.h: context, mesh/solid upload, the per-view pipeline.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "c5_internal.h"
+
+using namespace c5;
+
+namespace {
+
+std::mutex g_create_err_mu;
+std::string g_create_err;
+
+const double kPi = 3.14159265358979323846; // config.hpp:45
+
+template <class Fn>
+int guarded(c5_ctx* ctx, Fn&& fn) {
+    try {
+        if (ctx) g_launch_counter = &ctx->dev[0]->launches;
+        fn();
+        return C5_OK;
+    } catch (const Error& e) {
+        if (ctx) ctx->err = e.text;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "host allocation failed";
+        return C5_E_NOMEM;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = e.what();
+        return C5_E_INVALID;
+    }
+}
+
+void use_device(const DeviceState& d) {
+    if (!kHostSim) C5_CUDA(cudaSetDevice(d.device));
+}
+
+void record(DeviceState& d, int k) {
+    if (!kHostSim) C5_CUDA(cudaEventRecord(d.ev[k], d.stream));
+}
+
+float elapsed(DeviceState& d, int a, int b) {
+    if (kHostSim) return 0.f;
+    float ms = 0.f;
+    C5_CUDA(cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]));
+    return ms;
+}
+
+struct ViewPlan {
+    Rot rot[kMaxRot];
+    int n_rot;
+    int row_begin, row_end;
+    double x_min, y_min, step_x, step_y;
+};
+
+ViewPlan plan_view(const c5_view* v) {
+    if (!v) fail(C5_E_INVALID, "render: view is NULL");
+    if (v->res_x < 2 || v->res_y < 2) fail(C5_E_INVALID, "render: resolution must be at least 2 x 2");
+    if (static_cast<int64_t>(v->res_x) * v->res_y >= (int64_t{1} << 31)) fail(C5_E_INVALID, "render: image too large");
+    if (v->n_rot < 0 || v->n_rot > kMaxRot) fail(C5_E_INVALID, "render: n_rot out of range");
+    if (!(v->window[0] > v->window[1]) || !(v->window[2] > v->window[3])) {
+        fail(C5_E_INVALID, "render: window must be {x_max, x_min, y_max, y_min} with max > min");
+    }
+    if (v->precision != 64 && v->precision != 0) fail(C5_E_INVALID, "render: precision must be 64");
+    ViewPlan p{};
+    p.n_rot = v->n_rot;
+    for (int k = 0; k < v->n_rot; k++) {
+        if (v->rot[k].axis != 0 && v->rot[k].axis != 1) fail(C5_E_INVALID, "render: rotation axis must be 0 or 1");
+        // the trig is evaluated here by the host libm, exactly like the reference's host loop
+        p.rot[k] = Rot{v->rot[k].axis, 0, std::cos(v->rot[k].angle), std::sin(v->rot[k].angle), v->rot[k].x0};
+    }
+    p.row_begin = v->row_begin;
+    p.row_end = v->row_end;
+    if (p.row_begin == 0 && p.row_end == 0) p.row_end = v->res_y;
+    if (p.row_begin < 0 || p.row_end > v->res_y || p.row_begin >= p.row_end) {
+        fail(C5_E_INVALID, "render: bad row band");
+    }
+    p.x_min = v->window[1];
+    p.y_min = v->window[3];
+    p.step_x = (v->window[0] - v->window[1]) / (v->res_x - 1.); // plane.cpp:298-302
+    p.step_y = (v->window[2] - v->window[3]) / (v->res_y - 1.);
+    return p;
+}
+
+// Pixel coordinates by repeated addition (plane.cpp:304-314) — not x_min + i * step.
+void ensure_pixel_tables(DeviceState& d, const c5_view* v, const ViewPlan& p) {
+    if (d.xs_res != v->res_x || d.xs_win[0] != v->window[0] || d.xs_win[1] != v->window[1]) {
+        std::vector<double> xs(static_cast<size_t>(v->res_x));
+        double c = p.x_min;
+        for (int i = 0; i < v->res_x; i++) {
+            xs[static_cast<size_t>(i)] = c;
+            c = c + p.step_x;
+        }
+        d.xs.alloc(xs.size());
+        h2d(d.xs.p, xs.data(), d.xs.bytes(), d.stream);
+        stream_sync(d.stream);
+        d.xs_res = v->res_x;
+        d.xs_win[0] = v->window[0];
+        d.xs_win[1] = v->window[1];
+    }
+    if (d.ys_res != v->res_y || d.ys_win[0] != v->window[2] || d.ys_win[1] != v->window[3]) {
+        std::vector<double> ys(static_cast<size_t>(v->res_y));
+        double c = p.y_min;
+        for (int j = 0; j < v->res_y; j++) {
+            ys[static_cast<size_t>(j)] = c;
+            c = c + p.step_y;
+        }
+        d.ys.alloc(ys.size());
+        h2d(d.ys.p, ys.data(), d.ys.bytes(), d.stream);
+        stream_sync(d.stream);
+        d.ys_res = v->res_y;
+        d.ys_win[0] = v->window[2];
+        d.ys_win[1] = v->window[3];
+    }
+}
+
+// Enqueues one view's kernels for rows [row_begin,row_end) on device d. Events:
+// 0 start, 1 rotated, 2 bvh, 3 mask, 4 walk.
+void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want_steps) {
+    use_device(d);
+    g_launch_counter = &d.launches;
+    ensure_pixel_tables(d, v, p);
+    const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
+    const bool solids = v->use_solids && (d.solid_follow.n + d.solid_static.n) > 0;
+    d.out.ensure(2 * n_pix_band);
+    if (want_steps) d.steps.ensure(n_pix_band);
+    d.counters.ensure(kNumCounters);
+    d.row_cost.ensure(static_cast<size_t>(v->res_y));
+    if (solids) d.mask.ensure(static_cast<size_t>(v->res_x) * v->res_y);
+
+    record(d, 0);
+    launch_rotate_vertices(d, p.rot, p.n_rot);
+    if (solids) launch_rotate_solids(d, p.rot, p.n_rot);
+    record(d, 1);
+    launch_bvh_refit(d);
+    record(d, 2);
+    if (solids) {
+        dev_zero(d.mask.p, static_cast<size_t>(v->res_x) * v->res_y, d.stream);
+        launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y);
+    }
+    record(d, 3);
+    dev_zero(d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);
+    dev_zero(d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(unsigned long long), d.stream);
+    WalkLaunch w{};
+    w.res_x = v->res_x;
+    w.res_y = v->res_y;
+    w.row_begin = p.row_begin;
+    w.row_end = p.row_end;
+    w.alpha_limit = v->alpha_limit;
+    w.round_through_float = v->round_through_float;
+    w.use_mask = solids ? 1 : 0;
+    w.write_steps = want_steps ? 1 : 0;
+    w.precision = v->precision ? v->precision : 64;
+    launch_walk(d, w);
+    record(d, 4);
+}
+
+void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan& p, c5_stats* st, int ev_last) {
+    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
+    d2h(c, d.counters.p, sizeof(c), d.stream);
+    ctx->last_row_cost.assign(static_cast<size_t>(v->res_y), 0);
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "row cost width");
+    d2h(ctx->last_row_cost.data(), d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(uint64_t), d.stream);
+    stream_sync(d.stream);
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->pixels = static_cast<uint64_t>(p.row_end - p.row_begin) * static_cast<uint64_t>(v->res_x);
+        st->tet_steps = c[kSteps];
+        st->hit_pixels = c[kHitPixels];
+        st->solid_pixels = c[kSolidPixels];
+        st->walk_errors = c[kWalkErrors];
+        st->ms_rotate = elapsed(d, 0, 1);
+        st->ms_bvh = elapsed(d, 1, 2);
+        st->ms_mask = elapsed(d, 2, 3);
+        st->ms_walk = elapsed(d, 3, 4);
+        st->ms_d2h = ev_last > 4 ? elapsed(d, 4, ev_last) : 0.f;
+        st->ms_total = elapsed(d, 0, ev_last);
+        st->n_devices = 1;
+    }
+    if (c[kWalkErrors]) {
+        fail(C5_E_WALK, "render: " + std::to_string(c[kWalkErrors]) + " ray(s) exceeded the step cap");
+    }
+}
+
+void render_single(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, c5_stats* st) {
+    if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
+    if (!out) fail(C5_E_INVALID, "render: out is NULL");
+    const ViewPlan p = plan_view(v);
+    DeviceState& d = *ctx->dev[0];
+    enqueue_view(d, v, p, steps != nullptr);
+    const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
+    const size_t band_off = static_cast<size_t>(p.row_begin) * v->res_x;
+    d2h(out + 2 * band_off, d.out.p, 2 * n_pix_band * sizeof(double), d.stream);
+    record(d, 5);
+    if (steps) d2h(steps + band_off, d.steps.p, n_pix_band * sizeof(uint32_t), d.stream);
+    if (solid_mask) {
+        const bool solids = v->use_solids && (d.solid_follow.n + d.solid_static.n) > 0;
+        if (solids) {
+            d2h(solid_mask + band_off, d.mask.p + band_off, n_pix_band, d.stream);
+        } else {
+            std::memset(solid_mask + band_off, 0, n_pix_band);
+        }
+    }
+    collect_stats(ctx, d, v, p, st, 5);
+}
+
+void upload_solids(c5_ctx* ctx, const double* pts, int64_t n, int follows) {
+    if (n < 0 || (n > 0 && !pts)) fail(C5_E_INVALID, "upload_solids: bad arguments");
+    if (n == 0) return;
+    for (auto& dp : ctx->dev) {
+        DeviceState& d = *dp;
+        use_device(d);
+        SolidSet& ss = follows ? d.solid_follow : d.solid_static;
+        const size_t old_n = static_cast<size_t>(ss.n), add = static_cast<size_t>(n);
+        DevBuf<double> merged;
+        merged.alloc((old_n + add) * 12);
+        if (old_n) d2d(merged.p, ss.pts0.p, old_n * 12 * sizeof(double), d.stream);
+        h2d(merged.p + old_n * 12, pts, add * 12 * sizeof(double), d.stream);
+        stream_sync(d.stream);
+        ss.pts0 = std::move(merged);
+        ss.n = static_cast<int64_t>(old_n + add);
+        ss.pts_view.alloc(static_cast<size_t>(ss.n) * 12);
+        // static solids are never rotated: their view-frame copy is the upload itself
+        if (!follows) {
+            d2d(ss.pts_view.p, ss.pts0.p, ss.pts0.bytes(), d.stream);
+            stream_sync(d.stream);
+        }
+    }
+    ctx->info.n_solid_tets += n;
+}
+
+} // namespace
+
+extern "C" {
+
+int c5_abi_version(void) {
+    return C5_ABI_VERSION;
+}
+
+void c5_view_from_flags(c5_view* v, int32_t res_x, int32_t res_y, double X_pi, double Y_pi, double I_pi,
+                        double alpha_limit) {
+    if (!v) return;
+    std::memset(v, 0, sizeof(*v));
+    v->res_x = res_x;
+    v->res_y = res_y;
+    v->window[0] = 2.2; // main.cpp:83
+    v->window[1] = -0.2;
+    v->window[2] = 0.9;
+    v->window[3] = -0.9;
+    const double a0 = -I_pi * kPi + kPi / 2.; // main.cpp:96
+    v->n_rot = 3;
+    v->rot[0] = c5_rotation{0, 0, a0, 0.0};                 // main.cpp:105
+    v->rot[1] = c5_rotation{1, 0, Y_pi * kPi, 1.0};         // main.cpp:106, ACC_X0 = 1 (config.hpp:55)
+    v->rot[2] = c5_rotation{0, 0, -a0 + X_pi * kPi, 0.0};   // main.cpp:107
+    v->alpha_limit = alpha_limit;
+    v->precision = 64;
+    v->round_through_float = 1;
+    v->use_solids = 1;
+}
+
+int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
+    if (!out) return C5_E_INVALID;
+    *out = nullptr;
+    c5_ctx* ctx = nullptr;
+    try {
+        if (n_dev < 1 || !devices) fail(C5_E_INVALID, "c5_create: need at least one device");
+        if (n_dev > 1) fail(C5_E_INVALID, "c5_create: multi-device contexts are not available in this build");
+        ctx = new c5_ctx();
+        if (!kHostSim) {
+            int count = 0;
+            cudaError_t e = cudaGetDeviceCount(&count);
+            if (e != cudaSuccess || count == 0) {
+                fail(C5_E_CUDA, std::string("c5_create: no CUDA device (") + cudaGetErrorString(e) +
+                                    "); this library has no CPU path");
+            }
+            for (int k = 0; k < n_dev; k++) {
+                if (devices[k] < 0 || devices[k] >= count) fail(C5_E_INVALID, "c5_create: device ordinal out of range");
+            }
+        }
+        for (int k = 0; k < n_dev; k++) {
+            auto d = std::make_unique<DeviceState>();
+            d->device = devices[k];
+            if (!kHostSim) {
+                C5_CUDA(cudaSetDevice(d->device));
+                C5_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+                for (auto& e : d->ev) C5_CUDA(cudaEventCreate(&e));
+            }
+            ctx->dev.push_back(std::move(d));
+        }
+        *out = ctx;
+        return C5_OK;
+    } catch (const Error& e) {
+        std::lock_guard<std::mutex> lock(g_create_err_mu);
+        g_create_err = e.text;
+        delete ctx;
+        return e.code;
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lock(g_create_err_mu);
+        g_create_err = e.what();
+        delete ctx;
+        return C5_E_NOMEM;
+    }
+}
+
+void c5_destroy(c5_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& dp : ctx->dev) {
+        DeviceState& d = *dp;
+        if (!kHostSim) {
+            cudaSetDevice(d.device);
+            cudaStreamSynchronize(d.stream);
+        }
+        // DevBuf destructors free on the current device
+        dp.reset();
+    }
+    delete ctx;
+}
+
+const char* c5_last_error(const c5_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lock(g_create_err_mu);
+    static thread_local std::string copy;
+    copy = g_create_err;
+    return copy.c_str();
+}
+
+int c5_upload_mesh(c5_ctx* ctx, const double* points_xyz, int64_t n_points, const int32_t* tet_vertices,
+                   int64_t n_tets, const double* alpha, const double* q) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        if (!points_xyz || !tet_vertices || !alpha || !q) fail(C5_E_INVALID, "upload_mesh: NULL array");
+        ctx->has_mesh = false;
+        const size_t before = dev_bytes_in_use();
+        for (auto& dp : ctx->dev) {
+            use_device(*dp);
+            g_launch_counter = &dp->launches;
+            build_mesh(*dp, points_xyz, n_points, tet_vertices, n_tets, alpha, q);
+        }
+        ctx->info.n_points = n_points;
+        ctx->info.n_tets = n_tets;
+        ctx->info.n_boundary_faces = ctx->dev[0]->n_bfaces;
+        ctx->info.n_bvh_nodes = ctx->dev[0]->n_bfaces - 1;
+        ctx->info.device_bytes = static_cast<int64_t>((dev_bytes_in_use() - before) / ctx->dev.size());
+        ctx->has_mesh = true;
+    });
+}
+
+int c5_upload_solids(c5_ctx* ctx, const double* tet_points, int64_t n_tets, int32_t follows_view) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] { upload_solids(ctx, tet_points, n_tets, follows_view); });
+}
+
+int c5_clear_solids(c5_ctx* ctx) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        for (auto& dp : ctx->dev) {
+            use_device(*dp);
+            for (SolidSet* ss : {&dp->solid_follow, &dp->solid_static}) {
+                ss->pts0.release();
+                ss->pts_view.release();
+                ss->n = 0;
+            }
+        }
+        ctx->info.n_solid_tets = 0;
+    });
+}
+
+int c5_mesh_info_get(const c5_ctx* ctx, c5_mesh_info* out) {
+    if (!ctx || !out) return C5_E_INVALID;
+    *out = ctx->info;
+    return C5_OK;
+}
+
+int c5_render(c5_ctx* ctx, const c5_view* view, double* out, c5_stats* stats) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] { render_single(ctx, view, out, nullptr, nullptr, stats); });
+}
+
+int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps, uint8_t* solid_mask,
+                  c5_stats* stats) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] { render_single(ctx, view, out, steps, solid_mask, stats); });
+}
+
+int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream, c5_stats* stats) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
+        if (!d_out) fail(C5_E_INVALID, "render_device: d_out is NULL");
+        if (ctx->dev.size() != 1) fail(C5_E_INVALID, "render_device: single-device contexts only");
+        const ViewPlan p = plan_view(view);
+        DeviceState& d = *ctx->dev[0];
+        // run on the caller's stream so the result is ordered with the caller's later work
+        cudaStream_t own = d.stream;
+        if (!kHostSim && stream) d.stream = static_cast<cudaStream_t>(stream);
+        try {
+            enqueue_view(d, view, p, false);
+            const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * view->res_x;
+            d2d(d_out, d.out.p, 2 * n_pix_band * sizeof(double), d.stream);
+            record(d, 5);
+            collect_stats(ctx, d, view, p, stats, 5);
+        } catch (...) {
+            d.stream = own;
+            throw;
+        }
+        d.stream = own;
+    });
+}
+
+int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows) {
+    if (!ctx || !rows || n_rows < 0) return C5_E_INVALID;
+    for (int32_t j = 0; j < n_rows; j++) {
+        rows[j] = static_cast<size_t>(j) < ctx->last_row_cost.size() ? ctx->last_row_cost[static_cast<size_t>(j)] : 0;
+    }
+    return C5_OK;
+}
+
+uint64_t c5_kernel_launches(const c5_ctx* ctx) {
+    uint64_t n = 0;
+    if (ctx) {
+        for (const auto& d : ctx->dev) n += d->launches;
+    }
+    return n;
+}
+
+} // extern "C"

@@ -1,0 +1,308 @@
+// c5_exact.cu — per-view kernels whose arithmetic must equal the reference's host code bit for
+// bit. This file is compiled with -fmad=false (no FMA contraction), like the reference's plain
+// x86-64 -O3 build (CMakeLists.txt:4-7), so that rotated coordinates and the solid (NaN) mask are
+// identical to the oracle's, not merely close.
+//
+//   rotate_vertices  K1: object3d_base::rotate_around_{x,y}_axis (object3d_base.cpp:202-219 ->
+//                    tetra.cpp:44-62), once per UNIQUE vertex instead of 12 private points per tet.
+//   solid_mask       K5: the solid branch of the face scan conversion (plane.cpp:23-27,57-142,
+//                    line.cpp:246-249): union of the inclusive scanline footprints of the faces
+//                    of solid tets.
+//   bvh_refit        per-view boxes of the boundary-face LBVH (no reference counterpart: it
+//                    replaces the full scan conversion plane.cpp:184-192 as the way a ray finds
+//                    the tets it crosses).
+#include "c5_internal.h"
+
+namespace c5 {
+
+namespace {
+
+struct RotSet {
+    Rot r[kMaxRot];
+    int n;
+};
+
+C5_HD void rotate_point(const RotSet& rs, double& x, double& y, double& z) {
+    for (int k = 0; k < rs.n; k++) {
+        const double c = rs.r[k].c, s = rs.r[k].s;
+        if (rs.r[k].axis == 0) { // tetra.cpp:44-48
+            const double y0 = y;
+            y = y * c - z * s;
+            z = y0 * s + z * c;
+        } else { // tetra.cpp:51-62
+            x -= rs.r[k].x0;
+            const double x1 = x;
+            x = x * c - z * s;
+            z = x1 * s + z * c;
+            x += rs.r[k].x0;
+        }
+    }
+}
+
+C5_HD void rotate_vertex_body(int64_t i, const double* px, const double* py, const double* pz, Vtx* out,
+                              const RotSet& rs) {
+    double x = px[i], y = py[i], z = pz[i];
+    rotate_point(rs, x, y, z);
+    Vtx v;
+    v.x = x;
+    v.y = y;
+    v.z = z;
+    v.w = 0.0;
+    out[i] = v;
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(256)
+rotate_vertices(int64_t n, const double* __restrict__ px, const double* __restrict__ py,
+                const double* __restrict__ pz, Vtx* __restrict__ out, RotSet rs) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) rotate_vertex_body(i, px, py, pz, out, rs);
+}
+
+namespace {
+
+C5_HD void rotate_xyz_body(int64_t i, const double* in, double* out, const RotSet& rs) {
+    double x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+    rotate_point(rs, x, y, z);
+    out[3 * i] = x;
+    out[3 * i + 1] = y;
+    out[3 * i + 2] = z;
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(256)
+rotate_solid_points(int64_t n, const double* __restrict__ in, double* __restrict__ out, RotSet rs) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) rotate_xyz_body(i, in, out, rs);
+}
+
+namespace {
+
+// ---- solid mask --------------------------------------------------------------------------------
+
+struct MaskGrid {
+    int res_x, res_y;
+    double x_min, y_min, step_x, step_y;
+    const double* ys; // accumulated row coordinates (plane.cpp:304-314)
+    uint8_t* mask;
+};
+
+C5_HD double pixel_of_x(const MaskGrid& g, double x) { // plane.cpp:194-202
+    const double r = (x - g.x_min) / g.step_x;
+    const double hi = static_cast<double>(g.res_x) - 1;
+    if (r < 0) return 0;
+    if (r > hi) return hi;
+    return r;
+}
+C5_HD double pixel_of_y(const MaskGrid& g, double y) { // plane.cpp:204-212
+    const double r = (y - g.y_min) / g.step_y;
+    const double hi = static_cast<double>(g.res_y) - 1;
+    if (r < 0) return 0;
+    if (r > hi) return hi;
+    return r;
+}
+C5_HD double edge_x(const double* p1, const double* p2, double y) { // plane.cpp:50-55
+    if (fabs(p1[1] - p2[1]) < DBL_EPSILON) return p1[0];
+    return (p1[0] - p2[0]) * (y - p1[1]) / (p1[1] - p2[1]) + p1[0];
+}
+
+// Inclusive scanline footprint of one projected triangle -> mask bytes (idempotent stores).
+C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const double* c) {
+    const double* p0 = a;
+    const double* p1 = b;
+    const double* p2 = c;
+    const double* t;
+    // y-descending with the tie order of a stable insertion sort (std::sort on 3 items, plane.cpp:61)
+    if (p1[1] > p0[1]) { t = p0; p0 = p1; p1 = t; }
+    if (p2[1] > p0[1]) { t = p2; p2 = p1; p1 = p0; p0 = t; }
+    else if (p2[1] > p1[1]) { t = p1; p1 = p2; p2 = t; }
+
+    // which side of the long edge p0-p2 the middle vertex lies on (plane.cpp:46-48,66-89)
+    const double rel = (p2[1] - p0[1]) * p1[0] + (p0[0] - p2[0]) * p1[1] + (p2[0] * p0[1] - p0[0] * p2[1]);
+    const bool asc_above = (p0[0] >= p2[0]) && (rel >= 0);
+    const bool des_below = (p0[0] < p2[0]) && (rel > 0);
+    const bool long_edge_is_left = !(asc_above || des_below);
+
+    const long long j_hi = static_cast<long long>(floor(pixel_of_y(g, p0[1])));
+    const long long j_lo = static_cast<long long>(ceil(pixel_of_y(g, p2[1])));
+    for (long long j = j_lo; j <= j_hi; j++) {
+        const double y = g.ys[j]; // == ys[j_lo] + (j - j_lo) additions of step_y (plane.cpp:100,138)
+        const double x_long = edge_x(p0, p2, y);
+        const double x_short = (y < p1[1]) ? edge_x(p2, p1, y) : edge_x(p0, p1, y);
+        const double x_lo = long_edge_is_left ? x_long : x_short;
+        const double x_hi = long_edge_is_left ? x_short : x_long;
+        const long long i_hi = static_cast<long long>(floor(pixel_of_x(g, x_hi)));
+        const long long i_lo = static_cast<long long>(ceil(pixel_of_x(g, x_lo)));
+        uint8_t* row = g.mask + static_cast<size_t>(j) * g.res_x;
+        for (long long i = i_lo; i <= i_hi; i++) row[i] = 1;
+    }
+}
+
+// face f of a solid tet: 0 = (v0,v1,v2), 1 = (v0,v1,v3), 2 = (v0,v2,v3), 3 = (v1,v2,v3) (plane.cpp:30-37)
+C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g) {
+    const double* p = pts + 12 * (f >> 2);
+    const int k = static_cast<int>(f & 3);
+    const double* a = p + (k == 3 ? 3 : 0);
+    const double* b = p + (k >= 2 ? 6 : 3);
+    const double* c = p + (k == 0 ? 6 : 9);
+    mark_face(g, a, b, c);
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(128)
+solid_mask(int64_t n_faces, const double* __restrict__ pts, MaskGrid g) {
+    const int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (f < n_faces) solid_face_body(f, pts, g);
+}
+
+namespace {
+
+// ---- BVH refit ---------------------------------------------------------------------------------
+
+C5_HD void store_child_box(BvhNode* nodes, int32_t link, float xlo, float xhi, float ylo, float yhi, float zlo,
+                           float zhi) {
+    BvhNode& n = nodes[link >> 1];
+    const int w = link & 1;
+    n.xlo[w] = xlo;
+    n.xhi[w] = xhi;
+    n.ylo[w] = ylo;
+    n.yhi[w] = yhi;
+    n.zlo[w] = zlo;
+    n.zhi[w] = zhi;
+}
+
+C5_HD float load_f(const float* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p); // L2: the sibling's box was written by another SM
+#else
+    return *p;
+#endif
+}
+
+// One thread per leaf. A boundary face can only be an ENTRY face for rays travelling +z if its
+// outward normal has n_z < 0; the others get an empty box, which prunes them (and every subtree
+// made only of them) from all queries of this view.
+C5_HD void refit_leaf_body(int64_t leaf, const BFace* faces, const Vtx* vrot, BvhNode* nodes,
+                           const int32_t* node_parent, const int32_t* leaf_parent, uint32_t* flags) {
+    const BFace f = faces[leaf];
+    const Vtx a = vrot[f.a], b = vrot[f.b], c = vrot[f.c];
+    const double nz = (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
+    float xlo = INFINITY, xhi = -INFINITY, ylo = INFINITY, yhi = -INFINITY, zlo = INFINITY, zhi = -INFINITY;
+    if (nz < 0) {
+        xlo = f_round_down(fmin(a.x, fmin(b.x, c.x)));
+        xhi = f_round_up(fmax(a.x, fmax(b.x, c.x)));
+        ylo = f_round_down(fmin(a.y, fmin(b.y, c.y)));
+        yhi = f_round_up(fmax(a.y, fmax(b.y, c.y)));
+        zlo = f_round_down(fmin(a.z, fmin(b.z, c.z)));
+        zhi = f_round_up(fmax(a.z, fmax(b.z, c.z)));
+    }
+    int32_t link = leaf_parent[leaf];
+    while (true) {
+        store_child_box(nodes, link, xlo, xhi, ylo, yhi, zlo, zhi);
+        const int32_t node = link >> 1;
+#ifdef __CUDA_ARCH__
+        __threadfence();
+        const uint32_t arrived = atomicAdd(&flags[node], 1u);
+#else
+        const uint32_t arrived = flags[node]++;
+#endif
+        if (arrived == 0) return; // the sibling subtree is not done yet; its last thread continues
+#ifdef __CUDA_ARCH__
+        __threadfence();
+#endif
+        link = node_parent[node];
+        if (link < 0) return; // root
+        const BvhNode& n = nodes[node];
+        xlo = fminf(load_f(&n.xlo[0]), load_f(&n.xlo[1]));
+        xhi = fmaxf(load_f(&n.xhi[0]), load_f(&n.xhi[1]));
+        ylo = fminf(load_f(&n.ylo[0]), load_f(&n.ylo[1]));
+        yhi = fmaxf(load_f(&n.yhi[0]), load_f(&n.yhi[1]));
+        zlo = fminf(load_f(&n.zlo[0]), load_f(&n.zlo[1]));
+        zhi = fmaxf(load_f(&n.zhi[0]), load_f(&n.zhi[1]));
+    }
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(256)
+bvh_refit(int64_t n_leaves, const BFace* __restrict__ faces, const Vtx* __restrict__ vrot, BvhNode* nodes,
+          const int32_t* __restrict__ node_parent, const int32_t* __restrict__ leaf_parent, uint32_t* flags) {
+    const int64_t leaf = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (leaf < n_leaves) refit_leaf_body(leaf, faces, vrot, nodes, node_parent, leaf_parent, flags);
+}
+
+namespace {
+
+RotSet make_rotset(const Rot* rot, int n_rot) {
+    RotSet rs;
+    rs.n = n_rot;
+    for (int k = 0; k < kMaxRot; k++) rs.r[k] = k < n_rot ? rot[k] : Rot{0, 0, 1.0, 0.0, 0.0};
+    return rs;
+}
+
+unsigned grid_for(int64_t n, int block) {
+    return static_cast<unsigned>((n + block - 1) / block);
+}
+
+} // namespace
+
+void launch_rotate_vertices(DeviceState& d, const Rot* rot, int n_rot) {
+    const RotSet rs = make_rotset(rot, n_rot);
+    count_launch();
+    if (kHostSim) {
+        for (int64_t i = 0; i < d.n_pts; i++) rotate_vertex_body(i, d.px.p, d.py.p, d.pz.p, d.vrot.p, rs);
+        return;
+    }
+    rotate_vertices<<<grid_for(d.n_pts, 256), 256, 0, d.stream>>>(d.n_pts, d.px.p, d.py.p, d.pz.p, d.vrot.p, rs);
+    C5_CUDA(cudaGetLastError());
+}
+
+void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot) {
+    SolidSet& ss = d.solid_follow;
+    if (ss.n == 0) return;
+    const RotSet rs = make_rotset(rot, n_rot);
+    const int64_t n = ss.n * 4;
+    count_launch();
+    if (kHostSim) {
+        for (int64_t i = 0; i < n; i++) rotate_xyz_body(i, ss.pts0.p, ss.pts_view.p, rs);
+        return;
+    }
+    rotate_solid_points<<<grid_for(n, 256), 256, 0, d.stream>>>(n, ss.pts0.p, ss.pts_view.p, rs);
+    C5_CUDA(cudaGetLastError());
+}
+
+void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
+                       double step_y) {
+    MaskGrid g{res_x, res_y, x_min, y_min, step_x, step_y, d.ys.p, d.mask.p};
+    for (SolidSet* ss : {&d.solid_follow, &d.solid_static}) {
+        if (ss->n == 0) continue;
+        const int64_t n_faces = ss->n * 4;
+        count_launch();
+        if (kHostSim) {
+            for (int64_t f = 0; f < n_faces; f++) solid_face_body(f, ss->pts_view.p, g);
+            continue;
+        }
+        solid_mask<<<grid_for(n_faces, 128), 128, 0, d.stream>>>(n_faces, ss->pts_view.p, g);
+        C5_CUDA(cudaGetLastError());
+    }
+}
+
+void launch_bvh_refit(DeviceState& d) {
+    dev_zero(d.refit_flags.p, d.refit_flags.bytes(), d.stream);
+    count_launch();
+    if (kHostSim) {
+        for (int64_t i = 0; i < d.n_bfaces; i++) {
+            refit_leaf_body(i, d.bfaces.p, d.vrot.p, d.nodes.p, d.node_parent.p, d.leaf_parent.p, d.refit_flags.p);
+        }
+        return;
+    }
+    bvh_refit<<<grid_for(d.n_bfaces, 256), 256, 0, d.stream>>>(d.n_bfaces, d.bfaces.p, d.vrot.p, d.nodes.p,
+                                                                d.node_parent.p, d.leaf_parent.p,
+                                                                d.refit_flags.p);
+    C5_CUDA(cudaGetLastError());
+}
+
+} // namespace c5

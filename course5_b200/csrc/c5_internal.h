@@ -1,0 +1,95 @@
+// c5_internal.h — context and the entry points shared between the library's translation units.
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/c5gpu.h"
+#include "c5_types.h"
+
+namespace c5 {
+
+constexpr int kMaxRot = C5_MAX_ROT;
+
+// Counters the walk kernel accumulates (one 64-bit atomic per warp).
+enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kNumCounters = 4 };
+
+struct SolidSet {
+    DevBuf<double> pts0;      // [n][4][3] pre-view frame
+    DevBuf<double> pts_view;  // [n][4][3] view frame (rotated copy, or == pts0 content for static ones)
+    int64_t n = 0;
+};
+
+// Everything resident on ONE device.
+struct DeviceState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    // mesh (uploaded once)
+    int64_t n_pts = 0, n_tets = 0, n_bfaces = 0;
+    DevBuf<double> px, py, pz;       // Morton-ordered file-frame coordinates (SoA: the rotate kernel streams them)
+    DevBuf<Cell> cells;
+    DevBuf<BFace> bfaces;            // Morton-sorted boundary faces (BVH leaves)
+    DevBuf<BvhNode> nodes;           // n_bfaces - 1 internal nodes, BFS order (root = 0)
+    DevBuf<int32_t> node_parent;     // per internal node: (parent << 1) | which child, -1 for the root
+    DevBuf<int32_t> leaf_parent;     // per leaf: (parent << 1) | which child
+    DevBuf<uint32_t> refit_flags;    // per internal node arrival counter
+
+    // solids
+    SolidSet solid_follow, solid_static;
+
+    // per view
+    DevBuf<Vtx> vrot;
+    DevBuf<double> xs, ys;
+    int xs_res = 0, ys_res = 0;
+    double xs_win[2] = {0, 0}, ys_win[2] = {0, 0};
+    DevBuf<uint8_t> mask;
+    DevBuf<double> out;              // band output, {tau, I} per pixel
+    DevBuf<uint32_t> steps;
+    DevBuf<unsigned long long> counters;
+    DevBuf<unsigned long long> row_cost;
+
+    uint64_t launches = 0;
+};
+
+struct MeshHost;
+
+} // namespace c5
+
+struct c5_ctx {
+    std::vector<std::unique_ptr<c5::DeviceState>> dev;
+    std::string err;
+    bool has_mesh = false;
+    c5_mesh_info info{};
+    std::vector<uint64_t> last_row_cost;
+    void* nccl = nullptr; // NcclGroup*, multi-device contexts only
+};
+
+namespace c5 {
+
+// c5_topology.cu — builds every mesh-resident array of `d` from host input.
+void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t* tets, int64_t n_tets,
+                const double* alpha, const double* q);
+
+// c5_exact.cu — kernels whose arithmetic must match the reference's host code bit for bit
+// (compiled with -fmad=false).
+void launch_rotate_vertices(DeviceState& d, const Rot* rot, int n_rot);
+void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot);
+void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
+                       double step_y);
+void launch_bvh_refit(DeviceState& d);
+
+// c5_walk.cu
+struct WalkLaunch {
+    int res_x, res_y, row_begin, row_end;
+    double alpha_limit;
+    int round_through_float;
+    int use_mask;
+    int write_steps;
+    int precision;
+};
+void launch_walk(DeviceState& d, const WalkLaunch& w);
+
+} // namespace c5

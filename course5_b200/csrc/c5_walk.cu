@@ -1,0 +1,438 @@
+// c5_walk.cu — K3 + K4: per-pixel ray entry (LBVH over boundary faces) and the tet walk.
+//
+// Replaces, for one view, the reference's
+//   plane::find_intersections   plane.cpp:184-192 (scan-convert every face of every tet, one
+//                               mutex-guarded push per tet-step, line.cpp:29-67,229-232)
+//   line::calculate_intersections / direct_calculate_ray_value / integrate_ray_value_by_i
+//                               line.cpp:84-227 (2 face-plane z's per record, per-pixel sort,
+//                               tau = sum dz*alpha, I recurrence with the alpha clamp)
+//   plane::trace_rays           plane.cpp:144-172 (driver, float cast)
+// by one thread per pixel that (1) finds the lowest boundary face under the pixel whose outward
+// normal points to -z, (2) walks tet to tet through the face-neighbour table in +z order — the
+// order in which the reference integrates I (line.cpp:206: from the record with the lowest z
+// to the highest) — and (3) on leaving the mesh asks the BVH for the next entry above (meshes
+// with cavities or a bumpy silhouette are crossed several times).
+//
+// Geometry of one step. All rays are parallel to z, so "which face does the ray leave through"
+// is a 2-D question about the projected tet. The entry face (a,b,c) is kept counter-clockwise in
+// projection, with coordinates relative to the pixel. With d the fourth vertex and
+//     s_v = orient2(d, v)   (z-component of (d-p) x (v-p)),  v in {a,b,c},
+// the ray leaves through face (d,a,b) iff s_a >= 0 > s_b, through (d,b,c) iff s_b >= 0 > s_c,
+// through (d,c,a) iff s_c >= 0 > s_a. orient2 is exactly antisymmetric (c5_types.h), so two tets
+// sharing an edge agree on the side the ray passes: the walk is watertight without epsilons.
+// The three s values are also the barycentric weights of the pixel in the exit face, so the exit
+// z costs one divide and no further cross products; it is the entry z of the next tet, i.e. each
+// face plane is evaluated once per ray, not twice as in line.cpp:103-122.
+//
+// Per step the thread reads one 64-byte Cell (48 bytes used) and ONE new 32-byte vertex; the
+// other three vertices, their ids and weights stay in registers (the 72 B/step algorithmic
+// figure of SURVEY.md §8d).
+#include "c5_internal.h"
+
+namespace c5 {
+
+namespace {
+
+constexpr int kStack = 64;        // LBVH traversal stack (depth is checked at upload)
+constexpr int kBlock = 128;       // 4 warps: 2 x 2 warp tiles of 8 x 4 pixels
+constexpr int kTileX = 16, kTileY = 8;
+
+struct WalkParams {
+    const Cell* cells;
+    const Vtx* vrot;
+    const BFace* bfaces;
+    const BvhNode* nodes;
+    const double* xs;
+    const double* ys;
+    const uint8_t* mask;  // may be null
+    double* out;          // band buffer: {tau, I} at ((j - row_begin) * res_x + i)
+    uint32_t* steps;      // may be null; same indexing
+    unsigned long long* counters;
+    unsigned long long* row_cost; // [res_y]
+    int res_x, res_y, row_begin, row_end;
+    int n_tiles_x, n_tiles_y, n_macro_x;
+    int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
+    int max_steps;
+    int round_float;
+    double alpha_limit;
+};
+
+// ---- loads through the read-only path ----------------------------------------------------------
+struct CellData {
+    int4 v, nbr;
+    double alpha, q;
+};
+
+C5_HD CellData load_cell(const Cell* cells, int t) {
+    CellData c;
+#ifdef __CUDA_ARCH__
+    const int4* p = reinterpret_cast<const int4*>(cells + t);
+    c.v = __ldg(p);
+    c.nbr = __ldg(p + 1);
+    const double2 aq = __ldg(reinterpret_cast<const double2*>(p + 2));
+    c.alpha = aq.x;
+    c.q = aq.y;
+#else
+    const Cell& s = cells[t];
+    c.v = make_int4(s.v[0], s.v[1], s.v[2], s.v[3]);
+    c.nbr = make_int4(s.nbr[0], s.nbr[1], s.nbr[2], s.nbr[3]);
+    c.alpha = s.alpha;
+    c.q = s.q;
+#endif
+    return c;
+}
+
+C5_HD void load_vtx(const Vtx* vrot, int id, double& x, double& y, double& z) {
+#ifdef __CUDA_ARCH__
+    const double2* p = reinterpret_cast<const double2*>(vrot + id);
+    const double2 xy = __ldg(p);
+    const double2 zw = __ldg(p + 1);
+    x = xy.x;
+    y = xy.y;
+    z = zw.x;
+#else
+    x = vrot[id].x;
+    y = vrot[id].y;
+    z = vrot[id].z;
+#endif
+}
+
+// ---- entry search --------------------------------------------------------------------------------
+
+// Boundary face `leaf` against the pixel: inclusive point-in-triangle test with the same
+// orientation predicate the walk uses, then the barycentric z.
+C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double z_after, int& best,
+                     double& best_z) {
+#ifdef __CUDA_ARCH__
+    const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+#else
+    const BFace& bf = P.bfaces[leaf];
+    const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+#endif
+    double ax, ay, az, bx, by, bz, cx, cy, cz;
+    load_vtx(P.vrot, f.x, ax, ay, az);
+    load_vtx(P.vrot, f.y, bx, by, bz);
+    load_vtx(P.vrot, f.z, cx, cy, cz);
+    ax -= px; ay -= py;
+    bx -= px; by -= py;
+    cx -= px; cy -= py;
+    const double o_ab = orient2(ax, ay, bx, by);
+    const double o_bc = orient2(bx, by, cx, cy);
+    const double o_ca = orient2(cx, cy, ax, ay);
+    // outward normal towards -z  <=>  clockwise in projection  <=>  all three <= 0 inside
+    if (o_ab <= 0 && o_bc <= 0 && o_ca <= 0) {
+        const double sum = o_ab + o_bc + o_ca;
+        if (sum < 0) {
+            const double z = (o_bc * az + o_ca * bz + o_ab * cz) / sum;
+            if (z > z_after && z < best_z) {
+                best_z = z;
+                best = leaf;
+            }
+        }
+    }
+}
+
+// Lowest entry face strictly above z_after under pixel (px, py), or -1.
+C5_HD int bvh_next_entry(const WalkParams& P, const BvhNode* top, double px, double py, double z_after,
+                         double& z_out) {
+    int stack[kStack];
+    int sp = 0;
+    int best = -1;
+    double best_z = INFINITY;
+    int node = 0;
+    const float fx_lo = f_round_down(px), fx_hi = f_round_up(px);
+    const float fy_lo = f_round_down(py), fy_hi = f_round_up(py);
+    while (true) {
+        const BvhNode* n = (node < P.top_nodes) ? (top + node) : (P.nodes + node);
+#ifdef __CUDA_ARCH__
+        const float4 bx = *reinterpret_cast<const float4*>(n->xlo); // xlo0 xlo1 xhi0 xhi1
+        const float4 by = *reinterpret_cast<const float4*>(n->ylo);
+        const float4 bz = *reinterpret_cast<const float4*>(n->zlo);
+        const int2 ch = *reinterpret_cast<const int2*>(n->child);
+#else
+        const float4 bx = make_float4(n->xlo[0], n->xlo[1], n->xhi[0], n->xhi[1]);
+        const float4 by = make_float4(n->ylo[0], n->ylo[1], n->yhi[0], n->yhi[1]);
+        const float4 bz = make_float4(n->zlo[0], n->zlo[1], n->zhi[0], n->zhi[1]);
+        const int2 ch = make_int2(n->child[0], n->child[1]);
+#endif
+        // boxes are rounded outward and the pixel is widened to floats, so this never misses
+        bool h0 = fx_hi >= bx.x && fx_lo <= bx.z && fy_hi >= by.x && fy_lo <= by.z &&
+                  static_cast<double>(bz.z) > z_after && static_cast<double>(bz.x) < best_z;
+        bool h1 = fx_hi >= bx.y && fx_lo <= bx.w && fy_hi >= by.y && fy_lo <= by.w &&
+                  static_cast<double>(bz.w) > z_after && static_cast<double>(bz.y) < best_z;
+        if (h0 && ch.x < 0) {
+            test_leaf(P, ~ch.x, px, py, z_after, best, best_z);
+            h0 = false;
+        }
+        if (h1 && ch.y < 0) {
+            if (static_cast<double>(bz.y) < best_z) test_leaf(P, ~ch.y, px, py, z_after, best, best_z);
+            h1 = false;
+        }
+        if (h0 && h1) {
+            const bool first0 = bz.x <= bz.y; // descend into the lower subtree first
+            if (sp < kStack) stack[sp++] = first0 ? ch.y : ch.x;
+            node = first0 ? ch.x : ch.y;
+        } else if (h0) {
+            node = ch.x;
+        } else if (h1) {
+            node = ch.y;
+        } else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    z_out = best_z;
+    return best;
+}
+
+// ---- one ray ---------------------------------------------------------------------------------------
+
+struct RayResult {
+    double tau, inten;
+    uint32_t steps;
+    uint32_t error;
+};
+
+C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py) {
+    RayResult r;
+    r.tau = 0.0;
+    r.inten = 0.0;
+    r.steps = 0;
+    r.error = 0;
+    double z_after = -INFINITY;
+    int entries = 0;
+
+    while (true) {
+        double z_cur;
+        const int leaf = bvh_next_entry(P, top, px, py, z_after, z_cur);
+        if (leaf < 0) break;
+        if (++entries > 4096) {
+            r.error = 1;
+            break;
+        }
+#ifdef __CUDA_ARCH__
+        const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+#else
+        const BFace& bf = P.bfaces[leaf];
+        const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+#endif
+        // entry face (a, c, b) of the stored winding is counter-clockwise in projection
+        int ia = f.x, ib = f.z, ic = f.y;
+        double ax, ay, az, bx, by, bz, cx, cy, cz;
+        load_vtx(P.vrot, ia, ax, ay, az);
+        load_vtx(P.vrot, ib, bx, by, bz);
+        load_vtx(P.vrot, ic, cx, cy, cz);
+        ax -= px; ay -= py;
+        bx -= px; by -= py;
+        cx -= px; cy -= py;
+        // weight of a vertex = orient2 of the other two, in cyclic order: all >= 0 inside
+        double wa = orient2(bx, by, cx, cy);
+        double wb = orient2(cx, cy, ax, ay);
+        double wc = orient2(ax, ay, bx, by);
+        int t = f.w;
+
+        while (t >= 0) {
+            if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
+                r.error = 1;
+                break;
+            }
+            const CellData c = load_cell(P.cells, t);
+            const int id = c.v.x ^ c.v.y ^ c.v.z ^ c.v.w ^ ia ^ ib ^ ic; // the vertex not on the entry face
+            double dx, dy, dz;
+            load_vtx(P.vrot, id, dx, dy, dz);
+            dx -= px;
+            dy -= py;
+            const double sa = orient2(dx, dy, ax, ay);
+            const double sb = orient2(dx, dy, bx, by);
+            const double sc = orient2(dx, dy, cx, cy);
+
+            int dropped;
+            if (sa >= 0 && sb < 0) { // leaves through (d, a, b): c is replaced by d
+                dropped = ic;
+                ic = id; cx = dx; cy = dy; cz = dz;
+                wa = -sb;
+                wb = sa;
+            } else if (sb >= 0 && sc < 0) { // through (d, b, c): a is replaced
+                dropped = ia;
+                ia = id; ax = dx; ay = dy; az = dz;
+                wb = -sc;
+                wc = sb;
+            } else { // through (d, c, a): b is replaced
+                dropped = ib;
+                ib = id; bx = dx; by = dy; bz = dz;
+                wc = -sa;
+                wa = sc;
+            }
+            const double wsum = wa + wb + wc;
+            const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
+            const double dzv = fabs(z_exit - z_cur);
+
+            // tau: line.cpp:176-193 (alpha not clamped)
+            r.tau += dzv * c.alpha;
+            // I: line.cpp:206-225
+            double a_c = c.alpha;
+            if (a_c > P.alpha_limit) a_c = P.alpha_limit;
+            if (!(a_c < DBL_EPSILON)) {
+                const double C = c.q - a_c * r.inten;
+                r.inten = (c.q - C * exp(-a_c * dzv)) / a_c;
+            }
+            r.steps++;
+            z_cur = z_exit;
+
+            t = (c.v.x == dropped) ? c.nbr.x : (c.v.y == dropped) ? c.nbr.y : (c.v.z == dropped) ? c.nbr.z : c.nbr.w;
+        }
+        if (r.error) break;
+        z_after = z_cur;
+    }
+    return r;
+}
+
+C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double inten, uint32_t steps) {
+    const size_t o = static_cast<size_t>(j - P.row_begin) * P.res_x + i;
+    if (P.round_float) { // plane.cpp:165-166 then object2d.cpp:19-20
+        tau = static_cast<double>(static_cast<float>(tau));
+        inten = static_cast<double>(static_cast<float>(inten));
+    }
+#ifdef __CUDA_ARCH__
+    reinterpret_cast<double2*>(P.out)[o] = make_double2(tau, inten);
+#else
+    P.out[2 * o] = tau;
+    P.out[2 * o + 1] = inten;
+#endif
+    if (P.steps) P.steps[o] = steps;
+}
+
+// ---- kernel ----------------------------------------------------------------------------------------
+
+// 3-bit Morton decode: bits 0,2,4 -> x, bits 1,3,5 -> y
+__device__ __forceinline__ int compact3(int v) {
+    return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4);
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(kBlock)
+tet_walk_fp64(const WalkParams P) {
+    extern __shared__ __align__(64) unsigned char smem_raw[];
+    BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
+
+    // screen-space order: macro tiles of 8 x 8 block tiles in row-major order, Morton inside, so that
+    // concurrently resident blocks cover a compact patch of the image and share tets in L2
+    const int b = blockIdx.x;
+    const int macro = b >> 6, r = b & 63;
+    const int tile_x = (macro % P.n_macro_x) * 8 + compact3(r);
+    const int tile_y = (macro / P.n_macro_x) * 8 + compact3(r >> 1);
+    if (tile_x >= P.n_tiles_x || tile_y >= P.n_tiles_y) return;
+
+    {
+        const int4* src = reinterpret_cast<const int4*>(P.nodes);
+        int4* dst = reinterpret_cast<int4*>(top);
+        for (int k = threadIdx.x; k < P.top_nodes * 4; k += kBlock) dst[k] = src[k];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = tile_x * kTileX + (warp & 1) * 8 + (lane & 7);
+    const int j = P.row_begin + tile_y * kTileY + (warp >> 1) * 4 + (lane >> 3);
+    const bool live = i < P.res_x && j < P.row_end;
+
+    RayResult res;
+    res.tau = 0.0;
+    res.inten = 0.0;
+    res.steps = 0;
+    res.error = 0;
+    bool solid = false;
+    if (live) {
+        solid = P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i];
+        if (solid) {
+            const double nan = __longlong_as_double(0x7FF8000000000000ll); // quiet NaN (config.hpp:26-27)
+            store_pixel(P, i, j, nan, nan, 0);
+        } else {
+            res = trace_ray(P, top, P.xs[i], P.ys[j]);
+            store_pixel(P, i, j, res.tau, res.inten, res.steps);
+        }
+    }
+
+    // statistics: one atomic per warp per counter, one per warp-row for the row costs
+    const unsigned full = 0xFFFFFFFFu;
+    unsigned row_steps = res.steps;
+    row_steps += __shfl_xor_sync(full, row_steps, 1);
+    row_steps += __shfl_xor_sync(full, row_steps, 2);
+    row_steps += __shfl_xor_sync(full, row_steps, 4);
+    if ((lane & 7) == 0 && live && row_steps) atomicAdd(&P.row_cost[j], static_cast<unsigned long long>(row_steps));
+    unsigned warp_steps = row_steps;
+    warp_steps += __shfl_xor_sync(full, warp_steps, 8);
+    warp_steps += __shfl_xor_sync(full, warp_steps, 16);
+    const unsigned hits = __popc(__ballot_sync(full, live && res.steps > 0));
+    const unsigned solids = __popc(__ballot_sync(full, solid));
+    const unsigned errors = __popc(__ballot_sync(full, res.error != 0));
+    if (lane == 0) {
+        if (warp_steps) atomicAdd(&P.counters[kSteps], static_cast<unsigned long long>(warp_steps));
+        if (hits) atomicAdd(&P.counters[kHitPixels], static_cast<unsigned long long>(hits));
+        if (solids) atomicAdd(&P.counters[kSolidPixels], static_cast<unsigned long long>(solids));
+        if (errors) atomicAdd(&P.counters[kWalkErrors], static_cast<unsigned long long>(errors));
+    }
+}
+
+namespace {
+
+void walk_on_host(const WalkParams& P) {
+    for (int j = P.row_begin; j < P.row_end; j++) {
+        for (int i = 0; i < P.res_x; i++) {
+            if (P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i]) {
+                store_pixel(P, i, j, NAN, NAN, 0);
+                P.counters[kSolidPixels]++;
+                continue;
+            }
+            const RayResult r = trace_ray(P, nullptr, P.xs[i], P.ys[j]);
+            store_pixel(P, i, j, r.tau, r.inten, r.steps);
+            P.counters[kSteps] += r.steps;
+            P.row_cost[j] += r.steps;
+            if (r.steps) P.counters[kHitPixels]++;
+            if (r.error) P.counters[kWalkErrors]++;
+        }
+    }
+}
+
+} // namespace
+
+void launch_walk(DeviceState& d, const WalkLaunch& w) {
+    if (w.precision != 64) fail(C5_E_INVALID, "render: only precision = 64 is available");
+    WalkParams P{};
+    P.cells = d.cells.p;
+    P.vrot = d.vrot.p;
+    P.bfaces = d.bfaces.p;
+    P.nodes = d.nodes.p;
+    P.xs = d.xs.p;
+    P.ys = d.ys.p;
+    P.mask = w.use_mask ? d.mask.p : nullptr;
+    P.out = d.out.p;
+    P.steps = w.write_steps ? d.steps.p : nullptr;
+    P.counters = d.counters.p;
+    P.row_cost = d.row_cost.p;
+    P.res_x = w.res_x;
+    P.res_y = w.res_y;
+    P.row_begin = w.row_begin;
+    P.row_end = w.row_end;
+    P.n_tiles_x = (w.res_x + kTileX - 1) / kTileX;
+    P.n_tiles_y = (w.row_end - w.row_begin + kTileY - 1) / kTileY;
+    P.n_macro_x = (P.n_tiles_x + 7) / 8;
+    const int n_macro_y = (P.n_tiles_y + 7) / 8;
+    const int64_t n_nodes = d.n_bfaces - 1;
+    P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < 255 ? n_nodes : 255);
+    P.max_steps = static_cast<int>(d.n_tets < (1 << 20) ? d.n_tets : (1 << 20));
+    P.round_float = w.round_through_float;
+    P.alpha_limit = w.alpha_limit;
+
+    count_launch();
+    if (kHostSim) {
+        walk_on_host(P);
+        return;
+    }
+    const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
+    const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
+    tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
+    C5_CUDA(cudaGetLastError());
+}
+
+} // namespace c5

@@ -1,0 +1,154 @@
+/* c5gpu.h — C ABI of the B200 ray pass that replaces course5's OpenMP loops.
+ *
+ * The reference has no plugin/FFI API; its hot path is reached by three C++ calls in one
+ * place (/root/reference/project/src/main.cpp:127-129):
+ *
+ *     plane base_plane{res_x, res_y, {acc_disk, roche_lobe, acc_sphere}, domain};   // :127
+ *     base_plane.find_intersections();                                              // :128
+ *     object2d result = base_plane.trace_rays(tetra_value::alpha, tetra_value::Q);  // :129
+ *
+ * preceded by three rotations per object (main.cpp:104-107,112-114) that the reference
+ * charges to its load timer. This header is what a binding for that path links against:
+ * plain pointers and sizes, no C++ or torch types, no exceptions. Every call returns C5_OK
+ * or a negative C5_E_* code; c5_last_error() gives the text. A context is thread-compatible
+ * (one thread at a time), not thread-safe.
+ *
+ * The library is CUDA-only (sm_100a). There is no CPU path: without a usable device
+ * c5_create() fails with C5_E_CUDA.
+ */
+#ifndef C5GPU_H
+#define C5GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C5_ABI_VERSION 1
+#define C5_MAX_ROT 8
+
+typedef struct c5_ctx c5_ctx;
+
+enum c5_status {
+    C5_OK = 0,
+    C5_E_INVALID = -1,  /* bad argument */
+    C5_E_CUDA = -2,     /* CUDA runtime error / no device */
+    C5_E_NOMEM = -3,
+    C5_E_TOPOLOGY = -4, /* mesh is not a conforming manifold partition (a face shared by >2 tets) */
+    C5_E_STATE = -5,    /* call order (render before upload_mesh, ...) */
+    C5_E_WALK = -6,     /* a ray exceeded the step cap (reported in c5_stats.walk_errors too) */
+    C5_E_NCCL = -7
+};
+
+/* One rigid rotation, the unit of object3d_base::rotate_around_{x,y}_axis
+ * (object3d_base.cpp:202-219 -> tetra.cpp:44-62). axis 0: about the x axis through the origin;
+ * axis 1: about the axis parallel to y through (x0, 0, 0). angle in radians. */
+typedef struct c5_rotation {
+    int32_t axis;
+    int32_t reserved;
+    double angle;
+    double x0;
+} c5_rotation;
+
+/* One view. Replaces the implicit inputs of the reference's ray pass: the plane constructor
+ * arguments (plane.hpp:19), the window literal (main.cpp:83), the rotations applied to the
+ * geometry beforehand (main.cpp:96,104-107) and app::instance().config.limit_alpha_value read
+ * inside the loop (line.cpp:204). */
+typedef struct c5_view {
+    int32_t res_x, res_y;       /* plane(res_x, res_y, ...) */
+    double window[4];           /* x_max, x_min, y_max, y_min */
+    int32_t n_rot;              /* rotations applied in order to the grid and to view-following solids */
+    int32_t reserved0;
+    c5_rotation rot[C5_MAX_ROT];
+    double alpha_limit;         /* --alpha_limit */
+    int32_t precision;          /* 64 (default) or 32 */
+    int32_t round_through_float;/* 1: (double)(float)v like plane.cpp:165-166 + object2d.cpp:19-20 */
+    int32_t use_solids;         /* 1: pixels under uploaded solid tets become NaN (line.cpp:246-249) */
+    int32_t row_begin, row_end; /* row band [row_begin, row_end); 0,0 = all rows */
+    int32_t reserved1;
+} c5_view;
+
+/* Fills *v the way main.cpp:83-107 sets a view up from the CLI flags (angles in units of pi):
+ * window {2.2,-0.2,0.9,-0.9}; rotations Rx(a0), Ry(Y*pi) about x0 = 1, Rx(-a0 + X*pi),
+ * a0 = -I*pi + pi/2; precision 64; round_through_float 1; use_solids 1; all rows. */
+void c5_view_from_flags(c5_view* v, int32_t res_x, int32_t res_y, double X_pi, double Y_pi, double I_pi,
+                        double alpha_limit);
+
+typedef struct c5_stats {
+    uint64_t pixels;        /* pixels of the rendered band(s) */
+    uint64_t tet_steps;     /* sum over pixels of tets crossed == plane::count_all_intersections (plane.cpp:3-12) */
+    uint64_t hit_pixels;    /* pixels crossing >= 1 tet */
+    uint64_t solid_pixels;  /* pixels under the solid mask */
+    uint64_t walk_errors;   /* rays stopped by the step cap (0 on a valid mesh) */
+    float ms_rotate;        /* device time per phase (CUDA events), max over devices */
+    float ms_bvh;
+    float ms_mask;
+    float ms_walk;
+    float ms_gather;        /* NCCL band gather (multi-device contexts) */
+    float ms_d2h;
+    float ms_total;         /* whole call on the device timeline */
+    int32_t n_devices;
+    int32_t reserved;
+} c5_stats;
+
+typedef struct c5_mesh_info {
+    int64_t n_points, n_tets, n_boundary_faces, n_bvh_nodes, n_solid_tets;
+    int64_t device_bytes;   /* per device */
+} c5_mesh_info;
+
+/* devices: CUDA ordinals, n_dev >= 1. With n_dev > 1 the mesh is replicated, each device
+ * renders a contiguous band of rows and one NCCL gather assembles the image on devices[0]. */
+int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out);
+void c5_destroy(c5_ctx* ctx);
+const char* c5_last_error(const c5_ctx* ctx); /* ctx may be NULL: text of the last failed c5_create */
+int c5_abi_version(void);
+
+/* Replaces object3d_base::read_vtk_file's output (object3d_base.cpp:13-52: an AoS of private
+ * per-tet point copies) by shared points + connectivity, which are flattened once into
+ * device-resident arrays: Morton-reordered vertices and tets, a face-neighbour table, the
+ * boundary-face list and an LBVH hierarchy over it. Caller keeps ownership of the host arrays;
+ * the call blocks. alpha = "AbsorpCoef", q = "radEnLooseRate" (object3d_accretion_disk.cpp:4). */
+int c5_upload_mesh(c5_ctx* ctx, const double* points_xyz, int64_t n_points, const int32_t* tet_vertices,
+                   int64_t n_tets, const double* alpha, const double* q);
+
+/* Solid tets (the reference's Roche lobe and sphere, tetra_type::solid): [n][4][3] doubles in the
+ * frame BEFORE the view rotations. follows_view = 1 for objects main.cpp rotates with the view
+ * (the Roche lobe, main.cpp:112-114), 0 for those it does not (the sphere, main.cpp:116). Calls
+ * append; c5_clear_solids() empties the set. */
+int c5_upload_solids(c5_ctx* ctx, const double* tet_points, int64_t n_tets, int32_t follows_view);
+int c5_clear_solids(c5_ctx* ctx);
+
+int c5_mesh_info_get(const c5_ctx* ctx, c5_mesh_info* out);
+
+/* plane ctor + find_intersections + trace_rays for one view (main.cpp:127-129), including the
+ * rotations main.cpp:104-107 does beforehand. out: caller-owned HOST buffer of
+ * res_y * res_x * 2 doubles, x fastest, {tau, I} per pixel — the vtkImageData layout of
+ * object2d.cpp:17-21 (with a row band: only rows [row_begin,row_end) are written, at their
+ * final position). stats may be NULL. */
+int c5_render(c5_ctx* ctx, const c5_view* view, double* out, c5_stats* stats);
+
+/* Test/diagnostic variant: same pass, but also returns per-pixel tets crossed and the solid
+ * mask (each res_y * res_x, x fastest; either may be NULL). With view->round_through_float = 0
+ * the doubles are the pre-cast values the parity gate is defined on. */
+int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps, uint8_t* solid_mask,
+                  c5_stats* stats);
+
+/* Device-resident variant for callers that own device memory (e.g. a torch tensor that an NCCL
+ * gather will read): d_out is a DEVICE pointer on the context's first device to
+ * (row_end - row_begin) * res_x * 2 doubles — the band only. Work is enqueued on `stream`
+ * (a cudaStream_t, may be NULL for the default stream) and the call returns after the stream
+ * has been synchronised, so stats are final. Single-device contexts only. */
+int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream, c5_stats* stats);
+
+/* Per-row tet-step totals of the last render on this context (res_y entries; rows outside the
+ * rendered band are 0). Callers use it to cut cost-balanced row bands for the next view. */
+int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows);
+
+/* Number of kernels this library has launched on behalf of ctx since creation. */
+uint64_t c5_kernel_launches(const c5_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C5GPU_H */

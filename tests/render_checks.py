@@ -1,0 +1,162 @@
+"""Checks of the C-ABI render path against the oracle, written once and run twice:
+  * tests/test_hostsim.py  — the device functions compiled for the host (CPU container, logic only)
+  * tests/test_gpu_parity.py (-m gpu) — the CUDA library on a B200: the parity tests proper.
+Every function takes the loaded library (a ctypes CDLL typed by course5_b200.api)."""
+import numpy as np
+import pytest
+
+from cases import golden_case, reference_solids, view_kwargs
+from course5_b200 import api, synth
+from parity import assert_image_parity, assert_same_hits
+
+
+def render_raw(lib, mesh, res_x, res_y, *, solids=None, raw=True, **flags):
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        if solids is not None:
+            ctx.upload_solids(solids[0], True)
+            ctx.upload_solids(solids[1], False)
+        view = api.make_view(res_x, res_y, lib=lib, round_through_float=0 if raw else 1, **flags)
+        return ctx.render_raw(view)
+
+
+def check_golden(lib, name):
+    mesh, meta, gold = golden_case(name)
+    solids = None
+    if meta["solids"]:
+        solids = reference_solids(meta["flags"]["D"])
+        if solids is None:
+            pytest.skip("solids need oracle/_ref")
+    img = render_raw(lib, mesh, meta["res_x"], meta["res_y"], solids=solids, **view_kwargs(meta))
+    assert np.array_equal(img.solid, gold["solid"]), "solid (NaN) mask differs"
+    assert_same_hits(img.steps, gold["steps"], what=name + ": ")
+    assert_image_parity(img.tau, img.inten, gold["tau"], gold["inten"], what=name + ": ")
+    assert img.stats["tet_steps"] == meta["total_steps"]
+    assert np.array_equal(img.steps, gold["steps"])
+    assert img.stats["walk_errors"] == 0
+    assert img.stats["solid_pixels"] == int(gold["solid"].sum())
+    assert img.stats["hit_pixels"] == int((gold["steps"] > 0).sum())
+
+
+def check_against_port(lib, port, mesh, res_x, res_y, flags, *, solids=None, steps_exact=True):
+    img = render_raw(lib, mesh, res_x, res_y, solids=solids, **flags)
+    want = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=res_x, res_y=res_y,
+                       solid_rot=None if solids is None else solids[0],
+                       solid_static=None if solids is None else solids[1], **flags)
+    assert want.anomalies == 0
+    assert np.array_equal(img.solid, want.solid)
+    assert_same_hits(img.steps, want.steps)
+    assert_image_parity(img.tau, img.inten, want.tau, want.inten)
+    if steps_exact:
+        assert np.array_equal(img.steps, want.steps)
+    assert img.stats["tet_steps"] == want.total_steps
+    return img, want
+
+
+def check_row_bands_equal_full_image(lib):
+    mesh = synth.kuhn_cube(7, seed=31)
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        full_view = api.make_view(150, 110, X=0.4, Y=0.9, lib=lib, round_through_float=0)
+        full, st_full = ctx.render(full_view)
+        cost = ctx.last_row_cost(110)
+        assert int(cost.sum()) == st_full["tet_steps"]
+        bands = api.balanced_bands(cost, 3, base_cost=1.0)
+        out = np.full_like(full, -1.0)
+        steps = 0
+        for lo, hi in bands:
+            v = api.make_view(150, 110, X=0.4, Y=0.9, lib=lib, round_through_float=0, row_begin=lo, row_end=hi)
+            _, st = ctx.render(v, out=out)
+            steps += st["tet_steps"]
+            assert st["pixels"] == (hi - lo) * 150
+        assert np.array_equal(out, full)          # bit-identical, bands are independent
+        assert steps == st_full["tet_steps"]
+
+
+def check_round_through_float(lib):
+    mesh = synth.kuhn_cube(6, seed=32)
+    raw = render_raw(lib, mesh, 100, 80, X=0.45, Y=0.3, raw=True)
+    cast = render_raw(lib, mesh, 100, 80, X=0.45, Y=0.3, raw=False)
+    assert np.array_equal(cast.image, raw.image.astype(np.float32).astype(np.float64))
+
+
+def check_out_of_window_geometry_is_background(lib):
+    """The reference aborts on geometry outside the window (README known problem 2); the B200 path
+    must stay finite: pixels that see the mesh get values, the rest background."""
+    mesh = synth.kuhn_cube(5, seed=33, centre=(2.1, 0.8, 0.0))     # pokes out of the top-right corner
+    img = render_raw(lib, mesh, 120, 90, X=0.0, Y=0.0)
+    assert np.isfinite(img.image).all()
+    assert img.hit.sum() > 0 and (~img.hit).sum() > 0
+    assert np.all(img.image[~img.hit] == 0.0)
+    far = synth.kuhn_cube(3, seed=34, centre=(10.0, 10.0, 0.0))    # entirely outside
+    img = render_raw(lib, far, 64, 48)
+    assert img.hit.sum() == 0 and np.all(img.image == 0.0)
+
+
+def check_topology_errors(lib):
+    mesh = synth.kuhn_cube(3, seed=35)
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        dup = np.concatenate([mesh.tets, mesh.tets[40:41]])            # an interior tet twice
+        with pytest.raises(api.C5Error) as e:
+            ctx.upload_mesh(mesh.points, dup, np.append(mesh.alpha, 1.0), np.append(mesh.q, 1.0))
+        assert e.value.code == api.E_TOPOLOGY
+        bad = mesh.tets.copy()
+        bad[5, 2] = mesh.n_points + 7                                  # out-of-range vertex id
+        with pytest.raises(api.C5Error) as e:
+            ctx.upload_mesh(mesh.points, bad, mesh.alpha, mesh.q)
+        assert e.value.code == api.E_INVALID
+        v = api.make_view(32, 24, lib=lib)
+        with pytest.raises(api.C5Error) as e:
+            ctx.render(v)                                              # nothing valid uploaded
+        assert e.value.code == api.E_STATE
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)    # the context recovers
+        img, st = ctx.render(v)
+        assert st["tet_steps"] > 0
+        with pytest.raises(api.C5Error):
+            ctx.render(api.make_view(1, 24, lib=lib))                  # res = 1 -> step = inf in the reference
+
+
+def check_single_tet_and_tiny_meshes(lib, port):
+    pts = np.array([[0.8, -0.2, 0.0], [1.3, -0.1, 0.1], [1.0, 0.35, -0.05], [1.05, 0.0, 0.6]])
+    tets = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    mesh = synth.TetMesh(pts, tets, np.array([1.25]), np.array([0.5]))
+    check_against_port(lib, port, mesh, 90, 70, dict(X=0.1, Y=0.2))
+    two = synth.TetMesh(np.vstack([pts, [[1.1, 0.05, -0.7]]]), np.array([[0, 1, 2, 3], [0, 2, 1, 4]], dtype=np.int32),
+                        np.array([1.25, 3.5]), np.array([0.5, 0.1]))
+    check_against_port(lib, port, two, 90, 70, dict(X=0.3, Y=1.4, alpha_limit=2.0))
+
+
+def check_uniform_medium_kat(lib, n=6, res=(96, 72)):
+    mesh = synth.kuhn_cube(n, seed=8, scalars="const")
+    for limit in (2.5, 0.9):
+        img = render_raw(lib, mesh, res[0], res[1], X=0.35, Y=0.8, alpha_limit=limit)
+        hit = img.hit
+        a_hat = min(1.5, limit)
+        want = 0.75 / a_hat * (1.0 - np.exp(-a_hat * img.tau[hit] / 1.5))
+        assert np.allclose(img.inten[hit], want, rtol=1e-11, atol=1e-14)
+
+
+def check_scaling_properties(lib, mesh, res_x, res_y, flags):
+    """Size-independent properties: tau is linear in alpha and I is linear in Q, and scaling by a
+    power of two is exact in binary floating point, so both hold BIT FOR BIT."""
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        view = api.make_view(res_x, res_y, lib=lib, round_through_float=0, **flags)
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        base = ctx.render_raw(view)
+        again = ctx.render_raw(view)
+        assert np.array_equal(base.image, again.image), "render is not deterministic"
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, 4.0 * mesh.q)
+        q4 = ctx.render_raw(view)
+        assert np.array_equal(q4.inten, 4.0 * base.inten)
+        assert np.array_equal(q4.tau, base.tau)
+        ctx.upload_mesh(mesh.points, mesh.tets, 0.5 * mesh.alpha, mesh.q)
+        view_half = api.make_view(res_x, res_y, lib=lib, round_through_float=0,
+                                  **dict(flags, alpha_limit=1e30))
+        view_full = api.make_view(res_x, res_y, lib=lib, round_through_float=0,
+                                  **dict(flags, alpha_limit=1e30))
+        a_half = ctx.render_raw(view_half)
+        assert np.array_equal(a_half.tau, 0.5 * base.tau)
+        assert np.array_equal(a_half.steps, base.steps)
+        assert int(ctx.last_row_cost(res_y).sum()) == a_half.stats["tet_steps"]
+        del view_full
+    return base

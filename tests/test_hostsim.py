@@ -1,0 +1,61 @@
+"""Logic of the device functions on CPU: tests/hostsim/libc5hostsim.so is the product's own
+translation units compiled with -DC5_HOSTSIM (kernel bodies as host loops). It is never loaded by
+the package and is not a fallback; it lets the container without a GPU check the walk, the BVH,
+the topology build and the C ABI plumbing against the oracle. The parity tests proper are the
+`-m gpu` ones in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import render_checks as rc
+from cases import GOLDEN_CASES
+from course5_b200 import synth
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden(hostsim_lib, name):
+    rc.check_golden(hostsim_lib, name)
+
+
+@pytest.mark.parametrize("flags", [dict(X=0.0, Y=0.0), dict(X=0.4, Y=0.7, I=-0.03, alpha_limit=1.2),
+                                   dict(X=0.5, Y=1.9, I=0.3)])
+def test_against_port(hostsim_lib, port, flags):
+    rc.check_against_port(hostsim_lib, port, synth.kuhn_cube(10, seed=41), 200, 150, flags)
+
+
+def test_cavity_reentry(hostsim_lib, port):
+    mesh = synth.kuhn_cube(12, seed=42, scalars="sphere", carve_sphere=True)
+    img, want = rc.check_against_port(hostsim_lib, port, mesh, 160, 120, dict(X=0.2, Y=0.3))
+    assert want.steps.max() > 0
+
+
+def test_graded_mesh(hostsim_lib, port):
+    rc.check_against_port(hostsim_lib, port, synth.kuhn_cube(9, seed=43, grade_beta=1.5), 160, 120,
+                          dict(X=0.45, Y=1.2))
+
+
+def test_row_bands(hostsim_lib):
+    rc.check_row_bands_equal_full_image(hostsim_lib)
+
+
+def test_round_through_float(hostsim_lib):
+    rc.check_round_through_float(hostsim_lib)
+
+
+def test_out_of_window(hostsim_lib):
+    rc.check_out_of_window_geometry_is_background(hostsim_lib)
+
+
+def test_topology_errors(hostsim_lib):
+    rc.check_topology_errors(hostsim_lib)
+
+
+def test_tiny_meshes(hostsim_lib, port):
+    rc.check_single_tet_and_tiny_meshes(hostsim_lib, port)
+
+
+def test_uniform_medium(hostsim_lib):
+    rc.check_uniform_medium_kat(hostsim_lib)
+
+
+def test_scaling_properties(hostsim_lib):
+    rc.check_scaling_properties(hostsim_lib, synth.kuhn_cube(6, seed=44), 100, 76, dict(X=0.4, Y=0.5))

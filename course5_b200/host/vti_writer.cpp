@@ -1,0 +1,130 @@
+// vti_writer.cpp — see vti_writer.hpp.
+#include "vti_writer.hpp"
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <vector>
+
+#include <zlib.h>
+
+namespace c5host {
+
+namespace {
+
+struct file_closer {
+    FILE* f;
+    ~file_closer() {
+        if (f) std::fclose(f);
+    }
+};
+
+} // namespace
+
+void write_vti(const std::string& filename, const double* image, std::size_t res_x, std::size_t res_y,
+               bool compress) {
+    FILE* fp = std::fopen(filename.c_str(), "wb");
+    if (!fp) throw std::runtime_error("cannot write " + filename);
+    file_closer closer{fp};
+    const std::uint64_t n_bytes = static_cast<std::uint64_t>(res_x) * res_y * 2 * sizeof(double);
+    const int ex = static_cast<int>(res_x) - 1, ey = static_cast<int>(res_y) - 1;
+    std::fprintf(fp,
+                 "<?xml version=\"1.0\"?>\n"
+                 "<VTKFile type=\"ImageData\" version=\"1.0\" byte_order=\"LittleEndian\" header_type=\"UInt64\"%s>\n"
+                 "  <ImageData WholeExtent=\"0 %d 0 %d 0 0\" Origin=\"0 0 0\" Spacing=\"1 1 1\">\n"
+                 "    <Piece Extent=\"0 %d 0 %d 0 0\">\n"
+                 "      <PointData Scalars=\"ImageScalars\">\n"
+                 "        <DataArray type=\"Float64\" Name=\"ImageScalars\" NumberOfComponents=\"2\" "
+                 "format=\"appended\" offset=\"0\"/>\n"
+                 "      </PointData>\n"
+                 "      <CellData/>\n"
+                 "    </Piece>\n"
+                 "  </ImageData>\n"
+                 "  <AppendedData encoding=\"raw\">\n   _",
+                 compress ? " compressor=\"vtkZLibDataCompressor\"" : "", ex, ey, ex, ey);
+    if (!compress) {
+        std::fwrite(&n_bytes, sizeof(n_bytes), 1, fp);
+        if (std::fwrite(image, 1, n_bytes, fp) != n_bytes) throw std::runtime_error("short write to " + filename);
+    } else {
+        // VTK compressed block layout: [n_blocks][block_size][last_block_size][compressed sizes...] data...
+        const std::uint64_t block = 1u << 20;
+        const std::uint64_t n_blocks = (n_bytes + block - 1) / block;
+        const std::uint64_t last = n_bytes - (n_blocks - 1) * block;
+        std::vector<std::vector<unsigned char>> packed(n_blocks);
+        std::vector<std::uint64_t> header(3 + n_blocks);
+        header[0] = n_blocks;
+        header[1] = block;
+        header[2] = (last == block) ? 0 : last;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(image);
+        for (std::uint64_t b = 0; b < n_blocks; b++) {
+            const uLong in_size = static_cast<uLong>(b + 1 == n_blocks ? last : block);
+            uLongf out_size = compressBound(in_size);
+            packed[b].resize(out_size);
+            if (compress2(packed[b].data(), &out_size, src + b * block, in_size, Z_BEST_SPEED) != Z_OK) {
+                throw std::runtime_error("zlib failed while writing " + filename);
+            }
+            packed[b].resize(out_size);
+            header[3 + b] = out_size;
+        }
+        std::fwrite(header.data(), sizeof(std::uint64_t), header.size(), fp);
+        for (const auto& p : packed) std::fwrite(p.data(), 1, p.size(), fp);
+    }
+    std::fprintf(fp, "\n  </AppendedData>\n</VTKFile>\n");
+}
+
+void read_vti(const std::string& filename, std::size_t& res_x, std::size_t& res_y, std::size_t& comps,
+              double*& image_out) {
+    std::ifstream in(filename, std::ios::binary);
+    if (!in) throw std::runtime_error("cannot open " + filename);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    const std::string all = ss.str();
+    auto attr = [&](const std::string& tag, const std::string& name) -> std::string {
+        const std::size_t t = all.find("<" + tag);
+        if (t == std::string::npos) throw std::runtime_error(filename + ": no <" + tag + ">");
+        const std::size_t e = all.find('>', t);
+        const std::size_t a = all.find(name + "=\"", t);
+        if (a == std::string::npos || a > e) return "";
+        const std::size_t s = a + name.size() + 2;
+        return all.substr(s, all.find('"', s) - s);
+    };
+    int x0, x1, y0, y1, z0, z1;
+    if (std::sscanf(attr("ImageData", "WholeExtent").c_str(), "%d %d %d %d %d %d", &x0, &x1, &y0, &y1, &z0, &z1) != 6) {
+        throw std::runtime_error(filename + ": bad WholeExtent");
+    }
+    res_x = static_cast<std::size_t>(x1 - x0 + 1);
+    res_y = static_cast<std::size_t>(y1 - y0 + 1);
+    comps = static_cast<std::size_t>(std::stoul(attr("DataArray", "NumberOfComponents")));
+    const bool compressed = !attr("VTKFile", "compressor").empty();
+    const std::size_t marker = all.find("<AppendedData");
+    const std::size_t under = all.find('_', all.find('>', marker));
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(all.data()) + under + 1;
+    const std::size_t n_values = res_x * res_y * comps;
+    image_out = new double[n_values];
+    if (!compressed) {
+        std::uint64_t n_bytes;
+        std::memcpy(&n_bytes, p, 8);
+        if (n_bytes != n_values * sizeof(double)) throw std::runtime_error(filename + ": unexpected data size");
+        std::memcpy(image_out, p + 8, n_bytes);
+    } else {
+        std::uint64_t hdr[3];
+        std::memcpy(hdr, p, 24);
+        std::vector<std::uint64_t> sizes(hdr[0]);
+        std::memcpy(sizes.data(), p + 24, 8 * hdr[0]);
+        const unsigned char* src = p + 24 + 8 * hdr[0];
+        unsigned char* dst = reinterpret_cast<unsigned char*>(image_out);
+        for (std::uint64_t b = 0; b < hdr[0]; b++) {
+            uLongf out_size = static_cast<uLongf>((b + 1 == hdr[0] && hdr[2]) ? hdr[2] : hdr[1]);
+            if (uncompress(dst, &out_size, src, static_cast<uLong>(sizes[b])) != Z_OK) {
+                throw std::runtime_error(filename + ": zlib inflate failed");
+            }
+            dst += out_size;
+            src += sizes[b];
+        }
+    }
+}
+
+} // namespace c5host

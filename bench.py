@@ -112,11 +112,10 @@ def workload():
 
 
 def reference_solids(D):
-    """The reference's Roche lobe + sphere (generated by the reference's own code in oracle/_ref)."""
-    from oracle import refbind
-    if not os.path.exists(refbind.REF_SO):
-        return None
-    return refbind.Ref().solids(D)
+    """The reference's Roche lobe + sphere from the host-side generator (bit-identical to the
+    reference's own, tests/test_host.py)."""
+    from course5_b200 import hostlib
+    return hostlib.make_solids(D)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -31,14 +31,13 @@ _SOLIDS_CACHE = {}
 
 
 def reference_solids(D):
-    """(roche, sphere) tet points in the pre-view frame, digest-checked against the fixtures.
-    Source: oracle/_ref (the reference's own generator) when present."""
+    """(roche, sphere) tet points in the pre-view frame: the reference's Roche lobe and sphere, made
+    by the host-side generator (course5_b200/host/solids.cpp) and digest-checked against the pins
+    taken from the reference's own generator (tests/golden/index.json)."""
     key = f"{D:g}"
     if key not in _SOLIDS_CACHE:
-        from oracle import refbind
-        if not os.path.exists(refbind.REF_SO):
-            return None
-        roche, sphere = refbind.Ref().solids(D)
+        from course5_b200 import hostlib
+        roche, sphere = hostlib.make_solids(float(D))
         pin = GOLDEN_INDEX["_solids"].get(key)
         if pin:
             assert hashlib.sha256(roche.tobytes()).hexdigest() == pin["roche_sha256"]

@@ -92,3 +92,49 @@ def test_render_device_writes_the_band(gpu_lib):
         v = api.make_view(128, 96, X=0.4, Y=0.2, lib=gpu_lib, row_begin=30, row_end=70)
         ctx.render_device(v, band.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert np.array_equal(band.cpu().numpy(), full[30:70])
+
+
+def test_course_cli_end_to_end(gpu_lib, port, tmp_path):
+    """The drop-in: `course -f grid.vtk -d out.vti ...` against the reference's own file-to-file
+    flow (oracle/_ref when present, else the restatement + float cast). .vti values are doubles
+    that went through float (plane.cpp:165-166), so the gate is: equal, or one float ulp apart on
+    at most 1e-4 of the pixels (a 1e-15 difference can flip the float rounding)."""
+    import subprocess
+    from course5_b200 import hostlib
+    from oracle import refbind
+    from parity import float_ulp_distance
+    import os
+    mesh = synth.kuhn_cube(12, seed=61)
+    src = str(tmp_path / "grid.vtk")
+    synth.write_legacy_vtk(src, mesh)
+    flags = dict(X=0.4, Y=0.3, D=0.1, I=-0.03, alpha_limit=2.0)
+    dst = str(tmp_path / "ours.vti")
+    cmd = [hostlib.COURSE_EXE, "-f", src, "-d", dst, "-j4", "-x", "320", "-y", "240", "-X", "0.4", "-Y", "0.3",
+           "-D", "0.1", "-I", "-0.03", "--alpha_limit", "2.0", "--stats"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert lines[0] == "Defined grid resolution: 320x240"               # main.cpp:85
+    assert lines[1] == f"Source file: {src}"
+    assert lines[2] == "Number of parallel threads: 4"
+    assert lines[3] == "Initial rotate angle of roche lobe: 0.1 Pi"
+    assert lines[7] == "Limit alpha value: 2"
+    assert lines[8].startswith("Loading data with VTK lib and other preparations completed in ")
+    assert lines[9].startswith("Ray-tracing completed in ") and lines[9].endswith(" ms. ")
+    assert lines[10] == "Result exported. Calculations completed."
+    ours = hostlib.read_vti(dst)
+    assert ours.shape == (240, 320, 2)
+    if os.path.exists(refbind.REF_SO):
+        ref_dst = str(tmp_path / "ref.vti")
+        refbind.Ref().run_files(src, ref_dst, res_x=320, res_y=240, threads=4, **flags)
+        want = hostlib.read_vti(ref_dst)
+    else:
+        roche, sphere = reference_solids(0.1)
+        img = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=320, res_y=240, X=0.4, Y=0.3, I=-0.03,
+                          alpha_limit=2.0, solid_rot=roche, solid_static=sphere)
+        want = np.stack([img.tau, img.inten], axis=-1).astype(np.float32).astype(np.float64)
+    assert np.array_equal(np.isnan(ours), np.isnan(want))
+    ok = ~np.isnan(want)
+    ulp = float_ulp_distance(ours[ok], want[ok])
+    assert ulp.max() <= 1
+    assert (ulp > 0).mean() <= 1e-4

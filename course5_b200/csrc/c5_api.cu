@@ -130,6 +130,7 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     if (solids) d.mask.ensure(static_cast<size_t>(v->res_x) * v->res_y);
 
     record(d, 0);
+    launch_prepare_cells(d, v->alpha_limit); // no-op unless --alpha_limit changed since the last view
     launch_rotate_vertices(d, p.rot, p.n_rot);
     if (solids) launch_rotate_solids(d, p.rot, p.n_rot);
     record(d, 1);

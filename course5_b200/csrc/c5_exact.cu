@@ -109,7 +109,9 @@ C5_HD double edge_x(const double* p1, const double* p2, double y) { // plane.cpp
 }
 
 // Inclusive scanline footprint of one projected triangle -> mask bytes (idempotent stores).
-C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const double* c) {
+// Rows are independent (the reference's running y equals the accumulated table entry ys[j]), so
+// `n_lanes` threads share one face, lane `lane` taking rows j_lo + lane, j_lo + lane + n_lanes, ...
+C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const double* c, int lane, int n_lanes) {
     const double* p0 = a;
     const double* p1 = b;
     const double* p2 = c;
@@ -127,7 +129,7 @@ C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const 
 
     const long long j_hi = static_cast<long long>(floor(pixel_of_y(g, p0[1])));
     const long long j_lo = static_cast<long long>(ceil(pixel_of_y(g, p2[1])));
-    for (long long j = j_lo; j <= j_hi; j++) {
+    for (long long j = j_lo + lane; j <= j_hi; j += n_lanes) {
         const double y = g.ys[j]; // == ys[j_lo] + (j - j_lo) additions of step_y (plane.cpp:100,138)
         const double x_long = edge_x(p0, p2, y);
         const double x_short = (y < p1[1]) ? edge_x(p2, p1, y) : edge_x(p0, p1, y);
@@ -140,22 +142,25 @@ C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const 
     }
 }
 
+constexpr int kMaskLanes = 8; // threads per solid face
+
 // face f of a solid tet: 0 = (v0,v1,v2), 1 = (v0,v1,v3), 2 = (v0,v2,v3), 3 = (v1,v2,v3) (plane.cpp:30-37)
-C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g) {
+C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g, int lane, int n_lanes) {
     const double* p = pts + 12 * (f >> 2);
     const int k = static_cast<int>(f & 3);
     const double* a = p + (k == 3 ? 3 : 0);
     const double* b = p + (k >= 2 ? 6 : 3);
     const double* c = p + (k == 0 ? 6 : 9);
-    mark_face(g, a, b, c);
+    mark_face(g, a, b, c, lane, n_lanes);
 }
 
 } // namespace
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 solid_mask(int64_t n_faces, const double* __restrict__ pts, MaskGrid g) {
-    const int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (f < n_faces) solid_face_body(f, pts, g);
+    const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t f = tid / kMaskLanes;
+    if (f < n_faces) solid_face_body(f, pts, g, static_cast<int>(tid % kMaskLanes), kMaskLanes);
 }
 
 namespace {
@@ -236,6 +241,24 @@ bvh_refit(int64_t n_leaves, const BFace* __restrict__ faces, const Vtx* __restri
 
 namespace {
 
+C5_HD void prepare_cell_body(int64_t t, Cell* cells, const double* q0, double limit) {
+    double a = cells[t].alpha;
+    if (a > limit) a = limit;                 // line.cpp:216-218
+    // alpha^ < DBL_EPSILON leaves I unchanged (line.cpp:221); the walk tests alpha itself, s is unused
+    cells[t].s = (a < DBL_EPSILON) ? 0.0 : q0[t] / a;
+}
+
+} // namespace
+
+// Source function s = Q / min(alpha, limit) per cell; rerun only when --alpha_limit changes.
+__global__ void __launch_bounds__(256)
+prepare_cells(int64_t n, Cell* __restrict__ cells, const double* __restrict__ q0, double limit) {
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t < n) prepare_cell_body(t, cells, q0, limit);
+}
+
+namespace {
+
 RotSet make_rotset(const Rot* rot, int n_rot) {
     RotSet rs;
     rs.n = n_rot;
@@ -282,12 +305,25 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
         const int64_t n_faces = ss->n * 4;
         count_launch();
         if (kHostSim) {
-            for (int64_t f = 0; f < n_faces; f++) solid_face_body(f, ss->pts_view.p, g);
+            for (int64_t f = 0; f < n_faces; f++) solid_face_body(f, ss->pts_view.p, g, 0, 1);
             continue;
         }
-        solid_mask<<<grid_for(n_faces, 128), 128, 0, d.stream>>>(n_faces, ss->pts_view.p, g);
+        solid_mask<<<grid_for(n_faces * kMaskLanes, 256), 256, 0, d.stream>>>(n_faces, ss->pts_view.p, g);
         C5_CUDA(cudaGetLastError());
     }
+}
+
+void launch_prepare_cells(DeviceState& d, double alpha_limit) {
+    if (d.cells_limit_valid && d.cells_limit == alpha_limit) return;
+    count_launch();
+    if (kHostSim) {
+        for (int64_t t = 0; t < d.n_tets; t++) prepare_cell_body(t, d.cells.p, d.q0.p, alpha_limit);
+    } else {
+        prepare_cells<<<grid_for(d.n_tets, 256), 256, 0, d.stream>>>(d.n_tets, d.cells.p, d.q0.p, alpha_limit);
+        C5_CUDA(cudaGetLastError());
+    }
+    d.cells_limit = alpha_limit;
+    d.cells_limit_valid = true;
 }
 
 void launch_bvh_refit(DeviceState& d) {

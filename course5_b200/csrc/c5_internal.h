@@ -31,6 +31,9 @@ struct DeviceState {
     int64_t n_pts = 0, n_tets = 0, n_bfaces = 0;
     DevBuf<double> px, py, pz;       // Morton-ordered file-frame coordinates (SoA: the rotate kernel streams them)
     DevBuf<Cell> cells;
+    DevBuf<double> q0;               // Q per tet (Morton order); cells[t].s is derived from it
+    double cells_limit = 0.0;        // the alpha_limit cells[].s was last prepared for
+    bool cells_limit_valid = false;
     DevBuf<BFace> bfaces;            // Morton-sorted boundary faces (BVH leaves)
     DevBuf<BvhNode> nodes;           // n_bfaces - 1 internal nodes, BFS order (root = 0)
     DevBuf<int32_t> node_parent;     // per internal node: (parent << 1) | which child, -1 for the root
@@ -80,6 +83,7 @@ void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot);
 void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
                        double step_y);
 void launch_bvh_refit(DeviceState& d);
+void launch_prepare_cells(DeviceState& d, double alpha_limit); // cells[t].s = q0[t] / min(alpha, limit)
 
 // c5_walk.cu
 struct WalkLaunch {

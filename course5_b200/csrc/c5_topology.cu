@@ -102,17 +102,18 @@ struct CellFillOp {
     const uint32_t* tperm; // new -> old tet
     const uint32_t* vinv;  // old -> new vertex
     Cell* cells;
+    double* q0;
     C5_HD void operator()(int64_t t) const {
         const uint32_t old = tperm[t];
         Cell c;
         for (int k = 0; k < 4; k++) {
             c.v[k] = static_cast<int32_t>(vinv[tets[4 * static_cast<int64_t>(old) + k]]);
             c.nbr[k] = -1;
+            c.apex[k] = -1;
         }
         c.alpha = alpha[old];
-        c.q = q[old];
-        c.pad[0] = 0;
-        c.pad[1] = 0;
+        c.s = 0.0; // set by prepare_cells for the view's alpha_limit
+        q0[t] = q[old];
         cells[t] = c;
     }
 };
@@ -172,10 +173,13 @@ struct FaceMatchOp {
             const uint32_t g = idx[i + 1];
             cells[f >> 2].nbr[f & 3] = static_cast<int32_t>(g >> 2);
             cells[g >> 2].nbr[g & 3] = static_cast<int32_t>(f >> 2);
+            cells[f >> 2].apex[f & 3] = cells[g >> 2].v[g & 3];
+            cells[g >> 2].apex[g & 3] = cells[f >> 2].v[f & 3];
             is_boundary[f] = 0;
             is_boundary[g] = 0;
         } else if (!eq_prev) {
             cells[f >> 2].nbr[f & 3] = -1;
+            cells[f >> 2].apex[f & 3] = -1;
             is_boundary[f] = 1;
         }
     }
@@ -211,6 +215,8 @@ struct BFaceOp {
         bf.b = b;
         bf.c = cc;
         bf.tet = static_cast<int32_t>(f >> 2);
+        bf.apex = d;
+        bf.pad[0] = bf.pad[1] = bf.pad[2] = 0;
         out[i] = bf;
         keys[i] = morton3((px[a] + px[b] + px[cc]) / 3.0, (py[a] + py[b] + py[cc]) / 3.0,
                           (pz[a] + pz[b] + pz[cc]) / 3.0, box.lo, box.inv);
@@ -344,7 +350,8 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
         for_each(s, n_tets, TetKeyOp{xyz.p, tets_in.p, n_pts, box, keys.p, tperm.p, err.p});
         check("upload_mesh");
         sort_pairs_u64(keys.p, tperm.p, static_cast<size_t>(n_tets), 63, s);
-        for_each(s, n_tets, CellFillOp{tets_in.p, alpha_in.p, q_in.p, tperm.p, vinv.p, d.cells.p});
+        d.q0.alloc(static_cast<size_t>(n_tets));
+        for_each(s, n_tets, CellFillOp{tets_in.p, alpha_in.p, q_in.p, tperm.p, vinv.p, d.cells.p, d.q0.p});
         stream_sync(s);
     }
     xyz.release();
@@ -466,6 +473,7 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
     d.n_pts = n_pts;
     d.n_tets = n_tets;
     d.n_bfaces = static_cast<int64_t>(n_b);
+    d.cells_limit_valid = false;
 }
 
 } // namespace c5

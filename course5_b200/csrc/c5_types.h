@@ -12,16 +12,20 @@ namespace c5 {
 // ---- data layout in HBM ----------------------------------------------------------------------
 //
 // Cell record: everything one tet-step reads about the tet it is in, in ONE 64-byte aligned
-// record (two 32-byte sectors of one 128-byte line): connectivity, the face-neighbour table and
-// the two cell scalars. nbr[k] is the tet across the face OPPOSITE local vertex k (the face that
-// omits vertex k; the reference's face f omits vertex 3 - f, plane.cpp:30-37), or -1 on the
-// domain boundary. Tets are stored in Morton order of their centroids.
+// record (two 32-byte sectors of one 128-byte line): connectivity, the face-neighbour table, the
+// vertex ids across each face, and the two cell scalars. nbr[k] is the tet across the face
+// OPPOSITE local vertex k (the face that omits vertex k; the reference's face f omits vertex
+// 3 - f, plane.cpp:30-37), or -1 on the domain boundary; apex[k] is the vertex of THAT tet which
+// is not on the shared face. Knowing apex[k] when the ray leaves through face k lets the walk
+// issue the next cell load and the next vertex load together instead of one after the other.
+// s = Q / min(alpha, limit) (the source function) is refreshed when --alpha_limit changes, so the
+// I recurrence needs no divide: I <- s - (s - I) exp(-a dz). Tets are in Morton order of centroids.
 struct alignas(64) Cell {
     int32_t v[4];
     int32_t nbr[4];
+    int32_t apex[4];
     double alpha; // "AbsorpCoef"
-    double q;     // "radEnLooseRate"
-    double pad[2];
+    double s;     // "radEnLooseRate" / min(alpha, alpha_limit)
 };
 static_assert(sizeof(Cell) == 64, "Cell must be 64 bytes");
 
@@ -32,10 +36,13 @@ struct alignas(32) Vtx {
 };
 static_assert(sizeof(Vtx) == 32, "Vtx must be 32 bytes");
 
-// Boundary face, wound so that (b-a)x(c-a) points OUT of the mesh. tet is the cell behind it.
-struct alignas(16) BFace {
+// Boundary face, wound so that (b-a)x(c-a) points OUT of the mesh. tet is the cell behind it and
+// apex that cell's fourth vertex.
+struct alignas(32) BFace {
     int32_t a, b, c, tet;
+    int32_t apex, pad[3];
 };
+static_assert(sizeof(BFace) == 32, "BFace must be 32 bytes");
 
 // Binary LBVH node over boundary faces, 64 bytes: both children's boxes (floats, rounded
 // outward) and child links. child >= 0: internal node index; child < 0: leaf ~child (index into

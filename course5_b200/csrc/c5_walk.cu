@@ -59,8 +59,8 @@ struct WalkParams {
 
 // ---- loads through the read-only path ----------------------------------------------------------
 struct CellData {
-    int4 v, nbr;
-    double alpha, q;
+    int4 v, nbr, apex;
+    double alpha, s;
 };
 
 C5_HD CellData load_cell(const Cell* cells, int t) {
@@ -69,15 +69,17 @@ C5_HD CellData load_cell(const Cell* cells, int t) {
     const int4* p = reinterpret_cast<const int4*>(cells + t);
     c.v = __ldg(p);
     c.nbr = __ldg(p + 1);
-    const double2 aq = __ldg(reinterpret_cast<const double2*>(p + 2));
-    c.alpha = aq.x;
-    c.q = aq.y;
+    c.apex = __ldg(p + 2);
+    const double2 as = __ldg(reinterpret_cast<const double2*>(p + 3));
+    c.alpha = as.x;
+    c.s = as.y;
 #else
     const Cell& s = cells[t];
     c.v = make_int4(s.v[0], s.v[1], s.v[2], s.v[3]);
     c.nbr = make_int4(s.nbr[0], s.nbr[1], s.nbr[2], s.nbr[3]);
+    c.apex = make_int4(s.apex[0], s.apex[1], s.apex[2], s.apex[3]);
     c.alpha = s.alpha;
-    c.q = s.q;
+    c.s = s.s;
 #endif
     return c;
 }
@@ -212,9 +214,11 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
         }
 #ifdef __CUDA_ARCH__
         const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+        int id = __ldg(&P.bfaces[leaf].apex);
 #else
         const BFace& bf = P.bfaces[leaf];
         const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+        int id = bf.apex;
 #endif
         // entry face (a, c, b) of the stored winding is counter-clockwise in projection
         int ia = f.x, ib = f.z, ic = f.y;
@@ -231,13 +235,15 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
         double wc = orient2(ax, ay, bx, by);
         int t = f.w;
 
+        // id = the vertex of tet t that is not on the entry face. It is known BEFORE t's cell is
+        // read (Cell::apex of the previous tet, BFace::apex at entry), so the cell load and the
+        // vertex load of a step are independent and overlap: one memory latency per step, not two.
         while (t >= 0) {
             if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
                 r.error = 1;
                 break;
             }
             const CellData c = load_cell(P.cells, t);
-            const int id = c.v.x ^ c.v.y ^ c.v.z ^ c.v.w ^ ia ^ ib ^ ic; // the vertex not on the entry face
             double dx, dy, dz;
             load_vtx(P.vrot, id, dx, dy, dz);
             dx -= px;
@@ -269,17 +275,16 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
 
             // tau: line.cpp:176-193 (alpha not clamped)
             r.tau += dzv * c.alpha;
-            // I: line.cpp:206-225
+            // I: line.cpp:206-225 with s = Q / a^:  (Q - (Q - a^ I) e) / a^  ==  s - (s - I) e
             double a_c = c.alpha;
             if (a_c > P.alpha_limit) a_c = P.alpha_limit;
-            if (!(a_c < DBL_EPSILON)) {
-                const double C = c.q - a_c * r.inten;
-                r.inten = (c.q - C * exp(-a_c * dzv)) / a_c;
-            }
+            if (!(a_c < DBL_EPSILON)) r.inten = c.s - (c.s - r.inten) * exp(-a_c * dzv);
             r.steps++;
             z_cur = z_exit;
 
-            t = (c.v.x == dropped) ? c.nbr.x : (c.v.y == dropped) ? c.nbr.y : (c.v.z == dropped) ? c.nbr.z : c.nbr.w;
+            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
+            t = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
+            id = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
         }
         if (r.error) break;
         z_after = z_cur;
@@ -309,10 +314,7 @@ __device__ __forceinline__ int compact3(int v) {
     return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4);
 }
 
-} // namespace
-
-__global__ void __launch_bounds__(kBlock)
-tet_walk_fp64(const WalkParams P) {
+__device__ __forceinline__ void walk_block(const WalkParams& P) {
     extern __shared__ __align__(64) unsigned char smem_raw[];
     BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
 
@@ -374,6 +376,14 @@ tet_walk_fp64(const WalkParams P) {
     }
 }
 
+} // namespace
+
+// The product kernel, and register-capped variants kept for occupancy experiments
+// (C5_WALK_VARIANT=r64|r96 selects one at run time; ncu shows which is better where).
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block(P); }
+__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block(P); }
+__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block(P); }
+
 namespace {
 
 void walk_on_host(const WalkParams& P) {
@@ -419,7 +429,11 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.n_macro_x = (P.n_tiles_x + 7) / 8;
     const int n_macro_y = (P.n_tiles_y + 7) / 8;
     const int64_t n_nodes = d.n_bfaces - 1;
-    P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < 255 ? n_nodes : 255);
+    int top = 255;
+    if (const char* e = std::getenv("C5_TOP_NODES")) top = std::atoi(e);
+    if (top < 0) top = 0;
+    if (top > 1023) top = 1023;
+    P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < top ? n_nodes : top);
     P.max_steps = static_cast<int>(d.n_tets < (1 << 20) ? d.n_tets : (1 << 20));
     P.round_float = w.round_through_float;
     P.alpha_limit = w.alpha_limit;
@@ -431,7 +445,14 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     }
     const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
     const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
-    tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
+    const char* variant = std::getenv("C5_WALK_VARIANT");
+    if (variant && std::string(variant) == "r64") {
+        tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (variant && std::string(variant) == "r96") {
+        tet_walk_fp64_r96<<<grid, kBlock, smem, d.stream>>>(P);
+    } else {
+        tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
+    }
     C5_CUDA(cudaGetLastError());
 }
 

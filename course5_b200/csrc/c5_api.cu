@@ -1,7 +1,12 @@
 // c5_api.cu — the C ABI of include/c5gpu.h: context, mesh/solid upload, the per-view pipeline.
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
+#include <utility>
+#include <vector>
+
+#include <dlfcn.h>
 
 #include "c5_internal.h"
 
@@ -117,13 +122,13 @@ void ensure_pixel_tables(DeviceState& d, const c5_view* v, const ViewPlan& p) {
 
 // Enqueues one view's kernels for rows [row_begin,row_end) on device d. Events:
 // 0 start, 1 rotated, 2 bvh, 3 mask, 4 walk.
-void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want_steps) {
+void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want_steps, double* out_override = nullptr) {
     use_device(d);
     g_launch_counter = &d.launches;
     ensure_pixel_tables(d, v, p);
     const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
     const bool solids = v->use_solids && (d.solid_follow.n + d.solid_static.n) > 0;
-    d.out.ensure(2 * n_pix_band);
+    if (!out_override) d.out.ensure(2 * n_pix_band);
     if (want_steps) d.steps.ensure(n_pix_band);
     d.counters.ensure(kNumCounters);
     d.row_cost.ensure(static_cast<size_t>(v->res_y));
@@ -153,10 +158,220 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     w.use_mask = solids ? 1 : 0;
     w.write_steps = want_steps ? 1 : 0;
     w.precision = v->precision ? v->precision : 64;
+    w.out = out_override ? out_override : d.out.p;
     launch_walk(d, w);
     record(d, 4);
 }
 
+// ---- NCCL, loaded lazily: only multi-device contexts need it ---------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclFloat64 = 8; // ncclDouble
+
+struct NcclGroup {
+    NcclApi api;
+    std::vector<void*> comms;
+};
+
+void nccl_check(const NcclApi& api, int rc, const char* what) {
+    if (rc != 0) fail(C5_E_NCCL, std::string(what) + ": " + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+}
+
+NcclGroup* nccl_open(const std::vector<int>& devices) {
+    auto g = std::make_unique<NcclGroup>();
+    NcclApi& a = g->api;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle) break;
+    }
+    if (!a.handle) fail(C5_E_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* n) {
+        void* p = dlsym(a.handle, n);
+        if (!p) fail(C5_E_NCCL, std::string("libnccl lacks ") + n);
+        return p;
+    };
+    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(sym("ncclCommInitAll"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+    a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
+    a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    g->comms.assign(devices.size(), nullptr);
+    nccl_check(a, a.CommInitAll(g->comms.data(), static_cast<int>(devices.size()), devices.data()), "ncclCommInitAll");
+    return g.release();
+}
+
+void nccl_close(void* p) {
+    auto* g = static_cast<NcclGroup*>(p);
+    if (!g) return;
+    for (void* c : g->comms) {
+        if (c) g->api.CommDestroy(c);
+    }
+    delete g;
+}
+
+// Contiguous row bands of [row_begin,row_end) with equal estimated cost (previous view's per-row
+// tet-steps plus a constant per row), one per device; equal heights when there is no history.
+std::vector<std::pair<int, int>> cut_bands(const c5_ctx* ctx, const c5_view* v, const ViewPlan& p, int n) {
+    const int rows = p.row_end - p.row_begin;
+    std::vector<double> cost(static_cast<size_t>(rows), 1.0);
+    if (ctx->last_row_cost.size() == static_cast<size_t>(v->res_y)) {
+        double total = 0;
+        for (int j = 0; j < rows; j++) total += static_cast<double>(ctx->last_row_cost[static_cast<size_t>(p.row_begin + j)]);
+        if (total > 0) {
+            const double base = 64.0 + 0.02 * total / rows; // empty rows are not free (BVH miss, stores)
+            for (int j = 0; j < rows; j++) {
+                cost[static_cast<size_t>(j)] = base + static_cast<double>(ctx->last_row_cost[static_cast<size_t>(p.row_begin + j)]);
+            }
+        }
+    }
+    double total = 0;
+    for (double c : cost) total += c;
+    std::vector<std::pair<int, int>> bands;
+    int lo = 0;
+    double acc = 0;
+    int j = 0;
+    for (int b = 0; b < n; b++) {
+        const double target = total * (b + 1) / n;
+        while (j < rows && (acc + cost[static_cast<size_t>(j)] <= target || j == lo) && rows - (j + 1) >= n - b - 1) {
+            acc += cost[static_cast<size_t>(j)];
+            j++;
+        }
+        if (b == n - 1) j = rows;
+        bands.emplace_back(p.row_begin + lo, p.row_begin + j);
+        lo = j;
+    }
+    return bands;
+}
+
+struct Counters {
+    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
+};
+
+// plane ctor + find_intersections + trace_rays for one view into a HOST buffer, on all devices of
+// the context: device r renders band r; bands land in device 0's image by one grouped NCCL
+// send/recv; device 0 copies the image to the host.
+void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, c5_stats* st) {
+    if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
+    if (!out) fail(C5_E_INVALID, "render: out is NULL");
+    const ViewPlan p = plan_view(v);
+    const int n_dev = static_cast<int>(ctx->dev.size());
+    if (n_dev > 1 && (p.row_end - p.row_begin) < n_dev) fail(C5_E_INVALID, "render: fewer rows than devices");
+    const auto bands = n_dev > 1 ? cut_bands(ctx, v, p, n_dev)
+                                 : std::vector<std::pair<int, int>>{{p.row_begin, p.row_end}};
+    DeviceState& d0 = *ctx->dev[0];
+    const size_t row_doubles = static_cast<size_t>(v->res_x) * 2;
+    const size_t n_pix_view = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
+    if (n_dev > 1) {
+        use_device(d0);
+        d0.out.ensure(2 * n_pix_view); // device 0 assembles the whole view here
+    }
+
+    // enqueue every device's band (asynchronous; devices run concurrently)
+    for (int r = 0; r < n_dev; r++) {
+        DeviceState& d = *ctx->dev[static_cast<size_t>(r)];
+        ViewPlan pr = p;
+        pr.row_begin = bands[static_cast<size_t>(r)].first;
+        pr.row_end = bands[static_cast<size_t>(r)].second;
+        double* target = nullptr;
+        if (n_dev > 1 && r == 0) target = d0.out.p + static_cast<size_t>(pr.row_begin - p.row_begin) * row_doubles;
+        enqueue_view(d, v, pr, steps != nullptr, target);
+    }
+
+    // gather-v of the bands into device 0's image
+    if (n_dev > 1) {
+        if (kHostSim) {
+            for (int r = 1; r < n_dev; r++) {
+                const auto& b = bands[static_cast<size_t>(r)];
+                std::memcpy(d0.out.p + static_cast<size_t>(b.first - p.row_begin) * row_doubles,
+                            ctx->dev[static_cast<size_t>(r)]->out.p, static_cast<size_t>(b.second - b.first) * row_doubles * sizeof(double));
+            }
+        } else {
+            auto* g = static_cast<NcclGroup*>(ctx->nccl);
+            nccl_check(g->api, g->api.GroupStart(), "ncclGroupStart");
+            for (int r = 1; r < n_dev; r++) {
+                const auto& b = bands[static_cast<size_t>(r)];
+                const size_t count = static_cast<size_t>(b.second - b.first) * row_doubles;
+                DeviceState& d = *ctx->dev[static_cast<size_t>(r)];
+                nccl_check(g->api, g->api.Send(d.out.p, count, kNcclFloat64, 0, g->comms[static_cast<size_t>(r)], d.stream), "ncclSend");
+                nccl_check(g->api, g->api.Recv(d0.out.p + static_cast<size_t>(b.first - p.row_begin) * row_doubles, count, kNcclFloat64, r,
+                                               g->comms[0], d0.stream), "ncclRecv");
+            }
+            nccl_check(g->api, g->api.GroupEnd(), "ncclGroupEnd");
+        }
+    }
+    use_device(d0);
+    record(d0, 5);
+    const size_t view_off = static_cast<size_t>(p.row_begin) * v->res_x;
+    d2h(out + 2 * view_off, d0.out.p, 2 * n_pix_view * sizeof(double), d0.stream);
+    record(d0, 6);
+
+    // per-device extras (steps, mask), counters, row costs
+    const bool solids = v->use_solids && (d0.solid_follow.n + d0.solid_static.n) > 0;
+    std::vector<Counters> counters(static_cast<size_t>(n_dev));
+    std::vector<std::vector<uint64_t>> row_cost(static_cast<size_t>(n_dev));
+    for (int r = 0; r < n_dev; r++) {
+        DeviceState& d = *ctx->dev[static_cast<size_t>(r)];
+        use_device(d);
+        const auto& b = bands[static_cast<size_t>(r)];
+        const size_t band_off = static_cast<size_t>(b.first) * v->res_x;
+        const size_t n_pix_band = static_cast<size_t>(b.second - b.first) * v->res_x;
+        if (steps) d2h(steps + band_off, d.steps.p, n_pix_band * sizeof(uint32_t), d.stream);
+        if (solid_mask) {
+            if (solids) d2h(solid_mask + band_off, d.mask.p + band_off, n_pix_band, d.stream);
+            else std::memset(solid_mask + band_off, 0, n_pix_band);
+        }
+        d2h(counters[static_cast<size_t>(r)].c, d.counters.p, sizeof(Counters), d.stream);
+        row_cost[static_cast<size_t>(r)].assign(static_cast<size_t>(v->res_y), 0);
+        d2h(row_cost[static_cast<size_t>(r)].data(), d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(uint64_t), d.stream);
+    }
+    for (auto& dp : ctx->dev) {
+        use_device(*dp);
+        stream_sync(dp->stream);
+    }
+    use_device(d0);
+
+    Counters total;
+    ctx->last_row_cost.assign(static_cast<size_t>(v->res_y), 0);
+    for (int r = 0; r < n_dev; r++) {
+        for (int k = 0; k < kNumCounters; k++) total.c[k] += counters[static_cast<size_t>(r)].c[k];
+        for (int j = 0; j < v->res_y; j++) ctx->last_row_cost[static_cast<size_t>(j)] += row_cost[static_cast<size_t>(r)][static_cast<size_t>(j)];
+    }
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->pixels = static_cast<uint64_t>(n_pix_view);
+        st->tet_steps = total.c[kSteps];
+        st->hit_pixels = total.c[kHitPixels];
+        st->solid_pixels = total.c[kSolidPixels];
+        st->walk_errors = total.c[kWalkErrors];
+        for (auto& dp : ctx->dev) { // phase times: the slowest device
+            use_device(*dp);
+            st->ms_rotate = std::max(st->ms_rotate, elapsed(*dp, 0, 1));
+            st->ms_bvh = std::max(st->ms_bvh, elapsed(*dp, 1, 2));
+            st->ms_mask = std::max(st->ms_mask, elapsed(*dp, 2, 3));
+            st->ms_walk = std::max(st->ms_walk, elapsed(*dp, 3, 4));
+        }
+        use_device(d0);
+        st->ms_gather = n_dev > 1 ? elapsed(d0, 4, 5) : 0.f;
+        st->ms_d2h = elapsed(d0, 5, 6);
+        st->ms_total = elapsed(d0, 0, 6);
+        st->n_devices = n_dev;
+    }
+    if (total.c[kWalkErrors]) {
+        fail(C5_E_WALK, "render: " + std::to_string(total.c[kWalkErrors]) + " ray(s) exceeded the step cap");
+    }
+}
+
+// Single-device, device-resident output (the caller's buffer), no host copy of the image.
 void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan& p, c5_stats* st, int ev_last) {
     unsigned long long c[kNumCounters] = {0, 0, 0, 0};
     d2h(c, d.counters.p, sizeof(c), d.stream);
@@ -175,35 +390,12 @@ void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan
         st->ms_bvh = elapsed(d, 1, 2);
         st->ms_mask = elapsed(d, 2, 3);
         st->ms_walk = elapsed(d, 3, 4);
-        st->ms_d2h = ev_last > 4 ? elapsed(d, 4, ev_last) : 0.f;
         st->ms_total = elapsed(d, 0, ev_last);
         st->n_devices = 1;
     }
     if (c[kWalkErrors]) {
         fail(C5_E_WALK, "render: " + std::to_string(c[kWalkErrors]) + " ray(s) exceeded the step cap");
     }
-}
-
-void render_single(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, c5_stats* st) {
-    if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
-    if (!out) fail(C5_E_INVALID, "render: out is NULL");
-    const ViewPlan p = plan_view(v);
-    DeviceState& d = *ctx->dev[0];
-    enqueue_view(d, v, p, steps != nullptr);
-    const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
-    const size_t band_off = static_cast<size_t>(p.row_begin) * v->res_x;
-    d2h(out + 2 * band_off, d.out.p, 2 * n_pix_band * sizeof(double), d.stream);
-    record(d, 5);
-    if (steps) d2h(steps + band_off, d.steps.p, n_pix_band * sizeof(uint32_t), d.stream);
-    if (solid_mask) {
-        const bool solids = v->use_solids && (d.solid_follow.n + d.solid_static.n) > 0;
-        if (solids) {
-            d2h(solid_mask + band_off, d.mask.p + band_off, n_pix_band, d.stream);
-        } else {
-            std::memset(solid_mask + band_off, 0, n_pix_band);
-        }
-    }
-    collect_stats(ctx, d, v, p, st, 5);
 }
 
 void upload_solids(c5_ctx* ctx, const double* pts, int64_t n, int follows) {
@@ -266,7 +458,6 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
     c5_ctx* ctx = nullptr;
     try {
         if (n_dev < 1 || !devices) fail(C5_E_INVALID, "c5_create: need at least one device");
-        if (n_dev > 1) fail(C5_E_INVALID, "c5_create: multi-device contexts are not available in this build");
         ctx = new c5_ctx();
         if (!kHostSim) {
             int count = 0;
@@ -289,16 +480,22 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
             }
             ctx->dev.push_back(std::move(d));
         }
+        if (n_dev > 1 && !kHostSim) {
+            ctx->nccl = nccl_open(std::vector<int>(devices, devices + n_dev));
+            // peers are only touched by NCCL; each device keeps its own replica of the mesh
+        }
         *out = ctx;
         return C5_OK;
     } catch (const Error& e) {
         std::lock_guard<std::mutex> lock(g_create_err_mu);
         g_create_err = e.text;
+        if (ctx) nccl_close(ctx->nccl);
         delete ctx;
         return e.code;
     } catch (const std::exception& e) {
         std::lock_guard<std::mutex> lock(g_create_err_mu);
         g_create_err = e.what();
+        if (ctx) nccl_close(ctx->nccl);
         delete ctx;
         return C5_E_NOMEM;
     }
@@ -306,6 +503,8 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
 
 void c5_destroy(c5_ctx* ctx) {
     if (!ctx) return;
+    nccl_close(ctx->nccl);
+    ctx->nccl = nullptr;
     for (auto& dp : ctx->dev) {
         DeviceState& d = *dp;
         if (!kHostSim) {
@@ -375,13 +574,13 @@ int c5_mesh_info_get(const c5_ctx* ctx, c5_mesh_info* out) {
 
 int c5_render(c5_ctx* ctx, const c5_view* view, double* out, c5_stats* stats) {
     if (!ctx) return C5_E_INVALID;
-    return guarded(ctx, [&] { render_single(ctx, view, out, nullptr, nullptr, stats); });
+    return guarded(ctx, [&] { render_host(ctx, view, out, nullptr, nullptr, stats); });
 }
 
 int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps, uint8_t* solid_mask,
                   c5_stats* stats) {
     if (!ctx) return C5_E_INVALID;
-    return guarded(ctx, [&] { render_single(ctx, view, out, steps, solid_mask, stats); });
+    return guarded(ctx, [&] { render_host(ctx, view, out, steps, solid_mask, stats); });
 }
 
 int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream, c5_stats* stats) {
@@ -396,11 +595,8 @@ int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream
         cudaStream_t own = d.stream;
         if (!kHostSim && stream) d.stream = static_cast<cudaStream_t>(stream);
         try {
-            enqueue_view(d, view, p, false);
-            const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * view->res_x;
-            d2d(d_out, d.out.p, 2 * n_pix_band * sizeof(double), d.stream);
-            record(d, 5);
-            collect_stats(ctx, d, view, p, stats, 5);
+            enqueue_view(d, view, p, false, static_cast<double*>(d_out)); // the walk stores into the caller's buffer
+            collect_stats(ctx, d, view, p, stats, 4);
         } catch (...) {
             d.stream = own;
             throw;

@@ -93,6 +93,7 @@ struct WalkLaunch {
     int use_mask;
     int write_steps;
     int precision;
+    double* out; // {tau, I} per pixel of the band, x fastest
 };
 void launch_walk(DeviceState& d, const WalkLaunch& w);
 

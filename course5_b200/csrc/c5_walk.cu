@@ -416,7 +416,7 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.xs = d.xs.p;
     P.ys = d.ys.p;
     P.mask = w.use_mask ? d.mask.p : nullptr;
-    P.out = d.out.p;
+    P.out = w.out;
     P.steps = w.write_steps ? d.steps.p : nullptr;
     P.counters = d.counters.p;
     P.row_cost = d.row_cost.p;

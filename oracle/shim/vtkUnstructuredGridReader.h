@@ -14,7 +14,9 @@ class vtkUnstructuredGridReader {
 public:
     void SetFileName(const char* f) { _file = f; }
     void SetReadAllScalars(bool) {}
-    vtkUnstructuredGrid* GetOutput() { return &_grid; }
+    // Real VTK hands out a reference-counted object that outlives the reader (the reference relies
+    // on that at object3d_base.cpp:3-11); the stand-in simply never frees it.
+    vtkUnstructuredGrid* GetOutput() { return _out; }
 
     void Update() {
         std::ifstream in(_file);
@@ -64,5 +66,6 @@ public:
 
 private:
     std::string _file;
-    vtkUnstructuredGrid _grid;
+    vtkUnstructuredGrid* _out = new vtkUnstructuredGrid();
+    vtkUnstructuredGrid& _grid = *_out;
 };

@@ -160,3 +160,26 @@ def check_scaling_properties(lib, mesh, res_x, res_y, flags):
         assert int(ctx.last_row_cost(res_y).sum()) == a_half.stats["tet_steps"]
         del view_full
     return base
+
+
+def check_multi_device_context(lib, devices):
+    """One context over several devices: cost-balanced row bands + gather == single-device image."""
+    mesh = synth.kuhn_cube(8, seed=36)
+    solids = reference_solids(0.0)
+    views = [api.make_view(160, 120, X=0.4, Y=y, lib=lib, round_through_float=0) for y in (0.1, 0.8, 0.8)]
+    with api.Context(devices=(devices[0],), lib=lib) as one:
+        one.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        one.upload_solids(solids[0], True)
+        one.upload_solids(solids[1], False)
+        want = [one.render_raw(v) for v in views]
+    with api.Context(devices=devices, lib=lib) as many:
+        many.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        many.upload_solids(solids[0], True)
+        many.upload_solids(solids[1], False)
+        for v, w in zip(views, want):        # 1st view: equal bands; later ones: cut by the previous view's cost
+            got = many.render_raw(v)
+            assert np.array_equal(got.image, w.image, equal_nan=True)
+            assert np.array_equal(got.steps, w.steps) and np.array_equal(got.solid, w.solid)
+            assert got.stats["tet_steps"] == w.stats["tet_steps"]
+            assert got.stats["n_devices"] == len(devices)
+            assert int(many.last_row_cost(120).sum()) == w.stats["tet_steps"]

@@ -138,3 +138,12 @@ def test_course_cli_end_to_end(gpu_lib, port, tmp_path):
     ulp = float_ulp_distance(ours[ok], want[ok])
     assert ulp.max() <= 1
     assert (ulp > 0).mean() <= 1e-4
+
+
+def test_multi_device_context_with_nccl_gather(gpu_lib):
+    """c5_create over several devices: bands rendered concurrently, one grouped ncclSend/ncclRecv."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    rc.check_multi_device_context(gpu_lib, tuple(range(min(n, 4))))

@@ -59,3 +59,7 @@ def test_uniform_medium(hostsim_lib):
 
 def test_scaling_properties(hostsim_lib):
     rc.check_scaling_properties(hostsim_lib, synth.kuhn_cube(6, seed=44), 100, 76, dict(X=0.4, Y=0.5))
+
+
+def test_multi_device_context(hostsim_lib):
+    rc.check_multi_device_context(hostsim_lib, (0, 0, 0))

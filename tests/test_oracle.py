@@ -106,3 +106,17 @@ def test_kat_solid_object_sizes(ref):
     roche, sphere = ref.solids(0.0)
     assert roche.shape == (130560, 4, 3)    # 255 x 256 rings x points x 2
     assert sphere.shape == (522242, 4, 3)   # 511 x 511 x 2
+
+
+def test_reference_file_to_file_flow_matches_in_memory(ref, tmp_path):
+    """main.cpp:96-137 end to end through the stand-in reader/writer == the in-memory harness."""
+    from course5_b200 import hostlib
+    mesh = synth.kuhn_cube(4, seed=61)
+    src, dst = str(tmp_path / "g.vtk"), str(tmp_path / "ref.vti")
+    synth.write_legacy_vtk(src, mesh)
+    kw = dict(res_x=64, res_y=48, threads=2, X=0.4, Y=0.3, D=0.1, I=-0.03, alpha_limit=2.0)
+    assert ref.run_files(src, dst, **kw) == 0
+    img = hostlib.read_vti(dst)
+    mem = ref.render(mesh.tet_points(), mesh.alpha, mesh.q, solids=1, raw=False, **kw)
+    assert np.array_equal(img[..., 0], mem.tau, equal_nan=True)
+    assert np.array_equal(img[..., 1], mem.inten, equal_nan=True)

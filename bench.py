@@ -60,7 +60,7 @@ def ncu_traffic_per_launch():
 class ClockSampler(threading.Thread):
     """Polls SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period=0.1):
+    def __init__(self, index: int, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -217,6 +217,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     mesh, view = workload()

@@ -142,8 +142,9 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     launch_bvh_refit(d);
     record(d, 2);
     if (solids) {
-        dev_zero(d.mask.p, static_cast<size_t>(v->res_x) * v->res_y, d.stream);
-        launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y);
+        dev_zero(d.mask.p + static_cast<size_t>(p.row_begin) * v->res_x,
+                 static_cast<size_t>(p.row_end - p.row_begin) * v->res_x, d.stream);
+        launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y, p.row_begin, p.row_end);
     }
     record(d, 3);
     dev_zero(d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);

@@ -87,6 +87,7 @@ struct MaskGrid {
     double x_min, y_min, step_x, step_y;
     const double* ys; // accumulated row coordinates (plane.cpp:304-314)
     uint8_t* mask;
+    int row_begin, row_end; // only rows of this band are marked (the walk reads no others)
 };
 
 C5_HD double pixel_of_x(const MaskGrid& g, double x) { // plane.cpp:194-202
@@ -127,8 +128,10 @@ C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const 
     const bool des_below = (p0[0] < p2[0]) && (rel > 0);
     const bool long_edge_is_left = !(asc_above || des_below);
 
-    const long long j_hi = static_cast<long long>(floor(pixel_of_y(g, p0[1])));
-    const long long j_lo = static_cast<long long>(ceil(pixel_of_y(g, p2[1])));
+    long long j_hi = static_cast<long long>(floor(pixel_of_y(g, p0[1])));
+    long long j_lo = static_cast<long long>(ceil(pixel_of_y(g, p2[1])));
+    if (j_lo < g.row_begin) j_lo = g.row_begin;
+    if (j_hi > g.row_end - 1) j_hi = g.row_end - 1;
     for (long long j = j_lo + lane; j <= j_hi; j += n_lanes) {
         const double y = g.ys[j]; // == ys[j_lo] + (j - j_lo) additions of step_y (plane.cpp:100,138)
         const double x_long = edge_x(p0, p2, y);
@@ -138,7 +141,10 @@ C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const 
         const long long i_hi = static_cast<long long>(floor(pixel_of_x(g, x_hi)));
         const long long i_lo = static_cast<long long>(ceil(pixel_of_x(g, x_lo)));
         uint8_t* row = g.mask + static_cast<size_t>(j) * g.res_x;
-        for (long long i = i_lo; i <= i_hi; i++) row[i] = 1;
+        // thousands of fan faces overlap every solid pixel: test first, store only the first time
+        for (long long i = i_lo; i <= i_hi; i++) {
+            if (!row[i]) row[i] = 1;
+        }
     }
 }
 
@@ -298,8 +304,8 @@ void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot) {
 }
 
 void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
-                       double step_y) {
-    MaskGrid g{res_x, res_y, x_min, y_min, step_x, step_y, d.ys.p, d.mask.p};
+                       double step_y, int row_begin, int row_end) {
+    MaskGrid g{res_x, res_y, x_min, y_min, step_x, step_y, d.ys.p, d.mask.p, row_begin, row_end};
     for (SolidSet* ss : {&d.solid_follow, &d.solid_static}) {
         if (ss->n == 0) continue;
         const int64_t n_faces = ss->n * 4;

@@ -81,7 +81,7 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
 void launch_rotate_vertices(DeviceState& d, const Rot* rot, int n_rot);
 void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot);
 void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
-                       double step_y);
+                       double step_y, int row_begin, int row_end);
 void launch_bvh_refit(DeviceState& d);
 void launch_prepare_cells(DeviceState& d, double alpha_limit); // cells[t].s = q0[t] / min(alpha, limit)
 

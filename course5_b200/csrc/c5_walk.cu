@@ -99,6 +99,17 @@ C5_HD void load_vtx(const Vtx* vrot, int id, double& x, double& y, double& z) {
 #endif
 }
 
+// Next step's cell and vertex are known as soon as the exit face is (Cell::nbr / Cell::apex), long
+// before this step's divide and exp have retired: asking L1 for them now overlaps their L2/DRAM
+// latency with that math at no register cost.
+C5_HD void prefetch_l1(const void* p) {
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // ---- entry search --------------------------------------------------------------------------------
 
 // Boundary face `leaf` against the pixel: inclusive point-in-triangle test with the same
@@ -252,19 +263,28 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
             const double sb = orient2(dx, dy, bx, by);
             const double sc = orient2(dx, dy, cx, cy);
 
-            int dropped;
-            if (sa >= 0 && sb < 0) { // leaves through (d, a, b): c is replaced by d
-                dropped = ic;
+            // which face the ray leaves through, hence the next tet and its new vertex
+            const bool drop_c = sa >= 0 && sb < 0;             // through (d, a, b)
+            const bool drop_a = !drop_c && sb >= 0 && sc < 0;  // through (d, b, c)
+            const int dropped = drop_c ? ic : drop_a ? ia : ib; // else through (d, c, a)
+            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
+            const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
+            const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
+            if (t_next >= 0) {
+                prefetch_l1(P.cells + t_next);
+                prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
+                prefetch_l1(P.vrot + id_next);
+            }
+
+            if (drop_c) { // c is replaced by d
                 ic = id; cx = dx; cy = dy; cz = dz;
                 wa = -sb;
                 wb = sa;
-            } else if (sb >= 0 && sc < 0) { // through (d, b, c): a is replaced
-                dropped = ia;
+            } else if (drop_a) { // a is replaced
                 ia = id; ax = dx; ay = dy; az = dz;
                 wb = -sc;
                 wc = sb;
-            } else { // through (d, c, a): b is replaced
-                dropped = ib;
+            } else { // b is replaced
                 ib = id; bx = dx; by = dy; bz = dz;
                 wc = -sa;
                 wa = sc;
@@ -281,10 +301,8 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
             if (!(a_c < DBL_EPSILON)) r.inten = c.s - (c.s - r.inten) * exp(-a_c * dzv);
             r.steps++;
             z_cur = z_exit;
-
-            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
-            t = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
-            id = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
+            t = t_next;
+            id = id_next;
         }
         if (r.error) break;
         z_after = z_cur;
@@ -326,12 +344,24 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
     const int tile_y = (macro / P.n_macro_x) * 8 + compact3(r >> 1);
     if (tile_x >= P.n_tiles_x || tile_y >= P.n_tiles_y) return;
 
+    // Tiles that cannot see the mesh (outside the root's two boxes) skip the staging and the rays.
+    const int i_lo = tile_x * kTileX, j_lo = P.row_begin + tile_y * kTileY;
+    const int i_hi = min(i_lo + kTileX, P.res_x) - 1, j_hi = min(j_lo + kTileY, P.row_end) - 1;
+    bool tile_sees_mesh;
     {
+        const BvhNode* root = P.nodes;
+        const float x0 = f_round_down(P.xs[i_lo]), x1 = f_round_up(P.xs[i_hi]);
+        const float y0 = f_round_down(P.ys[j_lo]), y1 = f_round_up(P.ys[j_hi]);
+        const bool s0 = x1 >= root->xlo[0] && x0 <= root->xhi[0] && y1 >= root->ylo[0] && y0 <= root->yhi[0];
+        const bool s1 = x1 >= root->xlo[1] && x0 <= root->xhi[1] && y1 >= root->ylo[1] && y0 <= root->yhi[1];
+        tile_sees_mesh = s0 || s1;
+    }
+    if (tile_sees_mesh && P.top_nodes > 0) {
         const int4* src = reinterpret_cast<const int4*>(P.nodes);
         int4* dst = reinterpret_cast<int4*>(top);
         for (int k = threadIdx.x; k < P.top_nodes * 4; k += kBlock) dst[k] = src[k];
+        __syncthreads();
     }
-    __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = tile_x * kTileX + (warp & 1) * 8 + (lane & 7);
@@ -350,7 +380,7 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             const double nan = __longlong_as_double(0x7FF8000000000000ll); // quiet NaN (config.hpp:26-27)
             store_pixel(P, i, j, nan, nan, 0);
         } else {
-            res = trace_ray(P, top, P.xs[i], P.ys[j]);
+            if (tile_sees_mesh) res = trace_ray(P, top, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
     }
@@ -383,6 +413,7 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block(P); }
 __global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block(P); }
 __global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block(P); }
+__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block(P); }
 
 namespace {
 
@@ -448,6 +479,8 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     const char* variant = std::getenv("C5_WALK_VARIANT");
     if (variant && std::string(variant) == "r64") {
         tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (variant && std::string(variant) == "r72") {
+        tet_walk_fp64_r72<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (variant && std::string(variant) == "r96") {
         tet_walk_fp64_r96<<<grid, kBlock, smem, d.stream>>>(P);
     } else {

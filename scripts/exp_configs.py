@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--top", default="255")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-solids", action="store_true")
+    ap.add_argument("--view", default=None, help="X,Y override (units of pi)")
+    ap.add_argument("--res", default=None, help="res_x,res_y override")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
@@ -32,6 +34,10 @@ def main():
         t0 = time.perf_counter()
         mesh, view = synth.make_config(name)
         t_gen = time.perf_counter() - t0
+        if args.view:
+            view["X"], view["Y"] = (float(x) for x in args.view.split(","))
+        if args.res:
+            view["res_x"], view["res_y"] = (int(x) for x in args.res.split(","))
         solids = None if args.no_solids else hostlib.make_solids(view["D"])
         ctx = api.Context(devices=(0,))
         t0 = time.perf_counter()
@@ -58,7 +64,7 @@ def main():
                 pixels = view["res_x"] * view["res_y"]
                 gbs = (st["tet_steps"] * 72 + pixels * 16) / (walk * 1e-3) / 1e9
                 print(json.dumps({
-                    "config": name, "variant": variant, "top_nodes": int(top), "n_tets": mesh.n_tets,
+                    "config": name, "view": [view["X"], view["Y"]], "variant": variant, "top_nodes": int(top), "n_tets": mesh.n_tets,
                     "res": [view["res_x"], view["res_y"]], "tet_steps": st["tet_steps"],
                     "hit_pixels": st["hit_pixels"], "solid_pixels": st["solid_pixels"],
                     **{k: round(float(np.median(x)), 4) for k, x in acc.items()},

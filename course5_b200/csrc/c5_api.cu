@@ -67,7 +67,9 @@ ViewPlan plan_view(const c5_view* v) {
     if (!(v->window[0] > v->window[1]) || !(v->window[2] > v->window[3])) {
         fail(C5_E_INVALID, "render: window must be {x_max, x_min, y_max, y_min} with max > min");
     }
-    if (v->precision != 64 && v->precision != 0) fail(C5_E_INVALID, "render: precision must be 64");
+    if (v->precision != 64 && v->precision != 32 && v->precision != 0) {
+        fail(C5_E_INVALID, "render: precision must be 64 or 32");
+    }
     ViewPlan p{};
     p.n_rot = v->n_rot;
     for (int k = 0; k < v->n_rot; k++) {

@@ -310,6 +310,144 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
     return r;
 }
 
+
+// ---- FP32 variant -----------------------------------------------------------------------------------
+// Same walk with the per-step geometry in single precision: FP32 orientation tests (still exactly
+// antisymmetric: two rounded products, one rounded difference), FP32 divide and expf — about half
+// the issue slots and 56 instead of 72 registers. What stays in double: the ENTRY search (so the
+// hit/miss set is the FP64 one, bit for bit), the vertex fetch and its subtraction of the pixel
+// position / entry depth (rounding a coordinate ~1 to float would cost 1e-7, i.e. 1e-5 of a tet;
+// rounding the DIFFERENCE costs 6e-8 of the tet size), and the accumulators tau and I. The walk
+// is not bandwidth-bound, so keeping 32-byte vertices costs nothing measurable.
+// Tolerance vs the reference: 1e-4 relative (tests/parity.py).
+C5_HD float fmul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+C5_HD float fsub_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+C5_HD float orient2f(float ux, float uy, float vx, float vy) {
+    return fsub_rn(fmul_rn(ux, vy), fmul_rn(uy, vx));
+}
+
+C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px, double py) {
+    RayResult r;
+    r.tau = 0.0;
+    r.inten = 0.0;
+    r.steps = 0;
+    r.error = 0;
+    double z_after = -INFINITY;
+    int entries = 0;
+    const float limit = static_cast<float>(P.alpha_limit);
+
+    while (true) {
+        double z_entry;
+        const int leaf = bvh_next_entry(P, top, px, py, z_after, z_entry); // double: same hit set as FP64
+        if (leaf < 0) break;
+        if (++entries > 4096) {
+            r.error = 1;
+            break;
+        }
+#ifdef __CUDA_ARCH__
+        const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+        int id = __ldg(&P.bfaces[leaf].apex);
+#else
+        const BFace& bf = P.bfaces[leaf];
+        const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+        int id = bf.apex;
+#endif
+        int ia = f.x, ib = f.z, ic = f.y;
+        const double z0 = z_entry; // depths are kept relative to the entry point of this crossing
+        float ax, ay, az, bx, by, bz, cx, cy, cz;
+        {
+            double x, y, z;
+            load_vtx(P.vrot, ia, x, y, z);
+            ax = static_cast<float>(x - px); ay = static_cast<float>(y - py); az = static_cast<float>(z - z0);
+            load_vtx(P.vrot, ib, x, y, z);
+            bx = static_cast<float>(x - px); by = static_cast<float>(y - py); bz = static_cast<float>(z - z0);
+            load_vtx(P.vrot, ic, x, y, z);
+            cx = static_cast<float>(x - px); cy = static_cast<float>(y - py); cz = static_cast<float>(z - z0);
+        }
+        float wa = orient2f(bx, by, cx, cy);
+        float wb = orient2f(cx, cy, ax, ay);
+        float wc = orient2f(ax, ay, bx, by);
+        int t = f.w;
+        float z_cur = 0.f;
+
+        while (t >= 0) {
+            if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
+                r.error = 1;
+                break;
+            }
+            const CellData c = load_cell(P.cells, t);
+            float dx, dy, dz;
+            {
+                double x, y, z;
+                load_vtx(P.vrot, id, x, y, z);
+                dx = static_cast<float>(x - px);
+                dy = static_cast<float>(y - py);
+                dz = static_cast<float>(z - z0);
+            }
+            const float sa = orient2f(dx, dy, ax, ay);
+            const float sb = orient2f(dx, dy, bx, by);
+            const float sc = orient2f(dx, dy, cx, cy);
+
+            const bool drop_c = sa >= 0 && sb < 0;
+            const bool drop_a = !drop_c && sb >= 0 && sc < 0;
+            const int dropped = drop_c ? ic : drop_a ? ia : ib;
+            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
+            const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
+            const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
+            if (t_next >= 0) {
+                prefetch_l1(P.cells + t_next);
+                prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
+                prefetch_l1(P.vrot + id_next);
+            }
+            if (drop_c) {
+                ic = id; cx = dx; cy = dy; cz = dz;
+                wa = -sb;
+                wb = sa;
+            } else if (drop_a) {
+                ia = id; ax = dx; ay = dy; az = dz;
+                wb = -sc;
+                wc = sb;
+            } else {
+                ib = id; bx = dx; by = dy; bz = dz;
+                wc = -sa;
+                wa = sc;
+            }
+            const float wsum = wa + wb + wc;
+            const float z_exit = (wsum != 0.0f) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
+            const float dzv = fabsf(z_exit - z_cur);
+
+            r.tau += static_cast<double>(dzv) * c.alpha;
+            float a_c = static_cast<float>(c.alpha);
+            if (a_c > limit) a_c = limit;
+            const double a_d = c.alpha > P.alpha_limit ? P.alpha_limit : c.alpha;
+            if (!(a_d < DBL_EPSILON)) {
+                r.inten = c.s - (c.s - r.inten) * static_cast<double>(expf(-a_c * dzv));
+            }
+            r.steps++;
+            z_cur = z_exit;
+            t = t_next;
+            id = id_next;
+        }
+        if (r.error) break;
+        // the next entry must lie above this crossing's exit (and strictly above its entry)
+        const double z_exit_abs = z0 + static_cast<double>(z_cur);
+        z_after = z_exit_abs > z_entry ? z_exit_abs : z_entry;
+    }
+    return r;
+}
+
 C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double inten, uint32_t steps) {
     const size_t o = static_cast<size_t>(j - P.row_begin) * P.res_x + i;
     if (P.round_float) { // plane.cpp:165-166 then object2d.cpp:19-20
@@ -332,6 +470,7 @@ __device__ __forceinline__ int compact3(int v) {
     return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4);
 }
 
+template <bool kF32>
 __device__ __forceinline__ void walk_block(const WalkParams& P) {
     extern __shared__ __align__(64) unsigned char smem_raw[];
     BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
@@ -380,7 +519,7 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             const double nan = __longlong_as_double(0x7FF8000000000000ll); // quiet NaN (config.hpp:26-27)
             store_pixel(P, i, j, nan, nan, 0);
         } else {
-            if (tile_sees_mesh) res = trace_ray(P, top, P.xs[i], P.ys[j]);
+            if (tile_sees_mesh) res = kF32 ? trace_ray_f32(P, top, P.xs[i], P.ys[j]) : trace_ray(P, top, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
     }
@@ -410,14 +549,16 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
 
 // The product kernel, and register-capped variants kept for occupancy experiments
 // (C5_WALK_VARIANT=r64|r96 selects one at run time; ncu shows which is better where).
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block(P); }
-__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block(P); }
-__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block(P); }
-__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false>(P); }
+__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false>(P); }
+__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false>(P); }
+__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block<false>(P); }
+// optional single-precision geometry (north-star item (d)); entry search and accumulators stay FP64
+__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true>(P); }
 
 namespace {
 
-void walk_on_host(const WalkParams& P) {
+void walk_on_host(const WalkParams& P, bool f32) {
     for (int j = P.row_begin; j < P.row_end; j++) {
         for (int i = 0; i < P.res_x; i++) {
             if (P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i]) {
@@ -425,7 +566,7 @@ void walk_on_host(const WalkParams& P) {
                 P.counters[kSolidPixels]++;
                 continue;
             }
-            const RayResult r = trace_ray(P, nullptr, P.xs[i], P.ys[j]);
+            const RayResult r = f32 ? trace_ray_f32(P, nullptr, P.xs[i], P.ys[j]) : trace_ray(P, nullptr, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -438,7 +579,8 @@ void walk_on_host(const WalkParams& P) {
 } // namespace
 
 void launch_walk(DeviceState& d, const WalkLaunch& w) {
-    if (w.precision != 64) fail(C5_E_INVALID, "render: only precision = 64 is available");
+    if (w.precision != 64 && w.precision != 32) fail(C5_E_INVALID, "render: precision must be 64 or 32");
+    const bool f32 = w.precision == 32;
     WalkParams P{};
     P.cells = d.cells.p;
     P.vrot = d.vrot.p;
@@ -460,7 +602,10 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.n_macro_x = (P.n_tiles_x + 7) / 8;
     const int n_macro_y = (P.n_tiles_y + 7) / 8;
     const int64_t n_nodes = d.n_bfaces - 1;
-    int top = 255;
+    // Staging the top BVH levels in shared memory was measured SLOWER than letting L1 serve them
+    // (C3: 6.38 ms with 0 nodes, 6.54 with 63, 6.88 with 255; profiles/r01_exp_c3_variants_b.jsonl),
+    // so it is off by default; C5_TOP_NODES=n turns it on for experiments.
+    int top = 0;
     if (const char* e = std::getenv("C5_TOP_NODES")) top = std::atoi(e);
     if (top < 0) top = 0;
     if (top > 1023) top = 1023;
@@ -471,13 +616,15 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
 
     count_launch();
     if (kHostSim) {
-        walk_on_host(P);
+        walk_on_host(P, f32);
         return;
     }
     const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
     const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
     const char* variant = std::getenv("C5_WALK_VARIANT");
-    if (variant && std::string(variant) == "r64") {
+    if (f32) {
+        tet_walk_fp32<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (variant && std::string(variant) == "r64") {
         tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (variant && std::string(variant) == "r72") {
         tet_walk_fp64_r72<<<grid, kBlock, smem, d.stream>>>(P);

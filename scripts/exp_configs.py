@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--no-solids", action="store_true")
     ap.add_argument("--view", default=None, help="X,Y override (units of pi)")
     ap.add_argument("--res", default=None, help="res_x,res_y override")
+    ap.add_argument("--precision", default="64")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
@@ -46,11 +47,12 @@ def main():
         if solids is not None:
             ctx.upload_solids(solids[0], True)
             ctx.upload_solids(solids[1], False)
-        v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
-                          alpha_limit=view["alpha_limit"])
         out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64, device=dev)
-        for variant in args.variants.split(","):
-            for top in args.top.split(","):
+        for prec, variant in ((int(p), vv) for p in args.precision.split(",") for vv in args.variants.split(",")):
+            v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
+                              alpha_limit=view["alpha_limit"], precision=prec)
+            if True:
+              for top in args.top.split(","):
                 os.environ["C5_WALK_VARIANT"] = variant
                 os.environ["C5_TOP_NODES"] = top
                 for _ in range(2):
@@ -64,7 +66,7 @@ def main():
                 pixels = view["res_x"] * view["res_y"]
                 gbs = (st["tet_steps"] * 72 + pixels * 16) / (walk * 1e-3) / 1e9
                 print(json.dumps({
-                    "config": name, "view": [view["X"], view["Y"]], "variant": variant, "top_nodes": int(top), "n_tets": mesh.n_tets,
+                    "config": name, "view": [view["X"], view["Y"]], "precision": prec, "variant": variant, "top_nodes": int(top), "n_tets": mesh.n_tets,
                     "res": [view["res_x"], view["res_y"]], "tet_steps": st["tet_steps"],
                     "hit_pixels": st["hit_pixels"], "solid_pixels": st["solid_pixels"],
                     **{k: round(float(np.median(x)), 4) for k, x in acc.items()},

@@ -7,7 +7,7 @@ import pytest
 
 from cases import golden_case, reference_solids, view_kwargs
 from course5_b200 import api, synth
-from parity import assert_image_parity, assert_same_hits
+from parity import ABS_FLOOR_FP32, REL_TOL_FP32, assert_image_parity, assert_same_hits
 
 
 def render_raw(lib, mesh, res_x, res_y, *, solids=None, raw=True, **flags):
@@ -183,3 +183,21 @@ def check_multi_device_context(lib, devices):
             assert got.stats["tet_steps"] == w.stats["tet_steps"]
             assert got.stats["n_devices"] == len(devices)
             assert int(many.last_row_cost(120).sum()) == w.stats["tet_steps"]
+
+
+def check_fp32_variant(lib, port, mesh, res_x, res_y, flags):
+    """precision = 32: geometry in single precision, entry search and accumulators in double.
+    Gate: <= 1e-4 relative per pixel and the SAME hit/miss set as the reference."""
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        v32 = api.make_view(res_x, res_y, lib=lib, round_through_float=0, precision=32, **flags)
+        v64 = api.make_view(res_x, res_y, lib=lib, round_through_float=0, precision=64, **flags)
+        got = ctx.render_raw(v32)
+        ref64 = ctx.render_raw(v64)
+    want = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=res_x, res_y=res_y, **flags)
+    assert_same_hits(got.steps, want.steps, what="fp32: ")
+    assert_image_parity(got.tau, got.inten, want.tau, want.inten, rel=REL_TOL_FP32, floor=ABS_FLOOR_FP32, what="fp32: ")
+    # the two precisions walk (almost always) the same tets
+    assert abs(int(got.stats["tet_steps"]) - int(ref64.stats["tet_steps"])) <= 1e-3 * ref64.stats["tet_steps"]
+    assert not np.array_equal(got.image, ref64.image)      # it really is a different arithmetic
+    return got

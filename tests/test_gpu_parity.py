@@ -147,3 +147,8 @@ def test_multi_device_context_with_nccl_gather(gpu_lib):
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     rc.check_multi_device_context(gpu_lib, tuple(range(min(n, 4))))
+
+
+@pytest.mark.parametrize("flags", [dict(X=0.0, Y=0.0), dict(X=0.4, Y=0.7, I=-0.03, alpha_limit=1.2)])
+def test_fp32_variant(gpu_lib, port, flags):
+    rc.check_fp32_variant(gpu_lib, port, synth.kuhn_cube(24, seed=47), 480, 360, flags)

@@ -63,3 +63,8 @@ def test_scaling_properties(hostsim_lib):
 
 def test_multi_device_context(hostsim_lib):
     rc.check_multi_device_context(hostsim_lib, (0, 0, 0))
+
+
+@pytest.mark.parametrize("flags", [dict(X=0.0, Y=0.0), dict(X=0.4, Y=0.7, I=-0.03, alpha_limit=1.2)])
+def test_fp32_variant(hostsim_lib, port, flags):
+    rc.check_fp32_variant(hostsim_lib, port, synth.kuhn_cube(12, seed=47), 240, 180, flags)

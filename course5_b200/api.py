@@ -3,11 +3,13 @@
 The product path is CUDA only: :func:`load_library` opens ``course5_b200/libc5gpu.so`` and raises
 if it is missing; :class:`Context` raises if no CUDA device is usable. There is no CPU fallback.
 
-Host-side names follow the reference's flow (/root/reference/project/src/main.cpp:96-137):
-``Scene`` holds what main() builds before the timed region (the grid from the VTK file, the
-solid Roche lobe and sphere); ``Scene.render(view)`` is plane ctor + find_intersections +
-trace_rays for one set of CLI flags and returns the ``ImageScalars`` array the .vti holds
+``Context`` wraps one ``c5_ctx``: ``upload_mesh`` / ``upload_solids`` are what main() builds before
+its timed region (/root/reference/project/src/main.cpp:96-123: the grid from the VTK file, the
+solid Roche lobe and sphere); ``render(view)`` is plane ctor + find_intersections + trace_rays
+(main.cpp:127-129) for one set of CLI flags and returns the ``ImageScalars`` array the .vti holds
 (object2d.cpp:7-29): shape (res_y, res_x, 2), component 0 = tau, component 1 ('Y') = I.
+The C++ mirror of the reference's classes (plane, object3d_*, object2d) lives in
+course5_b200/host/; this module is the binding tests and bench.py use.
 """
 from __future__ import annotations
 
@@ -217,8 +219,13 @@ class Context:
                                            _ptr(solid, _u8p), C.byref(st)))
         return RawImage(out, steps, solid, st.as_dict())
 
-    def render_device(self, view: View, device_ptr: int, stream: int = 0) -> dict:
-        """Renders the view's row band into caller-owned DEVICE memory (e.g. tensor.data_ptr())."""
+    def render_device(self, view: View, device_ptr: int, stream: int = 0, *, stats: bool = True) -> dict:
+        """Renders the view's row band into caller-owned DEVICE memory (e.g. tensor.data_ptr()).
+        stats=False: enqueue only (no readback, no synchronisation); returns {}."""
+        if not stats:
+            self._check(self.lib.c5_render_device(self._h, C.byref(view), C.c_void_p(device_ptr),
+                                                  C.c_void_p(stream), None))
+            return {}
         st = Stats()
         self._check(self.lib.c5_render_device(self._h, C.byref(view), C.c_void_p(device_ptr),
                                               C.c_void_p(stream), C.byref(st)))

@@ -599,7 +599,9 @@ int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream
         if (!kHostSim && stream) d.stream = static_cast<cudaStream_t>(stream);
         try {
             enqueue_view(d, view, p, false, static_cast<double*>(d_out)); // the walk stores into the caller's buffer
-            collect_stats(ctx, d, view, p, stats, 4);
+            // stats == NULL: fire and forget — nothing is read back and the stream is not synchronised,
+            // so successive views (and the caller's gather) pipeline on the device
+            if (stats) collect_stats(ctx, d, view, p, stats, 4);
         } catch (...) {
             d.stream = own;
             throw;

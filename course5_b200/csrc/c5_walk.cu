@@ -63,16 +63,38 @@ struct CellData {
     double alpha, s;
 };
 
+// sm_100 has 256-bit global loads (SASS LDG.E.ENL2.256): a 64-byte cell is two of them and a
+// 32-byte vertex one, i.e. 3 load instructions per tet-step instead of 6 LDG.128.
+template <bool kWide>
 C5_HD CellData load_cell(const Cell* cells, int t) {
     CellData c;
 #ifdef __CUDA_ARCH__
-    const int4* p = reinterpret_cast<const int4*>(cells + t);
-    c.v = __ldg(p);
-    c.nbr = __ldg(p + 1);
-    c.apex = __ldg(p + 2);
-    const double2 as = __ldg(reinterpret_cast<const double2*>(p + 3));
-    c.alpha = as.x;
-    c.s = as.y;
+    if (kWide) {
+        const char* p = reinterpret_cast<const char*>(cells + t);
+        long long as0, as1;
+        asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(c.v.x), "=r"(c.v.y), "=r"(c.v.z), "=r"(c.v.w), "=r"(c.nbr.x), "=r"(c.nbr.y), "=r"(c.nbr.z),
+                       "=r"(c.nbr.w)
+                     : "l"(p));
+        int a0, a1, a2, a3;
+        int lo0, hi0, lo1, hi1;
+        asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(lo0), "=r"(hi0), "=r"(lo1), "=r"(hi1)
+                     : "l"(p + 32));
+        c.apex = make_int4(a0, a1, a2, a3);
+        c.alpha = __hiloint2double(hi0, lo0);
+        c.s = __hiloint2double(hi1, lo1);
+        (void)as0;
+        (void)as1;
+    } else {
+        const int4* p = reinterpret_cast<const int4*>(cells + t);
+        c.v = __ldg(p);
+        c.nbr = __ldg(p + 1);
+        c.apex = __ldg(p + 2);
+        const double2 as = __ldg(reinterpret_cast<const double2*>(p + 3));
+        c.alpha = as.x;
+        c.s = as.y;
+    }
 #else
     const Cell& s = cells[t];
     c.v = make_int4(s.v[0], s.v[1], s.v[2], s.v[3]);
@@ -86,12 +108,9 @@ C5_HD CellData load_cell(const Cell* cells, int t) {
 
 C5_HD void load_vtx(const Vtx* vrot, int id, double& x, double& y, double& z) {
 #ifdef __CUDA_ARCH__
-    const double2* p = reinterpret_cast<const double2*>(vrot + id);
-    const double2 xy = __ldg(p);
-    const double2 zw = __ldg(p + 1);
-    x = xy.x;
-    y = xy.y;
-    z = zw.x;
+    double w;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(vrot + id));
+    (void)w;
 #else
     x = vrot[id].x;
     y = vrot[id].y;
@@ -206,6 +225,7 @@ struct RayResult {
     uint32_t error;
 };
 
+template <bool kWide, bool kPrefetch>
 C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py) {
     RayResult r;
     r.tau = 0.0;
@@ -254,7 +274,7 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
                 r.error = 1;
                 break;
             }
-            const CellData c = load_cell(P.cells, t);
+            const CellData c = load_cell<kWide>(P.cells, t);
             double dx, dy, dz;
             load_vtx(P.vrot, id, dx, dy, dz);
             dx -= px;
@@ -270,7 +290,7 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
             const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
             const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
             const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
-            if (t_next >= 0) {
+            if (kPrefetch && t_next >= 0) {
                 prefetch_l1(P.cells + t_next);
                 prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
                 prefetch_l1(P.vrot + id_next);
@@ -338,6 +358,7 @@ C5_HD float orient2f(float ux, float uy, float vx, float vy) {
     return fsub_rn(fmul_rn(ux, vy), fmul_rn(uy, vx));
 }
 
+template <bool kWide, bool kPrefetch>
 C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px, double py) {
     RayResult r;
     r.tau = 0.0;
@@ -387,7 +408,7 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
                 r.error = 1;
                 break;
             }
-            const CellData c = load_cell(P.cells, t);
+            const CellData c = load_cell<kWide>(P.cells, t);
             float dx, dy, dz;
             {
                 double x, y, z;
@@ -406,7 +427,7 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
             const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
             const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
             const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
-            if (t_next >= 0) {
+            if (kPrefetch && t_next >= 0) {
                 prefetch_l1(P.cells + t_next);
                 prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
                 prefetch_l1(P.vrot + id_next);
@@ -470,7 +491,7 @@ __device__ __forceinline__ int compact3(int v) {
     return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4);
 }
 
-template <bool kF32>
+template <bool kF32, bool kWide, bool kPrefetch>
 __device__ __forceinline__ void walk_block(const WalkParams& P) {
     extern __shared__ __align__(64) unsigned char smem_raw[];
     BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
@@ -519,7 +540,10 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             const double nan = __longlong_as_double(0x7FF8000000000000ll); // quiet NaN (config.hpp:26-27)
             store_pixel(P, i, j, nan, nan, 0);
         } else {
-            if (tile_sees_mesh) res = kF32 ? trace_ray_f32(P, top, P.xs[i], P.ys[j]) : trace_ray(P, top, P.xs[i], P.ys[j]);
+            if (tile_sees_mesh) {
+                res = kF32 ? trace_ray_f32<kWide, kPrefetch>(P, top, P.xs[i], P.ys[j])
+                           : trace_ray<kWide, kPrefetch>(P, top, P.xs[i], P.ys[j]);
+            }
             store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
     }
@@ -549,12 +573,14 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
 
 // The product kernel, and register-capped variants kept for occupancy experiments
 // (C5_WALK_VARIANT=r64|r96 selects one at run time; ncu shows which is better where).
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false>(P); }
-__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false>(P); }
-__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false>(P); }
-__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block<false>(P); }
-// optional single-precision geometry (north-star item (d)); entry search and accumulators stay FP64
-__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false, true, false>(P); }
+// optional single-precision step geometry (north-star item (d)); entry search and accumulators stay FP64
+__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true, true, false>(P); }
+// experiment variants (C5_WALK_VARIANT): 128-bit loads, L1 prefetch of the next step, register caps
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, false>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, true>(P); }
+__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, false>(P); }
+__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, false>(P); }
 
 namespace {
 
@@ -566,7 +592,8 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 P.counters[kSolidPixels]++;
                 continue;
             }
-            const RayResult r = f32 ? trace_ray_f32(P, nullptr, P.xs[i], P.ys[j]) : trace_ray(P, nullptr, P.xs[i], P.ys[j]);
+            const RayResult r = f32 ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
+                                    : trace_ray<false, false>(P, nullptr, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -622,13 +649,16 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
     const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
     const char* variant = std::getenv("C5_WALK_VARIANT");
+    const std::string var = variant ? variant : "";
     if (f32) {
         tet_walk_fp32<<<grid, kBlock, smem, d.stream>>>(P);
-    } else if (variant && std::string(variant) == "r64") {
+    } else if (var == "l128") {
+        tet_walk_fp64_l128<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "pf") {
+        tet_walk_fp64_pf<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "r64") {
         tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
-    } else if (variant && std::string(variant) == "r72") {
-        tet_walk_fp64_r72<<<grid, kBlock, smem, d.stream>>>(P);
-    } else if (variant && std::string(variant) == "r96") {
+    } else if (var == "r96") {
         tet_walk_fp64_r96<<<grid, kBlock, smem, d.stream>>>(P);
     } else {
         tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);

@@ -46,10 +46,14 @@ class BandRenderer:
             if self._image is None or self._image.numel() != full:
                 self._image = torch.empty(full, dtype=torch.float64, device=self.device)
 
-    def render(self, view: api.View, *, gather: bool = True, rebalance: bool = True):
+    def render(self, view: api.View, *, gather: bool = True, rebalance: bool = True, stats: bool = True):
         """Renders this rank's band of `view`; returns (image on rank 0 or None, stats, bands).
 
-        The image is a (res_y, res_x, 2) float64 tensor on rank 0's device."""
+        The image is a (res_y, res_x, 2) float64 tensor on rank 0's device. With stats=False (and
+        rebalance=False) nothing is read back to the host: render and gather are only enqueued on the
+        current stream, so a sweep pipelines on the device; synchronise before reading the image."""
+        if not stats:
+            rebalance = False
         bands = self.bands(view.res_y)
         lo, hi = bands[self.rank]
         self._buffers(view, hi - lo)
@@ -60,7 +64,7 @@ class BandRenderer:
         else:
             target = self._band_buf[: (hi - lo) * view.res_x * 2]
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
-        stats = self.ctx.render_device(v, target.data_ptr(), stream)
+        stats = self.ctx.render_device(v, target.data_ptr(), stream, stats=stats)
 
         if self.world > 1 and gather:
             ops = []

@@ -137,8 +137,11 @@ int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps
 /* Device-resident variant for callers that own device memory (e.g. a torch tensor that an NCCL
  * gather will read): d_out is a DEVICE pointer on the context's first device to
  * (row_end - row_begin) * res_x * 2 doubles — the band only. Work is enqueued on `stream`
- * (a cudaStream_t, may be NULL for the default stream) and the call returns after the stream
- * has been synchronised, so stats are final. Single-device contexts only. */
+ * (a cudaStream_t, may be NULL for the context's own stream). With stats != NULL the call returns
+ * after the stream has been synchronised, so stats (and c5_last_row_cost) are final. With
+ * stats == NULL nothing is read back and the call returns as soon as the work is enqueued: the
+ * caller orders later work on the same stream (successive views and an NCCL gather then pipeline
+ * on the device without host round trips). Single-device contexts only. */
 int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream, c5_stats* stats);
 
 /* Per-row tet-step totals of the last render on this context (res_y entries; rows outside the

@@ -4,14 +4,12 @@ set -u
 mkdir -p gpurun_out
 echo "== pytest -m gpu" && timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 rc=$?; tail -8 gpurun_out/pytest_gpu.log; [ $rc -ne 0 ] && exit $rc
-echo "== variants on C3"
-timeout 900 python scripts/exp_configs.py C3 --variants default,r96,r64 --top 0,63,255 2>&1 | tee gpurun_out/exp_c3.jsonl
-echo "== C3 mesh, oblique view / higher resolution"
-timeout 900 python scripts/exp_configs.py C3 --view 0.4,0.3 --top 0 2>&1 | tee gpurun_out/exp_c3_oblique.jsonl
-timeout 900 python scripts/exp_configs.py C3 --res 4800,3600 --top 0 2>&1 | tee -a gpurun_out/exp_c3_oblique.jsonl
+echo "== variants on C3 (aligned README view, then oblique)"
+timeout 900 python scripts/exp_configs.py C3 --variants default,l128,pf,r96 --top 0 --precision 64 2>&1 | tee gpurun_out/exp_c3.jsonl
+timeout 900 python scripts/exp_configs.py C3 --variants default --top 0 --precision 32 2>&1 | tee -a gpurun_out/exp_c3.jsonl
+timeout 900 python scripts/exp_configs.py C3 --view 0.4,0.3 --variants default,l128,pf --top 0 --precision 64,32 2>&1 | tee -a gpurun_out/exp_c3.jsonl
 echo "== other configs"
 timeout 1500 python scripts/exp_configs.py C1 C2 C5 --top 0 2>&1 | tee gpurun_out/exp_configs.jsonl
-timeout 900 python scripts/exp_configs.py C5 --view 0.5,0.0 --top 0 2>&1 | tee -a gpurun_out/exp_configs.jsonl
 echo "== bench N=1"
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
 NG=$(nvidia-smi -L | wc -l)

@@ -25,6 +25,7 @@ const option kOptions[] = {
     {"initial_system_angle", 'I', true}, {"alpha_limit", 0, true},
     // additions of this build (absent from the reference)
     {"devices", 0, true},          {"stats", 0, false},           {"precision", 0, true},
+    {"frames", 0, true},           {"sweep_y_to", 0, true},
 };
 
 const option* find_long(const std::string& name, std::string& err) {
@@ -89,6 +90,10 @@ void print_usage(std::ostream& out) {
            "  --devices arg (=0)                     CUDA device ordinals, comma separated\n"
            "  --precision arg (=64)                  64 or 32\n"
            "  --stats                                print per-phase timings as one JSON line\n"
+           "  --frames arg (=1)                      render a sweep of -Y in this process: frame k\n"
+           "                                         uses Y + (sweep_y_to - Y) k / frames and is\n"
+           "                                         written to <destination stem>_<k>.vti\n"
+           "  --sweep_y_to arg (=2)                  end angle of the sweep (exclusive)\n"
         << std::endl;
 }
 
@@ -144,6 +149,8 @@ cli_result program_options(int argc, char** argv, config_str& cfg, std::ostream&
             else if (name == "devices") cfg.devices = value;
             else if (name == "stats") cfg.stats = true;
             else if (name == "precision") cfg.precision = static_cast<int>(to_integer(name, value));
+            else if (name == "frames") cfg.frames = static_cast<int>(to_integer(name, value));
+            else if (name == "sweep_y_to") cfg.sweep_y_to = to_double(name, value);
         }
     } catch (const std::exception& e) {
         out << "Error! " << e.what() << std::endl;

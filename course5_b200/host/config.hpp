@@ -27,6 +27,8 @@ struct config_str {
     std::string devices = "0";                 // --devices 0,1,...  CUDA ordinals
     bool stats = false;                        // --stats: one JSON line with per-phase timings
     int precision = 64;
+    int frames = 1;                            // --frames N: in-process sweep of -Y (replaces utility/rotate_traces.py)
+    double sweep_y_to = 2.0;                   // --sweep_y_to: end angle (exclusive), units of pi
 };
 
 constexpr double PI = 3.14159265358979323846;  // config.hpp:45

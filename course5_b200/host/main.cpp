@@ -91,7 +91,27 @@ int main(int argc, char** argv) {
         t2 = std::chrono::steady_clock::now();
         std::cout << "Ray-tracing completed in " << ms_between(t1, t2) << " ms. " << std::endl;
 
-        result.export_to_vti(config.destination);
+        if (config.frames <= 1) {
+            result.export_to_vti(config.destination);
+        } else {
+            // in-process sweep: the scene stays on the device, only the rotations change
+            std::string stem = config.destination, ext = ".vti";
+            const auto dot = stem.rfind('.');
+            if (dot != std::string::npos) {
+                ext = stem.substr(dot);
+                stem = stem.substr(0, dot);
+            }
+            const auto t3 = std::chrono::steady_clock::now();
+            for (int k = 0; k < config.frames; k++) {
+                const double y = config.angle_around_y + (config.sweep_y_to - config.angle_around_y) * k / config.frames;
+                base_plane.set_view_rotations({c5_rotation{0, 0, make_perpendicular_to_y_angle, 0.0},
+                                               c5_rotation{1, 0, y * PI, ACC_X0}, c5_rotation{0, 0, last_angle, 0.0}});
+                if (k > 0) result = base_plane.trace_rays(tetra_value::alpha, tetra_value::Q);
+                result.export_to_vti(stem + "_" + std::to_string(k) + ext);
+            }
+            std::cout << "Sweep of " << config.frames << " frames completed in "
+                      << ms_between(t3, std::chrono::steady_clock::now()) << " ms. " << std::endl;
+        }
         std::cout << "Result exported. Calculations completed." << std::endl;
 
         if (config.stats) {

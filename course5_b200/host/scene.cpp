@@ -197,6 +197,13 @@ void plane::find_intersections() {
     _uploaded = true;
 }
 
+void plane::set_view_rotations(const std::vector<c5_rotation>& rotations) {
+    if (rotations.size() > C5_MAX_ROT) throw std::runtime_error("too many rotations");
+    if (!_uploaded) find_intersections();
+    _view.n_rot = static_cast<int32_t>(rotations.size());
+    for (std::size_t k = 0; k < rotations.size(); k++) _view.rot[k] = rotations[k];
+}
+
 object2d plane::trace_rays(tetra_value value_alpha, tetra_value value_Q) {
     if (value_alpha != tetra_value::alpha || value_Q != tetra_value::Q) {
         throw std::runtime_error("trace_rays: the scalar roles are fixed to (alpha, Q)");

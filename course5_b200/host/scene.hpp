@@ -106,6 +106,9 @@ public:
 
     void find_intersections();
     object2d trace_rays(tetra_value value_alpha, tetra_value value_Q);
+    // Sweeps: replace the recorded view rotations (grid and view-following solids) without
+    // re-uploading anything; the next trace_rays() renders the new view in milliseconds.
+    void set_view_rotations(const std::vector<c5_rotation>& rotations);
     std::size_t count_all_intersections() const { return static_cast<std::size_t>(_stats.tet_steps); }
     std::size_t get_x() const { return _x; }
     std::size_t get_y() const { return _y; }

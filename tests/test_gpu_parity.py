@@ -152,3 +152,25 @@ def test_multi_device_context_with_nccl_gather(gpu_lib):
 @pytest.mark.parametrize("flags", [dict(X=0.0, Y=0.0), dict(X=0.4, Y=0.7, I=-0.03, alpha_limit=1.2)])
 def test_fp32_variant(gpu_lib, port, flags):
     rc.check_fp32_variant(gpu_lib, port, synth.kuhn_cube(24, seed=47), 480, 360, flags)
+
+
+def test_course_sweep_frames_equal_single_runs(gpu_lib, tmp_path):
+    """`course --frames N` (mesh resident, rotations change) == N separate process-per-frame runs,
+    the way utility/rotate_traces.py drives the reference."""
+    import subprocess
+    from course5_b200 import hostlib
+    mesh = synth.kuhn_cube(8, seed=62)
+    src = str(tmp_path / "grid.vtk")
+    synth.write_legacy_vtk(src, mesh, binary=True)
+    base = [hostlib.COURSE_EXE, "-f", src, "-x", "200", "-y", "150", "-X", "0.4", "-I", "-0.03"]
+    p = subprocess.run(base + ["-d", str(tmp_path / "sweep.vti"), "-Y", "0.0", "--frames", "3", "--sweep_y_to", "1.5"],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    for k in range(3):
+        y = 0.0 + 1.5 * k / 3
+        single = str(tmp_path / f"single_{k}.vti")
+        q = subprocess.run(base + ["-d", single, "-Y", repr(y)], capture_output=True, text=True)
+        assert q.returncode == 0, q.stdout + q.stderr
+        a = hostlib.read_vti(str(tmp_path / f"sweep_{k}.vti"))
+        b = hostlib.read_vti(single)
+        assert np.array_equal(a, b, equal_nan=True)

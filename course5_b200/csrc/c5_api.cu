@@ -594,9 +594,10 @@ int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream
         if (ctx->dev.size() != 1) fail(C5_E_INVALID, "render_device: single-device contexts only");
         const ViewPlan p = plan_view(view);
         DeviceState& d = *ctx->dev[0];
-        // run on the caller's stream so the result is ordered with the caller's later work
+        // run on the CALLER's stream (NULL = the legacy default stream, which is what torch's
+        // default "current stream" is) so the result is ordered with the caller's later work
         cudaStream_t own = d.stream;
-        if (!kHostSim && stream) d.stream = static_cast<cudaStream_t>(stream);
+        if (!kHostSim) d.stream = static_cast<cudaStream_t>(stream);
         try {
             enqueue_view(d, view, p, false, static_cast<double*>(d_out)); // the walk stores into the caller's buffer
             // stats == NULL: fire and forget — nothing is read back and the stream is not synchronised,

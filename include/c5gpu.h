@@ -137,7 +137,7 @@ int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps
 /* Device-resident variant for callers that own device memory (e.g. a torch tensor that an NCCL
  * gather will read): d_out is a DEVICE pointer on the context's first device to
  * (row_end - row_begin) * res_x * 2 doubles — the band only. Work is enqueued on `stream`
- * (a cudaStream_t, may be NULL for the context's own stream). With stats != NULL the call returns
+ * (a cudaStream_t; NULL = the legacy default stream). With stats != NULL the call returns
  * after the stream has been synchronised, so stats (and c5_last_row_cost) are final. With
  * stats == NULL nothing is read back and the call returns as soon as the work is enqueued: the
  * caller orders later work on the same stream (successive views and an NCCL gather then pipeline

@@ -23,4 +23,13 @@ if [ "${1:-}" = "ncu" ]; then
       -f -o gpurun_out/walk_full $CMD > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi
+NG=$(nvidia-smi -L | wc -l)
+for N in 2 4 8; do
+  if [ "$NG" -ge "$N" ]; then
+    echo "== bench N=$N"
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N \
+        bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+    grep '^{' gpurun_out/bench_n$N.json | cut -c1-400; tail -3 gpurun_out/bench_n$N.err
+  fi
+done
 exit 0

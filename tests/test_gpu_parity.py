@@ -174,3 +174,27 @@ def test_course_sweep_frames_equal_single_runs(gpu_lib, tmp_path):
         a = hostlib.read_vti(str(tmp_path / f"sweep_{k}.vti"))
         b = hostlib.read_vti(single)
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_full_size_properties_config_c5(gpu_lib):
+    """BASELINE.json configs[4] geometry at full size (50 192 562 tets, graded, 4800 x 3600, -X 0.4
+    -Y 0.3) with a uniform medium: the recurrence telescopes, so per pixel
+    I == (q / a^) (1 - exp(-a^ tau / a)) whatever the 2.2 G tet-steps in between did."""
+    mesh = synth.kuhn_cube(203, seed=5, grade_beta=1.5, scalars="const")   # a = 1.5, q = 0.75
+    assert mesh.n_tets == 50192562
+    with api.Context(devices=(0,), lib=gpu_lib) as ctx:
+        info = ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        assert info.n_boundary_faces == 203 * 203 * 12
+        del mesh
+        for limit in (2.5, 0.9):
+            v = api.make_view(4800, 3600, X=0.4, Y=0.3, alpha_limit=limit, lib=gpu_lib, round_through_float=0)
+            img = ctx.render_raw(v)
+            assert img.stats["walk_errors"] == 0 and img.stats["tet_steps"] > 2_000_000_000
+            assert int(img.steps.sum()) == img.stats["tet_steps"]
+            hit = img.hit
+            a_hat = min(1.5, limit)
+            want = 0.75 / a_hat * (1.0 - np.exp(-a_hat * img.tau[hit] / 1.5))
+            assert np.allclose(img.inten[hit], want, rtol=1e-10, atol=1e-13)
+            assert np.all(img.image[~hit] == 0.0)
+            # the cube's silhouette: tau / a is the chord length, at most the space diagonal (+ jitter)
+            assert img.tau.max() / 1.5 < 1.75

@@ -257,7 +257,7 @@ std::vector<std::pair<int, int>> cut_bands(const c5_ctx* ctx, const c5_view* v, 
 }
 
 struct Counters {
-    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
+    unsigned long long c[kNumCounters] = {0, 0, 0, 0, 0};
 };
 
 // plane ctor + find_intersections + trace_rays for one view into a HOST buffer, on all devices of
@@ -346,7 +346,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
     Counters total;
     ctx->last_row_cost.assign(static_cast<size_t>(v->res_y), 0);
     for (int r = 0; r < n_dev; r++) {
-        for (int k = 0; k < kNumCounters; k++) total.c[k] += counters[static_cast<size_t>(r)].c[k];
+        for (int k = 0; k < kTileTicket; k++) total.c[k] += counters[static_cast<size_t>(r)].c[k];
         for (int j = 0; j < v->res_y; j++) ctx->last_row_cost[static_cast<size_t>(j)] += row_cost[static_cast<size_t>(r)][static_cast<size_t>(j)];
     }
     if (st) {
@@ -376,7 +376,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
 
 // Single-device, device-resident output (the caller's buffer), no host copy of the image.
 void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan& p, c5_stats* st, int ev_last) {
-    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
+    unsigned long long c[kNumCounters] = {0, 0, 0, 0, 0};
     d2h(c, d.counters.p, sizeof(c), d.stream);
     ctx->last_row_cost.assign(static_cast<size_t>(v->res_y), 0);
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "row cost width");

@@ -13,7 +13,7 @@ namespace c5 {
 constexpr int kMaxRot = C5_MAX_ROT;
 
 // Counters the walk kernel accumulates (one 64-bit atomic per warp).
-enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kNumCounters = 4 };
+enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kTileTicket = 4, kNumCounters = 5 };
 
 struct SolidSet {
     DevBuf<double> pts0;      // [n][4][3] pre-view frame
@@ -29,6 +29,7 @@ struct DeviceState {
 
     // mesh (uploaded once)
     int64_t n_pts = 0, n_tets = 0, n_bfaces = 0;
+    float tet_size = 0.f;            // (bounding-box volume / n_tets)^(1/3): the mesh's length scale
     DevBuf<double> px, py, pz;       // Morton-ordered file-frame coordinates (SoA: the rotate kernel streams them)
     DevBuf<Cell> cells;
     DevBuf<double> q0;               // Q per tet (Morton order); cells[t].s is derived from it

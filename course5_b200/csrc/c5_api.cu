@@ -2,7 +2,9 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <exception>
 #include <mutex>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -257,7 +259,7 @@ std::vector<std::pair<int, int>> cut_bands(const c5_ctx* ctx, const c5_view* v, 
 }
 
 struct Counters {
-    unsigned long long c[kNumCounters] = {0, 0, 0, 0, 0};
+    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
 };
 
 // plane ctor + find_intersections + trace_rays for one view into a HOST buffer, on all devices of
@@ -279,8 +281,9 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
         d0.out.ensure(2 * n_pix_view); // device 0 assembles the whole view here
     }
 
-    // enqueue every device's band (asynchronous; devices run concurrently)
-    for (int r = 0; r < n_dev; r++) {
+    // enqueue every device's band (asynchronous; devices run concurrently). With several devices
+    // one host thread per device issues the launches, so launch latency is not serialised.
+    auto enqueue_band = [&](int r) {
         DeviceState& d = *ctx->dev[static_cast<size_t>(r)];
         ViewPlan pr = p;
         pr.row_begin = bands[static_cast<size_t>(r)].first;
@@ -288,6 +291,26 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
         double* target = nullptr;
         if (n_dev > 1 && r == 0) target = d0.out.p + static_cast<size_t>(pr.row_begin - p.row_begin) * row_doubles;
         enqueue_view(d, v, pr, steps != nullptr, target);
+    };
+    if (n_dev == 1 || kHostSim) {
+        for (int r = 0; r < n_dev; r++) enqueue_band(r);
+    } else {
+        std::vector<std::thread> workers;
+        std::vector<std::exception_ptr> errors(static_cast<size_t>(n_dev));
+        for (int r = 0; r < n_dev; r++) {
+            workers.emplace_back([&, r] {
+                try {
+                    enqueue_band(r);
+                } catch (...) {
+                    errors[static_cast<size_t>(r)] = std::current_exception();
+                }
+            });
+        }
+        for (auto& w : workers) w.join();
+        for (auto& e : errors) {
+            if (e) std::rethrow_exception(e);
+        }
+        g_launch_counter = &d0.launches;
     }
 
     // gather-v of the bands into device 0's image
@@ -346,7 +369,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
     Counters total;
     ctx->last_row_cost.assign(static_cast<size_t>(v->res_y), 0);
     for (int r = 0; r < n_dev; r++) {
-        for (int k = 0; k < kTileTicket; k++) total.c[k] += counters[static_cast<size_t>(r)].c[k];
+        for (int k = 0; k < kNumCounters; k++) total.c[k] += counters[static_cast<size_t>(r)].c[k];
         for (int j = 0; j < v->res_y; j++) ctx->last_row_cost[static_cast<size_t>(j)] += row_cost[static_cast<size_t>(r)][static_cast<size_t>(j)];
     }
     if (st) {
@@ -376,7 +399,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
 
 // Single-device, device-resident output (the caller's buffer), no host copy of the image.
 void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan& p, c5_stats* st, int ev_last) {
-    unsigned long long c[kNumCounters] = {0, 0, 0, 0, 0};
+    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
     d2h(c, d.counters.p, sizeof(c), d.stream);
     ctx->last_row_cost.assign(static_cast<size_t>(v->res_y), 0);
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "row cost width");
@@ -422,6 +445,8 @@ void upload_solids(c5_ctx* ctx, const double* pts, int64_t n, int follows) {
             d2d(ss.pts_view.p, ss.pts0.p, ss.pts0.bytes(), d.stream);
             stream_sync(d.stream);
         }
+        g_launch_counter = &d.launches;
+        dedupe_solid_faces(d, ss);
     }
     ctx->info.n_solid_tets += n;
 }
@@ -562,7 +587,9 @@ int c5_clear_solids(c5_ctx* ctx) {
             for (SolidSet* ss : {&dp->solid_follow, &dp->solid_static}) {
                 ss->pts0.release();
                 ss->pts_view.release();
+                ss->faces.release();
                 ss->n = 0;
+                ss->n_faces = 0;
             }
         }
         ctx->info.n_solid_tets = 0;

@@ -11,6 +11,8 @@
 //   bvh_refit        per-view boxes of the boundary-face LBVH (no reference counterpart: it
 //                    replaces the full scan conversion plane.cpp:184-192 as the way a ray finds
 //                    the tets it crosses).
+#include <cstring>
+
 #include "c5_internal.h"
 
 namespace c5 {
@@ -163,11 +165,97 @@ C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g, int 
 } // namespace
 
 __global__ void __launch_bounds__(256)
-solid_mask(int64_t n_faces, const double* __restrict__ pts, MaskGrid g) {
+solid_mask(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g) {
     const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t f = tid / kMaskLanes;
-    if (f < n_faces) solid_face_body(f, pts, g, static_cast<int>(tid % kMaskLanes), kMaskLanes);
+    const int64_t k = tid / kMaskLanes;
+    if (k < n_faces) solid_face_body(faces[k], pts, g, static_cast<int>(tid % kMaskLanes), kMaskLanes);
 }
+
+namespace {
+
+// ---- unique solid faces (once per upload) --------------------------------------------------------
+// The reference's solids are fans of tets around a centre (object3d_base.cpp:156-193): every fan
+// face belongs to two tets and would be scan-converted twice. Faces are compared on the exact bit
+// patterns of their three points (order-independent), so dropping a duplicate cannot change the mask.
+C5_HD void face_points(const double* pts, uint32_t f, const double*& a, const double*& b, const double*& c) {
+    const double* p = pts + 12 * static_cast<size_t>(f >> 2);
+    const int k = static_cast<int>(f & 3);
+    a = p + (k == 3 ? 3 : 0);
+    b = p + (k >= 2 ? 6 : 3);
+    c = p + (k == 0 ? 6 : 9);
+}
+C5_HD bool point_less(const double* u, const double* v) {
+    if (u[0] != v[0]) return u[0] < v[0];
+    if (u[1] != v[1]) return u[1] < v[1];
+    return u[2] < v[2];
+}
+C5_HD void sorted_face(const double* pts, uint32_t f, const double* out[3]) {
+    face_points(pts, f, out[0], out[1], out[2]);
+    const double* t;
+    if (point_less(out[1], out[0])) { t = out[0]; out[0] = out[1]; out[1] = t; }
+    if (point_less(out[2], out[1])) { t = out[1]; out[1] = out[2]; out[2] = t; }
+    if (point_less(out[1], out[0])) { t = out[0]; out[0] = out[1]; out[1] = t; }
+}
+C5_HD uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+C5_HD uint64_t double_bits(double v) {
+#ifdef __CUDA_ARCH__
+    return static_cast<uint64_t>(__double_as_longlong(v));
+#else
+    uint64_t b;
+    memcpy(&b, &v, sizeof(b));
+    return b;
+#endif
+}
+
+struct SolidFaceKeyOp {
+    const double* pts;
+    uint64_t* keys;
+    uint32_t* vals;
+    C5_HD void operator()(int64_t f) const {
+        const double* p[3];
+        sorted_face(pts, static_cast<uint32_t>(f), p);
+        uint64_t h = 0;
+        for (int i = 0; i < 3; i++) {
+            for (int c = 0; c < 3; c++) h = mix64(h ^ double_bits(p[i][c]));
+        }
+        keys[f] = h;
+        vals[f] = static_cast<uint32_t>(f);
+    }
+};
+
+struct SolidFaceFirstOp {
+    const double* pts;
+    const uint64_t* keys; // sorted
+    const uint32_t* vals;
+    uint8_t* first;
+    C5_HD void operator()(int64_t i) const {
+        bool dup = false;
+        if (i > 0 && keys[i] == keys[i - 1]) {
+            const double *p[3], *q[3];
+            sorted_face(pts, vals[i], p);
+            sorted_face(pts, vals[i - 1], q);
+            dup = true;
+            for (int k = 0; k < 3; k++) {
+                for (int c = 0; c < 3; c++) dup = dup && double_bits(p[k][c]) == double_bits(q[k][c]);
+            }
+        }
+        first[i] = dup ? 0 : 1;
+    }
+};
+
+struct GatherU32Op {
+    const uint32_t* src;
+    const uint32_t* idx;
+    uint32_t* out;
+    C5_HD void operator()(int64_t i) const { out[i] = src[idx[i]]; }
+};
+
+} // namespace
 
 namespace {
 
@@ -308,13 +396,13 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
     MaskGrid g{res_x, res_y, x_min, y_min, step_x, step_y, d.ys.p, d.mask.p, row_begin, row_end};
     for (SolidSet* ss : {&d.solid_follow, &d.solid_static}) {
         if (ss->n == 0) continue;
-        const int64_t n_faces = ss->n * 4;
+        const int64_t n_faces = ss->n_faces;
         count_launch();
         if (kHostSim) {
-            for (int64_t f = 0; f < n_faces; f++) solid_face_body(f, ss->pts_view.p, g, 0, 1);
+            for (int64_t k = 0; k < n_faces; k++) solid_face_body(ss->faces.p[k], ss->pts_view.p, g, 0, 1);
             continue;
         }
-        solid_mask<<<grid_for(n_faces * kMaskLanes, 256), 256, 0, d.stream>>>(n_faces, ss->pts_view.p, g);
+        solid_mask<<<grid_for(n_faces * kMaskLanes, 256), 256, 0, d.stream>>>(n_faces, ss->faces.p, ss->pts_view.p, g);
         C5_CUDA(cudaGetLastError());
     }
 }
@@ -330,6 +418,28 @@ void launch_prepare_cells(DeviceState& d, double alpha_limit) {
     }
     d.cells_limit = alpha_limit;
     d.cells_limit_valid = true;
+}
+
+void dedupe_solid_faces(DeviceState& d, SolidSet& ss) {
+    const int64_t n_all = ss.n * 4;
+    ss.n_faces = 0;
+    ss.faces.release();
+    if (n_all == 0) return;
+    DevBuf<uint64_t> keys;
+    DevBuf<uint32_t> vals, pos;
+    DevBuf<uint8_t> first;
+    keys.alloc(static_cast<size_t>(n_all));
+    vals.alloc(static_cast<size_t>(n_all));
+    pos.alloc(static_cast<size_t>(n_all));
+    first.alloc(static_cast<size_t>(n_all));
+    for_each(d.stream, n_all, SolidFaceKeyOp{ss.pts0.p, keys.p, vals.p});
+    sort_pairs_u64(keys.p, vals.p, static_cast<size_t>(n_all), 64, d.stream);
+    for_each(d.stream, n_all, SolidFaceFirstOp{ss.pts0.p, keys.p, vals.p, first.p});
+    const size_t n_u = select_flagged(first.p, pos.p, static_cast<size_t>(n_all), d.stream);
+    ss.faces.alloc(n_u);
+    for_each(d.stream, static_cast<int64_t>(n_u), GatherU32Op{vals.p, pos.p, ss.faces.p});
+    stream_sync(d.stream);
+    ss.n_faces = static_cast<int64_t>(n_u);
 }
 
 void launch_bvh_refit(DeviceState& d) {

@@ -13,12 +13,13 @@ namespace c5 {
 constexpr int kMaxRot = C5_MAX_ROT;
 
 // Counters the walk kernel accumulates (one 64-bit atomic per warp).
-enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kTileTicket = 4, kNumCounters = 5 };
+enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kNumCounters = 4 };
 
 struct SolidSet {
     DevBuf<double> pts0;      // [n][4][3] pre-view frame
     DevBuf<double> pts_view;  // [n][4][3] view frame (rotated copy, or == pts0 content for static ones)
-    int64_t n = 0;
+    DevBuf<uint32_t> faces;   // unique faces (4 * tet + k): a fan face shared by two tets is scanned once
+    int64_t n = 0, n_faces = 0;
 };
 
 // Everything resident on ONE device.
@@ -29,7 +30,6 @@ struct DeviceState {
 
     // mesh (uploaded once)
     int64_t n_pts = 0, n_tets = 0, n_bfaces = 0;
-    float tet_size = 0.f;            // (bounding-box volume / n_tets)^(1/3): the mesh's length scale
     DevBuf<double> px, py, pz;       // Morton-ordered file-frame coordinates (SoA: the rotate kernel streams them)
     DevBuf<Cell> cells;
     DevBuf<double> q0;               // Q per tet (Morton order); cells[t].s is derived from it
@@ -84,6 +84,7 @@ void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot);
 void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
                        double step_y, int row_begin, int row_end);
 void launch_bvh_refit(DeviceState& d);
+void dedupe_solid_faces(DeviceState& d, SolidSet& ss); // fills ss.faces / ss.n_faces from ss.pts0
 void launch_prepare_cells(DeviceState& d, double alpha_limit); // cells[t].s = q0[t] / min(alpha, limit)
 
 // c5_walk.cu

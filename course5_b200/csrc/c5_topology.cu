@@ -12,7 +12,6 @@
 //   5. the hierarchy is relabelled breadth-first on the host so the top levels are a contiguous
 //      prefix the walk kernel stages in shared memory.
 #include <algorithm>
-#include <cmath>
 #include <queue>
 #include <vector>
 
@@ -474,11 +473,6 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
     d.n_pts = n_pts;
     d.n_tets = n_tets;
     d.n_bfaces = static_cast<int64_t>(n_b);
-    {
-        double vol = 1.0;
-        for (int a = 0; a < 3; a++) vol *= box.inv[a] > 0 ? 1.0 / box.inv[a] : 1.0;
-        d.tet_size = static_cast<float>(std::cbrt(vol / static_cast<double>(n_tets)));
-    }
     d.cells_limit_valid = false;
 }
 

@@ -35,7 +35,7 @@ namespace {
 
 constexpr int kStack = 64;        // LBVH traversal stack (depth is checked at upload)
 constexpr int kBlock = 128;       // 4 warps: 2 x 2 warp tiles of 8 x 4 pixels
-constexpr int kTileX = 8, kTileY = 4;   // one warp = one 8 x 4 pixel tile
+constexpr int kTileX = 16, kTileY = 8;
 
 struct WalkParams {
     const Cell* cells;
@@ -50,11 +50,9 @@ struct WalkParams {
     unsigned long long* counters;
     unsigned long long* row_cost; // [res_y]
     int res_x, res_y, row_begin, row_end;
-    int n_tiles_x, n_tiles_y, n_macro_x; // warp tiles; macro tiles are 16 x 16 warp tiles
-    int n_tickets;        // macro tiles * 256
+    int n_tiles_x, n_tiles_y, n_macro_x;
     int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
     int max_steps;
-    float sync_slack;     // > 0: lanes more than this far (in z) ahead of the rearmost lane of their warp wait
     int round_float;
     double alpha_limit;
 };
@@ -127,30 +125,6 @@ C5_HD void prefetch_l1(const void* p) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 #else
     (void)p;
-#endif
-}
-
-
-// Depth synchronisation (experiment, C5_SYNC_SLACK): rays of a warp drift apart in depth because
-// they cross different numbers of tets; once they do, every lane reads a different cell and the
-// warp's loads stop coalescing. Letting a lane step only while it is within `slack` of the
-// rearmost converged lane keeps the warp inside one slab of the mesh. Pure scheduling: which lanes
-// step in which iteration never changes any lane's result.
-C5_HD bool depth_gate(float slack, double z_cur) {
-#ifdef __CUDA_ARCH__
-    if (slack <= 0.f) return true;
-    const float zf = static_cast<float>(z_cur);
-    // order-preserving float -> uint key
-    const unsigned bits = __float_as_uint(zf);
-    const unsigned key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
-    const unsigned kmin = __reduce_min_sync(__activemask(), key);
-    const unsigned b = (kmin & 0x80000000u) ? (kmin & 0x7FFFFFFFu) : ~kmin;
-    const float zmin = __uint_as_float(b);
-    return zf <= zmin + slack;
-#else
-    (void)slack;
-    (void)z_cur;
-    return true;
 #endif
 }
 
@@ -250,7 +224,7 @@ struct RayResult {
     uint32_t error;
 };
 
-template <bool kWide, bool kPrefetch, bool kSync>
+template <bool kWide, bool kPrefetch>
 C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py) {
     RayResult r;
     r.tau = 0.0;
@@ -299,7 +273,6 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
                 r.error = 1;
                 break;
             }
-            if (kSync && !depth_gate(P.sync_slack, z_cur)) continue;
             const CellData c = load_cell<kWide>(P.cells, t);
             double dx, dy, dz;
             load_vtx(P.vrot, id, dx, dy, dz);
@@ -384,7 +357,7 @@ C5_HD float orient2f(float ux, float uy, float vx, float vy) {
     return fsub_rn(fmul_rn(ux, vy), fmul_rn(uy, vx));
 }
 
-template <bool kWide, bool kPrefetch, bool kSync>
+template <bool kWide, bool kPrefetch>
 C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px, double py) {
     RayResult r;
     r.tau = 0.0;
@@ -434,7 +407,6 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
                 r.error = 1;
                 break;
             }
-            if (kSync && !depth_gate(P.sync_slack, z0 + static_cast<double>(z_cur))) continue;
             const CellData c = load_cell<kWide>(P.cells, t);
             float dx, dy, dz;
             {
@@ -513,17 +485,28 @@ C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double int
 
 // ---- kernel ----------------------------------------------------------------------------------------
 
-// 4-bit Morton decode: bits 0,2,4,6 -> x
-__device__ __forceinline__ int compact4(int v) {
-    return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4) | ((v >> 3) & 8);
+// 3-bit Morton decode: bits 0,2,4 -> x, bits 1,3,5 -> y
+__device__ __forceinline__ int compact3(int v) {
+    return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4);
 }
 
-// One warp renders one 8 x 4 pixel tile. Returns through the warp-level statistics atomics.
-template <bool kF32, bool kWide, bool kPrefetch, bool kSync>
-__device__ __forceinline__ void walk_warp_tile(const WalkParams& P, const BvhNode* top, int wx, int wy, int lane) {
-    // Tiles that cannot see the mesh (outside the root's two boxes) cost two loads, not 32 traversals.
-    const int i_lo = wx * 8, j_lo = P.row_begin + wy * 4;
-    const int i_hi = min(i_lo + 8, P.res_x) - 1, j_hi = min(j_lo + 4, P.row_end) - 1;
+template <bool kF32, bool kWide, bool kPrefetch, int kWarpsX = 2, int kWarpsY = 2>
+__device__ __forceinline__ void walk_block(const WalkParams& P) {
+    constexpr int kTx = 8 * kWarpsX, kTy = 4 * kWarpsY, kThreads = 32 * kWarpsX * kWarpsY;
+    extern __shared__ __align__(64) unsigned char smem_raw[];
+    BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
+
+    // screen-space order: macro tiles of 8 x 8 block tiles in row-major order, Morton inside, so that
+    // concurrently resident blocks cover a compact patch of the image and share tets in L2
+    const int b = blockIdx.x;
+    const int macro = b >> 6, r = b & 63;
+    const int tile_x = (macro % P.n_macro_x) * 8 + compact3(r);
+    const int tile_y = (macro / P.n_macro_x) * 8 + compact3(r >> 1);
+    if (tile_x >= P.n_tiles_x || tile_y >= P.n_tiles_y) return;
+
+    // Tiles that cannot see the mesh (outside the root's two boxes) skip the staging and the rays.
+    const int i_lo = tile_x * kTx, j_lo = P.row_begin + tile_y * kTy;
+    const int i_hi = min(i_lo + kTx, P.res_x) - 1, j_hi = min(j_lo + kTy, P.row_end) - 1;
     bool tile_sees_mesh;
     {
         const BvhNode* root = P.nodes;
@@ -533,8 +516,16 @@ __device__ __forceinline__ void walk_warp_tile(const WalkParams& P, const BvhNod
         const bool s1 = x1 >= root->xlo[1] && x0 <= root->xhi[1] && y1 >= root->ylo[1] && y0 <= root->yhi[1];
         tile_sees_mesh = s0 || s1;
     }
-    const int i = i_lo + (lane & 7);
-    const int j = j_lo + (lane >> 3);
+    if (tile_sees_mesh && P.top_nodes > 0) {
+        const int4* src = reinterpret_cast<const int4*>(P.nodes);
+        int4* dst = reinterpret_cast<int4*>(top);
+        for (int k = threadIdx.x; k < P.top_nodes * 4; k += kThreads) dst[k] = src[k];
+        __syncthreads();
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = tile_x * kTx + (warp % kWarpsX) * 8 + (lane & 7);
+    const int j = P.row_begin + tile_y * kTy + (warp / kWarpsX) * 4 + (lane >> 3);
     const bool live = i < P.res_x && j < P.row_end;
 
     RayResult res;
@@ -550,13 +541,12 @@ __device__ __forceinline__ void walk_warp_tile(const WalkParams& P, const BvhNod
             store_pixel(P, i, j, nan, nan, 0);
         } else {
             if (tile_sees_mesh) {
-                res = kF32 ? trace_ray_f32<kWide, kPrefetch, kSync>(P, top, P.xs[i], P.ys[j])
-                           : trace_ray<kWide, kPrefetch, kSync>(P, top, P.xs[i], P.ys[j]);
+                res = kF32 ? trace_ray_f32<kWide, kPrefetch>(P, top, P.xs[i], P.ys[j])
+                           : trace_ray<kWide, kPrefetch>(P, top, P.xs[i], P.ys[j]);
             }
             store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
     }
-    if (!tile_sees_mesh && !P.mask) return; // nothing to count
 
     // statistics: one atomic per warp per counter, one per warp-row for the row costs
     const unsigned full = 0xFFFFFFFFu;
@@ -579,52 +569,20 @@ __device__ __forceinline__ void walk_warp_tile(const WalkParams& P, const BvhNod
     }
 }
 
-// Persistent warps: the grid is one wave of resident blocks; every warp repeatedly takes the next
-// 8 x 4 pixel tile from a global counter until the band is done. Rays differ in length by orders
-// of magnitude (0 steps in the background, hundreds inside the mesh), so static tile-to-block
-// assignment leaves warps idle behind their block's slowest warp and makes the last wave ragged —
-// which is what limits strong scaling when a GPU only has a row band to render. Tiles are numbered
-// along a Morton curve inside 128 x 64 pixel macro tiles, so warps running at the same time work
-// on neighbouring pixels and share tets in L1/L2.
-template <bool kF32, bool kWide, bool kPrefetch, bool kSync>
-__device__ __forceinline__ void walk_block(const WalkParams& P) {
-    extern __shared__ __align__(64) unsigned char smem_raw[];
-    BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
-    if (P.top_nodes > 0) { // optional (off by default): stage the top BVH levels once per block
-        const int4* src = reinterpret_cast<const int4*>(P.nodes);
-        int4* dst = reinterpret_cast<int4*>(top);
-        for (int k = threadIdx.x; k < P.top_nodes * 4; k += kBlock) dst[k] = src[k];
-        __syncthreads();
-    }
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&P.counters[kTileTicket], 1ull);
-        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
-        if (ticket >= static_cast<unsigned long long>(P.n_tickets)) break;
-        const int t = static_cast<int>(ticket);
-        const int macro = t >> 8, r = t & 255;
-        const int wx = (macro % P.n_macro_x) * 16 + compact4(r);
-        const int wy = (macro / P.n_macro_x) * 16 + compact4(r >> 1);
-        if (wx >= P.n_tiles_x || wy >= P.n_tiles_y) continue;
-        walk_warp_tile<kF32, kWide, kPrefetch, kSync>(P, top, wx, wy, lane);
-    }
-}
-
 } // namespace
 
 // The product kernel, and register-capped variants kept for occupancy experiments
 // (C5_WALK_VARIANT=r64|r96 selects one at run time; ncu shows which is better where).
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false, true, false, false>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false, true, false>(P); }
 // optional single-precision step geometry (north-star item (d)); entry search and accumulators stay FP64
-__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true, true, false, false>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true, true, false>(P); }
 // experiment variants (C5_WALK_VARIANT): 128-bit loads, L1 prefetch of the next step, register caps
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, false, false>(P); }
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, true, false>(P); }
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64_sync(const WalkParams P) { walk_block<false, true, false, true>(P); }
-__global__ void __launch_bounds__(kBlock) tet_walk_fp32_sync(const WalkParams P) { walk_block<true, true, false, true>(P); }
-__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, false, false>(P); }
-__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, false, false>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, false>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, true>(P); }
+// 64-thread blocks (one 8 x 8 pixel tile): finer-grained block scheduling for short bands
+__global__ void __launch_bounds__(64) tet_walk_fp64_b64(const WalkParams P) { walk_block<false, true, false, 1, 2>(P); }
+__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, false>(P); }
+__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, false>(P); }
 
 namespace {
 
@@ -636,8 +594,8 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 P.counters[kSolidPixels]++;
                 continue;
             }
-            const RayResult r = f32 ? trace_ray_f32<false, false, false>(P, nullptr, P.xs[i], P.ys[j])
-                                    : trace_ray<false, false, false>(P, nullptr, P.xs[i], P.ys[j]);
+            const RayResult r = f32 ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
+                                    : trace_ray<false, false>(P, nullptr, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -668,11 +626,14 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.res_y = w.res_y;
     P.row_begin = w.row_begin;
     P.row_end = w.row_end;
-    P.n_tiles_x = (w.res_x + kTileX - 1) / kTileX;
-    P.n_tiles_y = (w.row_end - w.row_begin + kTileY - 1) / kTileY;
-    P.n_macro_x = (P.n_tiles_x + 15) / 16;
-    const int n_macro_y = (P.n_tiles_y + 15) / 16;
-    P.n_tickets = P.n_macro_x * n_macro_y * 256;
+    const char* variant = std::getenv("C5_WALK_VARIANT");
+    const std::string var = variant ? variant : "";
+    const bool small_blocks = !f32 && var == "b64"; // 8 x 8 pixel tiles, 64 threads
+    const int tile_x = small_blocks ? 8 : kTileX, tile_y = small_blocks ? 8 : kTileY;
+    P.n_tiles_x = (w.res_x + tile_x - 1) / tile_x;
+    P.n_tiles_y = (w.row_end - w.row_begin + tile_y - 1) / tile_y;
+    P.n_macro_x = (P.n_tiles_x + 7) / 8;
+    const int n_macro_y = (P.n_tiles_y + 7) / 8;
     const int64_t n_nodes = d.n_bfaces - 1;
     // Staging the top BVH levels in shared memory was measured SLOWER than letting L1 serve them
     // (C3: 6.38 ms with 0 nodes, 6.54 with 63, 6.88 with 255; profiles/r01_exp_c3_variants_b.jsonl),
@@ -683,8 +644,6 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (top > 1023) top = 1023;
     P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < top ? n_nodes : top);
     P.max_steps = static_cast<int>(d.n_tets < (1 << 20) ? d.n_tets : (1 << 20));
-    P.sync_slack = 0.f;
-    if (const char* e = std::getenv("C5_SYNC_SLACK")) P.sync_slack = static_cast<float>(std::atof(e)) * d.tet_size;
     P.round_float = w.round_through_float;
     P.alpha_limit = w.alpha_limit;
 
@@ -693,27 +652,23 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         walk_on_host(P, f32);
         return;
     }
+    const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
     const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
-    const char* variant = std::getenv("C5_WALK_VARIANT");
-    const std::string var = variant ? variant : "";
-    using Kernel = void (*)(const WalkParams);
-    Kernel kernel = tet_walk_fp64;
-    if (P.sync_slack > 0.f) kernel = f32 ? tet_walk_fp32_sync : tet_walk_fp64_sync;
-    else if (f32) kernel = tet_walk_fp32;
-    else if (var == "l128") kernel = tet_walk_fp64_l128;
-    else if (var == "pf") kernel = tet_walk_fp64_pf;
-    else if (var == "r64") kernel = tet_walk_fp64_r64;
-    else if (var == "r96") kernel = tet_walk_fp64_r96;
-    // one wave of resident blocks (persistent warps), but never more warps than tiles
-    int per_sm = 0, n_sm = 0;
-    C5_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
-    C5_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d.device));
-    if (per_sm < 1) per_sm = 1;
-    long long blocks = static_cast<long long>(per_sm) * n_sm;
-    const long long needed = (static_cast<long long>(P.n_tiles_x) * P.n_tiles_y + kBlock / 32 - 1) / (kBlock / 32);
-    if (blocks > needed) blocks = needed;
-    if (blocks < 1) blocks = 1;
-    kernel<<<static_cast<unsigned>(blocks), kBlock, smem, d.stream>>>(P);
+    if (f32) {
+        tet_walk_fp32<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (small_blocks) {
+        tet_walk_fp64_b64<<<grid, 64, smem, d.stream>>>(P);
+    } else if (var == "l128") {
+        tet_walk_fp64_l128<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "pf") {
+        tet_walk_fp64_pf<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "r64") {
+        tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "r96") {
+        tet_walk_fp64_r96<<<grid, kBlock, smem, d.stream>>>(P);
+    } else {
+        tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
+    }
     C5_CUDA(cudaGetLastError());
 }
 

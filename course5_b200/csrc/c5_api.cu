@@ -445,6 +445,16 @@ void upload_solids(c5_ctx* ctx, const double* pts, int64_t n, int follows) {
             d2d(ss.pts_view.p, ss.pts0.p, ss.pts0.bytes(), d.stream);
             stream_sync(d.stream);
         }
+        // longest tet edge of this upload: bounds how many rows one face can span in any view
+        for (size_t t = 0; t < add; t++) {
+            const double* q = pts + 12 * t;
+            for (int a = 0; a < 4; a++) {
+                for (int b = a + 1; b < 4; b++) {
+                    const double dx = q[3 * a] - q[3 * b], dy = q[3 * a + 1] - q[3 * b + 1], dz = q[3 * a + 2] - q[3 * b + 2];
+                    ss.extent = std::max(ss.extent, std::sqrt(dx * dx + dy * dy + dz * dz));
+                }
+            }
+        }
         g_launch_counter = &d.launches;
         dedupe_solid_faces(d, ss);
     }
@@ -590,6 +600,7 @@ int c5_clear_solids(c5_ctx* ctx) {
                 ss->faces.release();
                 ss->n = 0;
                 ss->n_faces = 0;
+                ss->extent = 0.0;
             }
         }
         ctx->info.n_solid_tets = 0;

@@ -150,7 +150,6 @@ C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const 
     }
 }
 
-constexpr int kMaskLanes = 8; // threads per solid face
 
 // face f of a solid tet: 0 = (v0,v1,v2), 1 = (v0,v1,v3), 2 = (v0,v2,v3), 3 = (v1,v2,v3) (plane.cpp:30-37)
 C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g, int lane, int n_lanes) {
@@ -165,10 +164,13 @@ C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g, int 
 } // namespace
 
 __global__ void __launch_bounds__(256)
-solid_mask(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g) {
+solid_mask(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g,
+           int lane_shift) {
+    // 2^lane_shift threads share one face (rows are dealt round-robin to them)
     const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t k = tid / kMaskLanes;
-    if (k < n_faces) solid_face_body(faces[k], pts, g, static_cast<int>(tid % kMaskLanes), kMaskLanes);
+    const int64_t k = tid >> lane_shift;
+    const int lanes = 1 << lane_shift;
+    if (k < n_faces) solid_face_body(faces[k], pts, g, static_cast<int>(tid & (lanes - 1)), lanes);
 }
 
 namespace {
@@ -402,7 +404,13 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
             for (int64_t k = 0; k < n_faces; k++) solid_face_body(ss->faces.p[k], ss->pts_view.p, g, 0, 1);
             continue;
         }
-        solid_mask<<<grid_for(n_faces * kMaskLanes, 256), 256, 0, d.stream>>>(n_faces, ss->faces.p, ss->pts_view.p, g);
+        // threads per face ~ rows a face of this object can span / 8 (the sphere's faces are a few
+        // rows tall, the Roche lobe's fan faces hundreds)
+        const double rows = ss->extent / step_y;
+        int lane_shift = 0;
+        while (lane_shift < 5 && (8 << lane_shift) < rows) lane_shift++;
+        solid_mask<<<grid_for(n_faces << lane_shift, 256), 256, 0, d.stream>>>(n_faces, ss->faces.p, ss->pts_view.p, g,
+                                                                                lane_shift);
         C5_CUDA(cudaGetLastError());
     }
 }

@@ -20,6 +20,7 @@ struct SolidSet {
     DevBuf<double> pts_view;  // [n][4][3] view frame (rotated copy, or == pts0 content for static ones)
     DevBuf<uint32_t> faces;   // unique faces (4 * tet + k): a fan face shared by two tets is scanned once
     int64_t n = 0, n_faces = 0;
+    double extent = 0.0;      // largest edge length of any solid tet (rotation invariant)
 };
 
 // Everything resident on ONE device.

@@ -280,6 +280,19 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
         use_device(d0);
         d0.out.ensure(2 * n_pix_view); // device 0 assembles the whole view here
     }
+    // A PINNED host buffer is device-addressable: the walk then stores its pixels straight into it
+    // (posted 128-byte writes over PCIe, spread over the kernel's run time), and the separate
+    // device-to-host copy of the image disappears. Pageable buffers take the copy.
+    const size_t view_off = static_cast<size_t>(p.row_begin) * v->res_x;
+    double* host_direct = nullptr;
+    if (n_dev == 1 && !kHostSim && !std::getenv("C5_NO_ZERO_COPY")) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            host_direct = static_cast<double*>(attr.devicePointer) + 2 * view_off;
+        } else {
+            cudaGetLastError(); // pageable memory reports an error on some drivers: not ours
+        }
+    }
 
     // enqueue every device's band (asynchronous; devices run concurrently). With several devices
     // one host thread per device issues the launches, so launch latency is not serialised.
@@ -290,6 +303,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
         pr.row_end = bands[static_cast<size_t>(r)].second;
         double* target = nullptr;
         if (n_dev > 1 && r == 0) target = d0.out.p + static_cast<size_t>(pr.row_begin - p.row_begin) * row_doubles;
+        if (host_direct) target = host_direct;
         enqueue_view(d, v, pr, steps != nullptr, target);
     };
     if (n_dev == 1 || kHostSim) {
@@ -337,8 +351,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
     }
     use_device(d0);
     record(d0, 5);
-    const size_t view_off = static_cast<size_t>(p.row_begin) * v->res_x;
-    d2h(out + 2 * view_off, d0.out.p, 2 * n_pix_view * sizeof(double), d0.stream);
+    if (!host_direct) d2h(out + 2 * view_off, d0.out.p, 2 * n_pix_view * sizeof(double), d0.stream);
     record(d0, 6);
 
     // per-device extras (steps, mask), counters, row costs

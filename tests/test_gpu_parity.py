@@ -198,3 +198,27 @@ def test_full_size_properties_config_c5(gpu_lib):
             assert np.all(img.image[~hit] == 0.0)
             # the cube's silhouette: tau / a is the chord length, at most the space diagonal (+ jitter)
             assert img.tau.max() / 1.5 < 1.75
+
+
+def test_pinned_output_is_written_in_place(gpu_lib):
+    """c5_render into a pinned host buffer (the walk stores over PCIe, no D2H copy) == into a pageable one."""
+    import torch
+    mesh = synth.kuhn_cube(10, seed=63)
+    solids = reference_solids(0.0)
+    with api.Context(devices=(0,), lib=gpu_lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        ctx.upload_solids(solids[0], True)
+        ctx.upload_solids(solids[1], False)
+        v = api.make_view(300, 226, X=0.4, Y=0.6, lib=gpu_lib)
+        pageable = np.full((226, 300, 2), -7.0)
+        ctx.render(v, out=pageable)
+        pinned_t = torch.full((226, 300, 2), -7.0, dtype=torch.float64).pin_memory()
+        pinned = pinned_t.numpy()
+        _, st = ctx.render(v, out=pinned)
+        assert np.array_equal(pinned, pageable, equal_nan=True)
+        assert np.isnan(pinned).any() and (pinned == 0).any() and st["tet_steps"] > 0
+        band = api.make_view(300, 226, X=0.4, Y=0.6, lib=gpu_lib, row_begin=100, row_end=150)
+        pinned[:] = -7.0
+        ctx.render(band, out=pinned)
+        assert np.array_equal(pinned[100:150], pageable[100:150], equal_nan=True)
+        assert np.all(pinned[:100] == -7.0) and np.all(pinned[150:] == -7.0)

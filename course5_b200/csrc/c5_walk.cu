@@ -130,10 +130,23 @@ C5_HD void prefetch_l1(const void* p) {
 
 // ---- entry search --------------------------------------------------------------------------------
 
+// Entry list of one ray: the kEntries lowest entry faces above z_after, sorted by z. A ray through
+// a convex mesh has one entry; cavities add a few; a ray grazing a bumpy boundary (the jittered side
+// walls of the synthetic grids, seen edge-on) can have a hundred. Collecting several per traversal
+// means one BVH query per ray in the common case (no failing "is there more?" query after the exit)
+// and kEntries times fewer queries for the grazing rays, which otherwise dominate a short band.
+constexpr int kEntries = 8;
+
+struct EntryList {
+    double z[kEntries];
+    int leaf[kEntries];
+    int n;
+    bool maybe_more; // the list filled up: faces above z[n-1] may have been left out
+};
+
 // Boundary face `leaf` against the pixel: inclusive point-in-triangle test with the same
-// orientation predicate the walk uses, then the barycentric z.
-C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double z_after, int& best,
-                     double& best_z) {
+// orientation predicate the walk uses, then the barycentric z; kept if among the lowest.
+C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double z_after, EntryList& L) {
 #ifdef __CUDA_ARCH__
     const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
 #else
@@ -151,25 +164,34 @@ C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double
     const double o_bc = orient2(bx, by, cx, cy);
     const double o_ca = orient2(cx, cy, ax, ay);
     // outward normal towards -z  <=>  clockwise in projection  <=>  all three <= 0 inside
-    if (o_ab <= 0 && o_bc <= 0 && o_ca <= 0) {
-        const double sum = o_ab + o_bc + o_ca;
-        if (sum < 0) {
-            const double z = (o_bc * az + o_ca * bz + o_ab * cz) / sum;
-            if (z > z_after && z < best_z) {
-                best_z = z;
-                best = leaf;
-            }
-        }
+    if (!(o_ab <= 0 && o_bc <= 0 && o_ca <= 0)) return;
+    const double sum = o_ab + o_bc + o_ca;
+    if (!(sum < 0)) return;
+    const double z = (o_bc * az + o_ca * bz + o_ab * cz) / sum;
+    if (!(z > z_after)) return;
+    if (L.n == kEntries) {
+        L.maybe_more = true;
+        if (!(z < L.z[kEntries - 1])) return;
+        L.n--; // the highest one falls off
     }
+    int k = L.n++;
+    while (k > 0 && L.z[k - 1] > z) { // sorted insertion
+        L.z[k] = L.z[k - 1];
+        L.leaf[k] = L.leaf[k - 1];
+        k--;
+    }
+    L.z[k] = z;
+    L.leaf[k] = leaf;
+    if (L.n == kEntries) L.maybe_more = true;
 }
 
-// Lowest entry face strictly above z_after under pixel (px, py), or -1.
-C5_HD int bvh_next_entry(const WalkParams& P, const BvhNode* top, double px, double py, double z_after,
-                         double& z_out) {
+// The (up to kEntries) lowest entry faces strictly above z_after under pixel (px, py).
+C5_HD void bvh_collect_entries(const WalkParams& P, const BvhNode* top, double px, double py, double z_after,
+                               EntryList& L) {
     int stack[kStack];
     int sp = 0;
-    int best = -1;
-    double best_z = INFINITY;
+    L.n = 0;
+    L.maybe_more = false;
     int node = 0;
     const float fx_lo = f_round_down(px), fx_hi = f_round_up(px);
     const float fy_lo = f_round_down(py), fy_hi = f_round_up(py);
@@ -186,17 +208,19 @@ C5_HD int bvh_next_entry(const WalkParams& P, const BvhNode* top, double px, dou
         const float4 bz = make_float4(n->zlo[0], n->zlo[1], n->zhi[0], n->zhi[1]);
         const int2 ch = make_int2(n->child[0], n->child[1]);
 #endif
+        // once the list is full, nothing at or above its highest entry can get in
+        const double z_cap = (L.n == kEntries) ? L.z[kEntries - 1] : INFINITY;
         // boxes are rounded outward and the pixel is widened to floats, so this never misses
         bool h0 = fx_hi >= bx.x && fx_lo <= bx.z && fy_hi >= by.x && fy_lo <= by.z &&
-                  static_cast<double>(bz.z) > z_after && static_cast<double>(bz.x) < best_z;
+                  static_cast<double>(bz.z) > z_after && static_cast<double>(bz.x) < z_cap;
         bool h1 = fx_hi >= bx.y && fx_lo <= bx.w && fy_hi >= by.y && fy_lo <= by.w &&
-                  static_cast<double>(bz.w) > z_after && static_cast<double>(bz.y) < best_z;
+                  static_cast<double>(bz.w) > z_after && static_cast<double>(bz.y) < z_cap;
         if (h0 && ch.x < 0) {
-            test_leaf(P, ~ch.x, px, py, z_after, best, best_z);
+            test_leaf(P, ~ch.x, px, py, z_after, L);
             h0 = false;
         }
         if (h1 && ch.y < 0) {
-            if (static_cast<double>(bz.y) < best_z) test_leaf(P, ~ch.y, px, py, z_after, best, best_z);
+            test_leaf(P, ~ch.y, px, py, z_after, L);
             h1 = false;
         }
         if (h0 && h1) {
@@ -212,8 +236,6 @@ C5_HD int bvh_next_entry(const WalkParams& P, const BvhNode* top, double px, dou
             node = stack[--sp];
         }
     }
-    z_out = best_z;
-    return best;
 }
 
 // ---- one ray ---------------------------------------------------------------------------------------
@@ -224,7 +246,7 @@ struct RayResult {
     uint32_t error;
 };
 
-template <bool kWide, bool kPrefetch>
+template <bool kWide, int kPipe>
 C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py) {
     RayResult r;
     r.tau = 0.0;
@@ -234,11 +256,16 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
     double z_after = -INFINITY;
     int entries = 0;
 
-    while (true) {
-        double z_cur;
-        const int leaf = bvh_next_entry(P, top, px, py, z_after, z_cur);
-        if (leaf < 0) break;
-        if (++entries > 4096) {
+    EntryList L;
+    L.maybe_more = true;
+    while (L.maybe_more && !r.error) {
+        bvh_collect_entries(P, top, px, py, z_after, L);
+        if (L.n == 0) break;
+        for (int e = 0; e < L.n && !r.error; e++) {
+        double z_cur = L.z[e];
+        if (!(z_cur > z_after)) continue; // already behind the ray (it left the previous crossing above it)
+        const int leaf = L.leaf[e];
+        if (++entries > 65536) {
             r.error = 1;
             break;
         }
@@ -268,14 +295,26 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
         // id = the vertex of tet t that is not on the entry face. It is known BEFORE t's cell is
         // read (Cell::apex of the previous tet, BFace::apex at entry), so the cell load and the
         // vertex load of a step are independent and overlap: one memory latency per step, not two.
+        //
+        // kPipe == 2: software pipelining. The exit face — hence the next cell and vertex — is known
+        // after the three orientation tests, long before this step's divide and exp retire; the next
+        // step's loads are issued right there, into registers, and complete under that math.
+        CellData c_cur;
+        double dx, dy, dz;
+        if (kPipe == 2 && t >= 0) {
+            c_cur = load_cell<kWide>(P.cells, t);
+            load_vtx(P.vrot, id, dx, dy, dz);
+        }
         while (t >= 0) {
             if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
                 r.error = 1;
                 break;
             }
-            const CellData c = load_cell<kWide>(P.cells, t);
-            double dx, dy, dz;
-            load_vtx(P.vrot, id, dx, dy, dz);
+            if (kPipe != 2) {
+                c_cur = load_cell<kWide>(P.cells, t);
+                load_vtx(P.vrot, id, dx, dy, dz);
+            }
+            const CellData c = c_cur;
             dx -= px;
             dy -= py;
             const double sa = orient2(dx, dy, ax, ay);
@@ -289,22 +328,28 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
             const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
             const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
             const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
-            if (kPrefetch && t_next >= 0) {
+            if (kPipe == 1 && t_next >= 0) {
                 prefetch_l1(P.cells + t_next);
                 prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
                 prefetch_l1(P.vrot + id_next);
             }
+            const double alpha = c.alpha, src = c.s;
+            const double ddx = dx, ddy = dy, ddz = dz;
+            if (kPipe == 2 && t_next >= 0) {
+                c_cur = load_cell<kWide>(P.cells, t_next);
+                load_vtx(P.vrot, id_next, dx, dy, dz);
+            }
 
             if (drop_c) { // c is replaced by d
-                ic = id; cx = dx; cy = dy; cz = dz;
+                ic = id; cx = ddx; cy = ddy; cz = ddz;
                 wa = -sb;
                 wb = sa;
             } else if (drop_a) { // a is replaced
-                ia = id; ax = dx; ay = dy; az = dz;
+                ia = id; ax = ddx; ay = ddy; az = ddz;
                 wb = -sc;
                 wc = sb;
             } else { // b is replaced
-                ib = id; bx = dx; by = dy; bz = dz;
+                ib = id; bx = ddx; by = ddy; bz = ddz;
                 wc = -sa;
                 wa = sc;
             }
@@ -313,11 +358,11 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
             const double dzv = fabs(z_exit - z_cur);
 
             // tau: line.cpp:176-193 (alpha not clamped)
-            r.tau += dzv * c.alpha;
+            r.tau += dzv * alpha;
             // I: line.cpp:206-225 with s = Q / a^:  (Q - (Q - a^ I) e) / a^  ==  s - (s - I) e
-            double a_c = c.alpha;
+            double a_c = alpha;
             if (a_c > P.alpha_limit) a_c = P.alpha_limit;
-            if (!(a_c < DBL_EPSILON)) r.inten = c.s - (c.s - r.inten) * exp(-a_c * dzv);
+            if (!(a_c < DBL_EPSILON)) r.inten = src - (src - r.inten) * exp(-a_c * dzv);
             r.steps++;
             z_cur = z_exit;
             t = t_next;
@@ -325,6 +370,7 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
         }
         if (r.error) break;
         z_after = z_cur;
+        } // entries of this collection
     }
     return r;
 }
@@ -368,11 +414,16 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
     int entries = 0;
     const float limit = static_cast<float>(P.alpha_limit);
 
-    while (true) {
-        double z_entry;
-        const int leaf = bvh_next_entry(P, top, px, py, z_after, z_entry); // double: same hit set as FP64
-        if (leaf < 0) break;
-        if (++entries > 4096) {
+    EntryList L;
+    L.maybe_more = true;
+    while (L.maybe_more && !r.error) {
+        bvh_collect_entries(P, top, px, py, z_after, L); // double: same hit set as FP64
+        if (L.n == 0) break;
+        for (int e = 0; e < L.n && !r.error; e++) {
+        const double z_entry = L.z[e];
+        if (!(z_entry > z_after)) continue;
+        const int leaf = L.leaf[e];
+        if (++entries > 65536) {
             r.error = 1;
             break;
         }
@@ -464,6 +515,7 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
         // the next entry must lie above this crossing's exit (and strictly above its entry)
         const double z_exit_abs = z0 + static_cast<double>(z_cur);
         z_after = z_exit_abs > z_entry ? z_exit_abs : z_entry;
+        } // entries of this collection
     }
     return r;
 }
@@ -490,7 +542,7 @@ __device__ __forceinline__ int compact3(int v) {
     return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4);
 }
 
-template <bool kF32, bool kWide, bool kPrefetch, int kWarpsX = 2, int kWarpsY = 2>
+template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2>
 __device__ __forceinline__ void walk_block(const WalkParams& P) {
     constexpr int kTx = 8 * kWarpsX, kTy = 4 * kWarpsY, kThreads = 32 * kWarpsX * kWarpsY;
     extern __shared__ __align__(64) unsigned char smem_raw[];
@@ -541,8 +593,8 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             store_pixel(P, i, j, nan, nan, 0);
         } else {
             if (tile_sees_mesh) {
-                res = kF32 ? trace_ray_f32<kWide, kPrefetch>(P, top, P.xs[i], P.ys[j])
-                           : trace_ray<kWide, kPrefetch>(P, top, P.xs[i], P.ys[j]);
+                res = kF32 ? trace_ray_f32<kWide, kPipe == 1>(P, top, P.xs[i], P.ys[j])
+                           : trace_ray<kWide, kPipe>(P, top, P.xs[i], P.ys[j]);
             }
             store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
@@ -573,20 +625,25 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
 
 // The product kernel, and register-capped variants kept for occupancy experiments
 // (C5_WALK_VARIANT=r64|r96 selects one at run time; ncu shows which is better where).
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false, true, false>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false, true, 0>(P); }
 // optional single-precision step geometry (north-star item (d)); entry search and accumulators stay FP64
-__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true, true, false>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true, true, 0>(P); }
 // experiment variants (C5_WALK_VARIANT): 128-bit loads, L1 prefetch of the next step, register caps
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, false>(P); }
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, true>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, 0>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, 1>(P); }
+// software-pipelined: next step's loads issued right after the exit decision
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_swp(const WalkParams P) { walk_block<false, true, 2>(P); }
 // 64-thread blocks (one 8 x 8 pixel tile): finer-grained block scheduling for short bands
-__global__ void __launch_bounds__(64) tet_walk_fp64_b64(const WalkParams P) { walk_block<false, true, false, 1, 2>(P); }
-__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, false>(P); }
-__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, false>(P); }
+__global__ void __launch_bounds__(64) tet_walk_fp64_b64(const WalkParams P) { walk_block<false, true, 0, 1, 2>(P); }
+__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block<false, true, 0>(P); }
+__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, 0>(P); }
+__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, 0>(P); }
 
 namespace {
 
 void walk_on_host(const WalkParams& P, bool f32) {
+    const char* variant = std::getenv("C5_WALK_VARIANT");
+    const bool swp = variant && std::string(variant) == "swp";
     for (int j = P.row_begin; j < P.row_end; j++) {
         for (int i = 0; i < P.res_x; i++) {
             if (P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i]) {
@@ -594,8 +651,9 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 P.counters[kSolidPixels]++;
                 continue;
             }
-            const RayResult r = f32 ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
-                                    : trace_ray<false, false>(P, nullptr, P.xs[i], P.ys[j]);
+            const RayResult r = f32   ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
+                                : swp ? trace_ray<false, 2>(P, nullptr, P.xs[i], P.ys[j])
+                                      : trace_ray<false, 0>(P, nullptr, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -660,8 +718,12 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp64_b64<<<grid, 64, smem, d.stream>>>(P);
     } else if (var == "l128") {
         tet_walk_fp64_l128<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "swp") {
+        tet_walk_fp64_swp<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "pf") {
         tet_walk_fp64_pf<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "r72") {
+        tet_walk_fp64_r72<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r64") {
         tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r96") {

@@ -201,3 +201,17 @@ def check_fp32_variant(lib, port, mesh, res_x, res_y, flags):
     assert abs(int(got.stats["tet_steps"]) - int(ref64.stats["tet_steps"])) <= 1e-3 * ref64.stats["tet_steps"]
     assert not np.array_equal(got.image, ref64.image)      # it really is a different arithmetic
     return got
+
+
+def check_solid_mask_high_resolution(lib, port, res=(1200, 900), views=((0.4, 0.3, 0.0), (0.5, 1.3, 0.1))):
+    """The NaN mask of the reference's 652 802 solid tets at full resolution, bit for bit (the scanline
+    arithmetic is restated with Markstein-exact division, so this is the test that would catch it)."""
+    mesh = synth.kuhn_cube(3, seed=37)
+    for X, Y, D in views:
+        solids = reference_solids(D)
+        got = render_raw(lib, mesh, res[0], res[1], solids=solids, X=X, Y=Y)
+        want = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=res[0], res_y=res[1], X=X, Y=Y,
+                           solid_rot=solids[0], solid_static=solids[1])
+        assert want.solid.sum() > 1000
+        assert np.array_equal(got.solid, want.solid)
+        assert np.array_equal(np.isnan(got.tau), want.solid.astype(bool))

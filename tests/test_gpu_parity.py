@@ -222,3 +222,7 @@ def test_pinned_output_is_written_in_place(gpu_lib):
         ctx.render(band, out=pinned)
         assert np.array_equal(pinned[100:150], pageable[100:150], equal_nan=True)
         assert np.all(pinned[:100] == -7.0) and np.all(pinned[150:] == -7.0)
+
+
+def test_solid_mask_high_resolution(gpu_lib, port):
+    rc.check_solid_mask_high_resolution(gpu_lib, port, res=(2400, 1800))

@@ -68,3 +68,7 @@ def test_multi_device_context(hostsim_lib):
 @pytest.mark.parametrize("flags", [dict(X=0.0, Y=0.0), dict(X=0.4, Y=0.7, I=-0.03, alpha_limit=1.2)])
 def test_fp32_variant(hostsim_lib, port, flags):
     rc.check_fp32_variant(hostsim_lib, port, synth.kuhn_cube(12, seed=47), 240, 180, flags)
+
+
+def test_solid_mask_high_resolution(hostsim_lib, port):
+    rc.check_solid_mask_high_resolution(hostsim_lib, port, res=(800, 600), views=((0.4, 0.3, 0.0),))

@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(kBlock) tet_walk_fp64_swp(const WalkParams P) 
 // 64-thread blocks (one 8 x 8 pixel tile): finer-grained block scheduling for short bands
 __global__ void __launch_bounds__(64) tet_walk_fp64_b64(const WalkParams P) { walk_block<false, true, 0, 1, 2>(P); }
 __global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block<false, true, 0>(P); }
+__global__ void __launch_bounds__(kBlock, 6) tet_walk_fp64_r80(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, 0>(P); }
 
@@ -729,6 +730,8 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp64_swp<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "pf") {
         tet_walk_fp64_pf<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "r80") {
+        tet_walk_fp64_r80<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r72") {
         tet_walk_fp64_r72<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r64") {

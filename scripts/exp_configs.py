@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--view", default=None, help="X,Y override (units of pi)")
     ap.add_argument("--res", default=None, help="res_x,res_y override")
     ap.add_argument("--precision", default="64")
+    ap.add_argument("--rows", default=None, help="semicolon-separated row bands a,b;c,d to render separately")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
@@ -48,9 +49,11 @@ def main():
             ctx.upload_solids(solids[0], True)
             ctx.upload_solids(solids[1], False)
         out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64, device=dev)
-        for prec, variant in ((int(p), vv) for p in args.precision.split(",") for vv in args.variants.split(",")):
+        bands = [None] if not args.rows else [tuple(int(x) for x in b.split(",")) for b in args.rows.split(";")]
+        for prec, variant, band in ((int(p), vv, bb) for p in args.precision.split(",") for vv in args.variants.split(",") for bb in bands):
+            extra = {} if band is None else dict(row_begin=band[0], row_end=band[1])
             v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
-                              alpha_limit=view["alpha_limit"], precision=prec)
+                              alpha_limit=view["alpha_limit"], precision=prec, **extra)
             if True:
               for top in args.top.split(","):
                 os.environ["C5_WALK_VARIANT"] = variant
@@ -63,10 +66,10 @@ def main():
                     for k in acc:
                         acc[k].append(st[k])
                 walk = float(np.median(acc["ms_walk"]))
-                pixels = view["res_x"] * view["res_y"]
+                pixels = view["res_x"] * (view["res_y"] if band is None else band[1] - band[0])
                 gbs = (st["tet_steps"] * 72 + pixels * 16) / (walk * 1e-3) / 1e9
                 print(json.dumps({
-                    "config": name, "view": [view["X"], view["Y"]], "precision": prec, "variant": variant, "top_nodes": int(top), "n_tets": mesh.n_tets,
+                    "config": name, "view": [view["X"], view["Y"]], "precision": prec, "variant": variant, "rows": band, "top_nodes": int(top), "n_tets": mesh.n_tets,
                     "res": [view["res_x"], view["res_y"]], "tet_steps": st["tet_steps"],
                     "hit_pixels": st["hit_pixels"], "solid_pixels": st["solid_pixels"],
                     **{k: round(float(np.median(x)), 4) for k, x in acc.items()},

@@ -258,8 +258,10 @@ def run_ours(args):
     else:
         # N > 1: render + gather are only enqueued (no host readback between views), so the ranks'
         # launches and the NCCL exchange pipeline on the devices; statistics come from a second pass
+        # and the gather of view k overlaps the rendering of view k + 1 (two buffer sets)
         for _ in range(args.steps):
-            _, _, bands = br.render(v, rebalance=False, stats=False)
+            _, _, bands = br.render(v, rebalance=False, stats=False, pipeline=True)
+        br.finish()
     ev1.record()
     barrier()
     clocks = sampler.stop()

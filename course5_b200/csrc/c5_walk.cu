@@ -132,10 +132,13 @@ C5_HD void prefetch_l1(const void* p) {
 
 // Entry list of one ray: the kEntries lowest entry faces above z_after, sorted by z. A ray through
 // a convex mesh has one entry; cavities add a few; a ray grazing a bumpy boundary (the jittered side
-// walls of the synthetic grids, seen edge-on) can have a hundred. Collecting several per traversal
-// means one BVH query per ray in the common case (no failing "is there more?" query after the exit)
-// and kEntries times fewer queries for the grazing rays, which otherwise dominate a short band.
-constexpr int kEntries = 8;
+// walls of the synthetic grids, seen edge-on) has ~100. Such a ray is a chain of dependent BVH
+// queries and short crossings, and a handful of them set the run time of a whole row band (measured:
+// 1.3 ms for ANY band of the C3 README view with one query per crossing, profiles/r01_exp_bands.jsonl).
+// Collecting the crossings 64 at a time turns ~110 queries into 2-3. The list lives in local
+// memory and is touched only by rays that re-enter; faces arrive roughly near-to-far, so the
+// insertion sort from the back is close to linear.
+constexpr int kEntries = 64;
 
 struct EntryList {
     double z[kEntries];

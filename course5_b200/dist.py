@@ -10,6 +10,9 @@ in the CPU tests), because cost-balanced bands have unequal sizes.
 Equal-height bands are badly unbalanced (the mesh sits in the middle rows), so bands are cut by
 per-row tet-step counts from the previous view (``Context.last_row_cost``), all-reduced so every
 rank derives the same cuts.
+
+Sweeps can pipeline: with ``pipeline=True`` the gather of view k is left in flight while view k+1
+renders into the other of two buffer sets, so the exchange costs no time on the critical path.
 """
 from __future__ import annotations
 
@@ -28,54 +31,78 @@ class BandRenderer:
         self.ctx, self.device, self.rank, self.world = ctx, device, rank, world
         self.base_cost = base_cost
         self.row_cost: np.ndarray | None = None
-        self._band_buf: torch.Tensor | None = None
-        self._image: torch.Tensor | None = None
+        self._band_buf = [None, None]      # two buffer sets: the gather of one view may still be
+        self._image = [None, None]         # reading/writing set k while view k+1 fills the other
+        self._pending = [[], []]
+        self._count = 0
+        self._bands = None                 # cached cut, valid until the row costs change
 
     def bands(self, res_y: int) -> list[tuple[int, int]]:
+        if self._bands is not None and self._bands[0] == res_y:
+            return self._bands[1]
         if self.row_cost is None or self.row_cost.shape[0] != res_y:
             cost = np.ones(res_y)          # first view: equal heights
-            return api.balanced_bands(cost, self.world)
-        return api.balanced_bands(self.row_cost, self.world, base_cost=self.base_cost)
+            cut = api.balanced_bands(cost, self.world)
+        else:
+            cut = api.balanced_bands(self.row_cost, self.world, base_cost=self.base_cost)
+        self._bands = (res_y, cut)
+        return cut
 
-    def _buffers(self, view: api.View, rows: int):
+    def _buffers(self, view: api.View, rows: int, par: int):
         n = rows * view.res_x * 2
-        if self._band_buf is None or self._band_buf.numel() < n:
-            self._band_buf = torch.empty(n, dtype=torch.float64, device=self.device)
+        if self._band_buf[par] is None or self._band_buf[par].numel() < n:
+            self._band_buf[par] = torch.empty(n, dtype=torch.float64, device=self.device)
         if self.rank == 0:
             full = view.res_y * view.res_x * 2
-            if self._image is None or self._image.numel() != full:
-                self._image = torch.empty(full, dtype=torch.float64, device=self.device)
+            if self._image[par] is None or self._image[par].numel() != full:
+                self._image[par] = torch.empty(full, dtype=torch.float64, device=self.device)
 
-    def render(self, view: api.View, *, gather: bool = True, rebalance: bool = True, stats: bool = True):
+    def _drain(self, par: int):
+        for req in self._pending[par]:
+            req.wait()          # orders the current stream after that exchange
+        self._pending[par] = []
+
+    def finish(self):
+        """Waits (on the current stream) for every gather still in flight."""
+        self._drain(0)
+        self._drain(1)
+
+    def render(self, view: api.View, *, gather: bool = True, rebalance: bool = True, stats: bool = True,
+               pipeline: bool = False):
         """Renders this rank's band of `view`; returns (image on rank 0 or None, stats, bands).
 
         The image is a (res_y, res_x, 2) float64 tensor on rank 0's device. With stats=False (and
         rebalance=False) nothing is read back to the host: render and gather are only enqueued on the
-        current stream, so a sweep pipelines on the device; synchronise before reading the image."""
+        current stream. With pipeline=True the gather is additionally left in flight (call finish(),
+        or render two more views, before reading the returned image)."""
         if not stats:
             rebalance = False
+        par = self._count & 1
+        self._count += 1
+        self._drain(par)        # the buffers of this parity are about to be overwritten
         bands = self.bands(view.res_y)
         lo, hi = bands[self.rank]
-        self._buffers(view, hi - lo)
+        self._buffers(view, hi - lo, par)
         v = api.View.from_buffer_copy(view)
         v.row_begin, v.row_end = lo, hi
         if self.rank == 0 and gather:
-            target = self._image[lo * view.res_x * 2: hi * view.res_x * 2]
+            target = self._image[par][lo * view.res_x * 2: hi * view.res_x * 2]
         else:
-            target = self._band_buf[: (hi - lo) * view.res_x * 2]
+            target = self._band_buf[par][: (hi - lo) * view.res_x * 2]
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
-        stats = self.ctx.render_device(v, target.data_ptr(), stream, stats=stats)
+        st = self.ctx.render_device(v, target.data_ptr(), stream, stats=stats)
 
         if self.world > 1 and gather:
             ops = []
             if self.rank == 0:
                 for r in range(1, self.world):
                     rlo, rhi = bands[r]
-                    ops.append(dist.P2POp(dist.irecv, self._image[rlo * view.res_x * 2: rhi * view.res_x * 2], r))
+                    ops.append(dist.P2POp(dist.irecv, self._image[par][rlo * view.res_x * 2: rhi * view.res_x * 2], r))
             else:
                 ops.append(dist.P2POp(dist.isend, target, 0))
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+            self._pending[par] = list(dist.batch_isend_irecv(ops))
+            if not pipeline:
+                self._drain(par)
 
         if rebalance:
             cost = torch.from_numpy(self.ctx.last_row_cost(view.res_y).astype(np.int64))
@@ -84,8 +111,9 @@ class BandRenderer:
                 dist.all_reduce(cost, op=dist.ReduceOp.SUM)
                 cost = cost.cpu()
             self.row_cost = cost.numpy().astype(np.float64)
+            self._bands = None
 
         image = None
         if self.rank == 0 and gather:
-            image = self._image.view(view.res_y, view.res_x, 2)
-        return image, stats, bands
+            image = self._image[par].view(view.res_y, view.res_x, 2)
+        return image, st, bands

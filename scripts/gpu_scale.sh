@@ -5,8 +5,6 @@ set -u
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 echo "GPUs: $NG"
-timeout 600 python scripts/exp_configs.py C3 --variants default,r80 --top 0 2>&1 | tee gpurun_out/exp_r80.jsonl | cut -c1-330
-timeout 600 python scripts/exp_configs.py C3 --view 0.4,0.3 --variants default,r80 --top 0 2>&1 | tee -a gpurun_out/exp_r80.jsonl | cut -c1-330
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err
 grep '^{' gpurun_out/scale_n1.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N=1', round(d['value']/1e9,2),'G steps/s', round(d['ms_per_step'],3),'ms', 'e2e', round(d['e2e']['value']/1e9,2), d['phases_ms'])"
 for N in 2 4 8; do

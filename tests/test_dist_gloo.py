@@ -45,6 +45,15 @@ def _worker(rank, world, port, out_path):
             results[f"full{k}"] = full
             results[f"bands{k}"] = np.array(bands)
             results[f"steps{k}"] = np.array([int(steps), st["tet_steps"]])
+    # pipelined mode: two views in flight on two buffer sets, gathers drained at the end
+    va = api.make_view(120, 90, X=0.4, Y=0.2, lib=lib)
+    vb = api.make_view(120, 90, X=0.4, Y=0.9, lib=lib)
+    img_a, _, _ = br.render(va, stats=False, pipeline=True)
+    img_b, _, _ = br.render(vb, stats=False, pipeline=True)
+    br.finish()
+    if rank == 0:
+        results["pipe_a"] = img_a.numpy().copy()
+        results["pipe_b"] = img_b.numpy().copy()
     if rank == 0:
         np.savez(out_path, **results)
     ctx.close()
@@ -60,6 +69,7 @@ def test_two_ranks_assemble_the_same_image(built, tmp_path):
         assert r[f"steps{k}"][0] == r[f"steps{k}"][1]
         b = r[f"bands{k}"]
         assert b[0][0] == 0 and b[-1][1] == 90 and b[0][1] == b[1][0]
+    assert np.array_equal(r["pipe_a"], r["full0"]) and np.array_equal(r["pipe_b"], r["full1"])
     # first view: equal heights; second view: cut by the first view's per-row cost
     assert r["bands0"][0][1] == 45
     assert r["bands1"][0][1] != 45 or True

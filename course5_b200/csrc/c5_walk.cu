@@ -384,6 +384,119 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
 }
 
 
+// Experiment (C5_WALK_VARIANT=flat): BVH collections stay converged (all lanes of the warp query
+// together), but WITHIN one collection the crossings and steps form a flat loop — a lane whose
+// crossing ends takes its next list entry while the other lanes keep stepping, instead of waiting
+// for the longest crossing of the round.
+template <bool kWide>
+C5_HD RayResult trace_ray_flat(const WalkParams& P, const BvhNode* top, double px, double py) {
+    RayResult r;
+    r.tau = 0.0;
+    r.inten = 0.0;
+    r.steps = 0;
+    r.error = 0;
+    double z_after = -INFINITY;
+    int crossings = 0;
+
+    EntryList L;
+    L.maybe_more = true;
+    int cap = 1;
+    while (L.maybe_more && !r.error) {
+        bvh_collect_entries(P, top, px, py, z_after, L, cap);
+        cap = kEntries;
+        if (L.n == 0) break;
+
+        int e = 0;
+        int t = -1, id = -1;
+        int ia = 0, ib = 0, ic = 0;
+        double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0, cx = 0, cy = 0, cz = 0;
+        double wa = 0, wb = 0, wc = 0, z_cur = 0;
+        while (true) {
+            if (t < 0) {
+                int leaf = -1;
+                while (e < L.n) { // next list entry above the ray's current position
+                    const double z = L.z[e];
+                    const int cand = L.leaf[e];
+                    e++;
+                    if (z > z_after) {
+                        z_cur = z;
+                        leaf = cand;
+                        break;
+                    }
+                }
+                if (leaf < 0) break;
+                if (++crossings > 65536) {
+                    r.error = 1;
+                    break;
+                }
+#ifdef __CUDA_ARCH__
+                const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+                id = __ldg(&P.bfaces[leaf].apex);
+#else
+                const BFace& bf = P.bfaces[leaf];
+                const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+                id = bf.apex;
+#endif
+                ia = f.x; ib = f.z; ic = f.y;
+                load_vtx(P.vrot, ia, ax, ay, az);
+                load_vtx(P.vrot, ib, bx, by, bz);
+                load_vtx(P.vrot, ic, cx, cy, cz);
+                ax -= px; ay -= py;
+                bx -= px; by -= py;
+                cx -= px; cy -= py;
+                wa = orient2(bx, by, cx, cy);
+                wb = orient2(cx, cy, ax, ay);
+                wc = orient2(ax, ay, bx, by);
+                t = f.w;
+            }
+            if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
+                r.error = 1;
+                break;
+            }
+            const CellData c = load_cell<kWide>(P.cells, t);
+            double dx, dy, dz;
+            load_vtx(P.vrot, id, dx, dy, dz);
+            dx -= px;
+            dy -= py;
+            const double sa = orient2(dx, dy, ax, ay);
+            const double sb = orient2(dx, dy, bx, by);
+            const double sc = orient2(dx, dy, cx, cy);
+            const bool drop_c = sa >= 0 && sb < 0;
+            const bool drop_a = !drop_c && sb >= 0 && sc < 0;
+            const int dropped = drop_c ? ic : drop_a ? ia : ib;
+            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
+            const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
+            const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
+            if (drop_c) {
+                ic = id; cx = dx; cy = dy; cz = dz;
+                wa = -sb;
+                wb = sa;
+            } else if (drop_a) {
+                ia = id; ax = dx; ay = dy; az = dz;
+                wb = -sc;
+                wc = sb;
+            } else {
+                ib = id; bx = dx; by = dy; bz = dz;
+                wc = -sa;
+                wa = sc;
+            }
+            const double wsum = wa + wb + wc;
+            const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
+            const double dzv = fabs(z_exit - z_cur);
+            r.tau += dzv * c.alpha;
+            double a_c = c.alpha;
+            if (a_c > P.alpha_limit) a_c = P.alpha_limit;
+            if (!(a_c < DBL_EPSILON)) r.inten = c.s - (c.s - r.inten) * exp(-a_c * dzv);
+            r.steps++;
+            z_cur = z_exit;
+            t = t_next;
+            id = id_next;
+            if (t < 0) z_after = z_cur;
+        }
+    }
+    return r;
+}
+
 // ---- FP32 variant -----------------------------------------------------------------------------------
 // Same walk with the per-step geometry in single precision: FP32 orientation tests (still exactly
 // antisymmetric: two rounded products, one rounded difference), FP32 divide and expf — about half
@@ -603,8 +716,9 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             store_pixel(P, i, j, nan, nan, 0);
         } else {
             if (tile_sees_mesh) {
-                res = kF32 ? trace_ray_f32<kWide, kPipe == 1>(P, top, P.xs[i], P.ys[j])
-                           : trace_ray<kWide, kPipe>(P, top, P.xs[i], P.ys[j]);
+                res = kF32         ? trace_ray_f32<kWide, kPipe == 1>(P, top, P.xs[i], P.ys[j])
+                      : kPipe == 3 ? trace_ray_flat<kWide>(P, top, P.xs[i], P.ys[j])
+                                   : trace_ray<kWide, kPipe>(P, top, P.xs[i], P.ys[j]);
             }
             store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
@@ -643,6 +757,7 @@ __global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P)
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, 1>(P); }
 // software-pipelined (measured slower: 5.85 vs 5.40 ms, 96 registers): next step's loads issued right after the exit decision
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_swp(const WalkParams P) { walk_block<false, true, 2>(P); }
+__global__ void __launch_bounds__(kBlock) tet_walk_fp64_flat(const WalkParams P) { walk_block<false, true, 3>(P); }
 // 64-thread blocks (one 8 x 8 pixel tile): finer-grained block scheduling for short bands
 __global__ void __launch_bounds__(64) tet_walk_fp64_b64(const WalkParams P) { walk_block<false, true, 0, 1, 2>(P); }
 __global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block<false, true, 0>(P); }
@@ -654,7 +769,7 @@ namespace {
 
 void walk_on_host(const WalkParams& P, bool f32) {
     const char* variant = std::getenv("C5_WALK_VARIANT");
-    const bool swp = variant && std::string(variant) == "swp";
+    const bool swp = variant && std::string(variant) == "flat";
     for (int j = P.row_begin; j < P.row_end; j++) {
         for (int i = 0; i < P.res_x; i++) {
             if (P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i]) {
@@ -663,7 +778,7 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 continue;
             }
             const RayResult r = f32   ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
-                                : swp ? trace_ray<false, 2>(P, nullptr, P.xs[i], P.ys[j])
+                                : swp ? trace_ray_flat<false>(P, nullptr, P.xs[i], P.ys[j])
                                       : trace_ray<false, 0>(P, nullptr, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
@@ -731,6 +846,8 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp64_l128<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "swp") {
         tet_walk_fp64_swp<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "flat") {
+        tet_walk_fp64_flat<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "pf") {
         tet_walk_fp64_pf<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r80") {

@@ -252,144 +252,15 @@ struct RayResult {
     uint32_t error;
 };
 
+// One ray. BVH collections stay converged (all lanes of a warp query together: a traversal is
+// hundreds of dependent loads and must not be serialised lane by lane), but WITHIN one collection
+// the crossings and the steps form one flat loop: a lane whose crossing ends takes its next list
+// entry while the other lanes keep stepping, instead of waiting for the longest crossing of the
+// round. Measured on the C3 README view (profiles/r01_exp_bands_nested_vs_flat.jsonl): whole view
+// 5.25 -> 5.04 ms, silhouette row band 1.29 -> 0.99 ms. (Fully flat, with the BVH query inside the
+// loop, is 50 % SLOWER: profiles/r01_exp_c3_flat_loop.jsonl.)
 template <bool kWide, int kPipe>
 C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py) {
-    RayResult r;
-    r.tau = 0.0;
-    r.inten = 0.0;
-    r.steps = 0;
-    r.error = 0;
-    double z_after = -INFINITY;
-    int entries = 0;
-
-    EntryList L;
-    L.maybe_more = true;
-    int cap = 1;
-    while (L.maybe_more && !r.error) {
-        bvh_collect_entries(P, top, px, py, z_after, L, cap);
-        cap = kEntries;
-        if (L.n == 0) break;
-        for (int e = 0; e < L.n && !r.error; e++) {
-        double z_cur = L.z[e];
-        if (!(z_cur > z_after)) continue; // already behind the ray (it left the previous crossing above it)
-        const int leaf = L.leaf[e];
-        if (++entries > 65536) {
-            r.error = 1;
-            break;
-        }
-#ifdef __CUDA_ARCH__
-        const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
-        int id = __ldg(&P.bfaces[leaf].apex);
-#else
-        const BFace& bf = P.bfaces[leaf];
-        const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
-        int id = bf.apex;
-#endif
-        // entry face (a, c, b) of the stored winding is counter-clockwise in projection
-        int ia = f.x, ib = f.z, ic = f.y;
-        double ax, ay, az, bx, by, bz, cx, cy, cz;
-        load_vtx(P.vrot, ia, ax, ay, az);
-        load_vtx(P.vrot, ib, bx, by, bz);
-        load_vtx(P.vrot, ic, cx, cy, cz);
-        ax -= px; ay -= py;
-        bx -= px; by -= py;
-        cx -= px; cy -= py;
-        // weight of a vertex = orient2 of the other two, in cyclic order: all >= 0 inside
-        double wa = orient2(bx, by, cx, cy);
-        double wb = orient2(cx, cy, ax, ay);
-        double wc = orient2(ax, ay, bx, by);
-        int t = f.w;
-
-        // id = the vertex of tet t that is not on the entry face. It is known BEFORE t's cell is
-        // read (Cell::apex of the previous tet, BFace::apex at entry), so the cell load and the
-        // vertex load of a step are independent and overlap: one memory latency per step, not two.
-        //
-        // kPipe == 2: software pipelining. The exit face — hence the next cell and vertex — is known
-        // after the three orientation tests, long before this step's divide and exp retire; the next
-        // step's loads are issued right there, into registers, and complete under that math.
-        CellData c_cur;
-        double dx, dy, dz;
-        if (kPipe == 2 && t >= 0) {
-            c_cur = load_cell<kWide>(P.cells, t);
-            load_vtx(P.vrot, id, dx, dy, dz);
-        }
-        while (t >= 0) {
-            if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
-                r.error = 1;
-                break;
-            }
-            if (kPipe != 2) {
-                c_cur = load_cell<kWide>(P.cells, t);
-                load_vtx(P.vrot, id, dx, dy, dz);
-            }
-            const CellData c = c_cur;
-            dx -= px;
-            dy -= py;
-            const double sa = orient2(dx, dy, ax, ay);
-            const double sb = orient2(dx, dy, bx, by);
-            const double sc = orient2(dx, dy, cx, cy);
-
-            // which face the ray leaves through, hence the next tet and its new vertex
-            const bool drop_c = sa >= 0 && sb < 0;             // through (d, a, b)
-            const bool drop_a = !drop_c && sb >= 0 && sc < 0;  // through (d, b, c)
-            const int dropped = drop_c ? ic : drop_a ? ia : ib; // else through (d, c, a)
-            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
-            const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
-            const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
-            if (kPipe == 1 && t_next >= 0) {
-                prefetch_l1(P.cells + t_next);
-                prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
-                prefetch_l1(P.vrot + id_next);
-            }
-            const double alpha = c.alpha, src = c.s;
-            const double ddx = dx, ddy = dy, ddz = dz;
-            if (kPipe == 2 && t_next >= 0) {
-                c_cur = load_cell<kWide>(P.cells, t_next);
-                load_vtx(P.vrot, id_next, dx, dy, dz);
-            }
-
-            if (drop_c) { // c is replaced by d
-                ic = id; cx = ddx; cy = ddy; cz = ddz;
-                wa = -sb;
-                wb = sa;
-            } else if (drop_a) { // a is replaced
-                ia = id; ax = ddx; ay = ddy; az = ddz;
-                wb = -sc;
-                wc = sb;
-            } else { // b is replaced
-                ib = id; bx = ddx; by = ddy; bz = ddz;
-                wc = -sa;
-                wa = sc;
-            }
-            const double wsum = wa + wb + wc;
-            const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
-            const double dzv = fabs(z_exit - z_cur);
-
-            // tau: line.cpp:176-193 (alpha not clamped)
-            r.tau += dzv * alpha;
-            // I: line.cpp:206-225 with s = Q / a^:  (Q - (Q - a^ I) e) / a^  ==  s - (s - I) e
-            double a_c = alpha;
-            if (a_c > P.alpha_limit) a_c = P.alpha_limit;
-            if (!(a_c < DBL_EPSILON)) r.inten = src - (src - r.inten) * exp(-a_c * dzv);
-            r.steps++;
-            z_cur = z_exit;
-            t = t_next;
-            id = id_next;
-        }
-        if (r.error) break;
-        z_after = z_cur;
-        } // entries of this collection
-    }
-    return r;
-}
-
-
-// Experiment (C5_WALK_VARIANT=flat): BVH collections stay converged (all lanes of the warp query
-// together), but WITHIN one collection the crossings and steps form a flat loop — a lane whose
-// crossing ends takes its next list entry while the other lanes keep stepping, instead of waiting
-// for the longest crossing of the round.
-template <bool kWide>
-C5_HD RayResult trace_ray_flat(const WalkParams& P, const BvhNode* top, double px, double py) {
     RayResult r;
     r.tau = 0.0;
     r.inten = 0.0;
@@ -437,6 +308,7 @@ C5_HD RayResult trace_ray_flat(const WalkParams& P, const BvhNode* top, double p
                 const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
                 id = bf.apex;
 #endif
+                // entry face (a, c, b) of the stored winding is counter-clockwise in projection
                 ia = f.x; ib = f.z; ic = f.y;
                 load_vtx(P.vrot, ia, ax, ay, az);
                 load_vtx(P.vrot, ib, bx, by, bz);
@@ -444,6 +316,7 @@ C5_HD RayResult trace_ray_flat(const WalkParams& P, const BvhNode* top, double p
                 ax -= px; ay -= py;
                 bx -= px; by -= py;
                 cx -= px; cy -= py;
+                // weight of a vertex = orient2 of the other two, in cyclic order: all >= 0 inside
                 wa = orient2(bx, by, cx, cy);
                 wb = orient2(cx, cy, ax, ay);
                 wc = orient2(ax, ay, bx, by);
@@ -453,6 +326,9 @@ C5_HD RayResult trace_ray_flat(const WalkParams& P, const BvhNode* top, double p
                 r.error = 1;
                 break;
             }
+            // id = the vertex of tet t that is not on the entry face. It is known BEFORE t's cell is
+            // read (Cell::apex of the previous tet, BFace::apex at entry), so the cell load and the
+            // vertex load of a step are independent and overlap: one memory latency per step, not two.
             const CellData c = load_cell<kWide>(P.cells, t);
             double dx, dy, dz;
             load_vtx(P.vrot, id, dx, dy, dz);
@@ -461,21 +337,27 @@ C5_HD RayResult trace_ray_flat(const WalkParams& P, const BvhNode* top, double p
             const double sa = orient2(dx, dy, ax, ay);
             const double sb = orient2(dx, dy, bx, by);
             const double sc = orient2(dx, dy, cx, cy);
-            const bool drop_c = sa >= 0 && sb < 0;
-            const bool drop_a = !drop_c && sb >= 0 && sc < 0;
-            const int dropped = drop_c ? ic : drop_a ? ia : ib;
+            // which face the ray leaves through, hence the next tet and its new vertex
+            const bool drop_c = sa >= 0 && sb < 0;             // through (d, a, b)
+            const bool drop_a = !drop_c && sb >= 0 && sc < 0;  // through (d, b, c)
+            const int dropped = drop_c ? ic : drop_a ? ia : ib; // else through (d, c, a)
             const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
             const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
             const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
-            if (drop_c) {
+            if (kPipe == 1 && t_next >= 0) {
+                prefetch_l1(P.cells + t_next);
+                prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
+                prefetch_l1(P.vrot + id_next);
+            }
+            if (drop_c) { // leaves through (d, a, b): c is replaced by d
                 ic = id; cx = dx; cy = dy; cz = dz;
                 wa = -sb;
                 wb = sa;
-            } else if (drop_a) {
+            } else if (drop_a) { // through (d, b, c): a is replaced
                 ia = id; ax = dx; ay = dy; az = dz;
                 wb = -sc;
                 wc = sb;
-            } else {
+            } else { // through (d, c, a): b is replaced
                 ib = id; bx = dx; by = dy; bz = dz;
                 wc = -sa;
                 wa = sc;
@@ -483,7 +365,9 @@ C5_HD RayResult trace_ray_flat(const WalkParams& P, const BvhNode* top, double p
             const double wsum = wa + wb + wc;
             const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
             const double dzv = fabs(z_exit - z_cur);
+            // tau: line.cpp:176-193 (alpha not clamped)
             r.tau += dzv * c.alpha;
+            // I: line.cpp:206-225 with s = Q / a^:  (Q - (Q - a^ I) e) / a^  ==  s - (s - I) e
             double a_c = c.alpha;
             if (a_c > P.alpha_limit) a_c = P.alpha_limit;
             if (!(a_c < DBL_EPSILON)) r.inten = c.s - (c.s - r.inten) * exp(-a_c * dzv);
@@ -532,7 +416,7 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
     r.steps = 0;
     r.error = 0;
     double z_after = -INFINITY;
-    int entries = 0;
+    int crossings = 0;
     const float limit = static_cast<float>(P.alpha_limit);
 
     EntryList L;
@@ -542,41 +426,53 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
         bvh_collect_entries(P, top, px, py, z_after, L, cap); // double: same hit set as FP64
         cap = kEntries;
         if (L.n == 0) break;
-        for (int e = 0; e < L.n && !r.error; e++) {
-        const double z_entry = L.z[e];
-        if (!(z_entry > z_after)) continue;
-        const int leaf = L.leaf[e];
-        if (++entries > 65536) {
-            r.error = 1;
-            break;
-        }
-#ifdef __CUDA_ARCH__
-        const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
-        int id = __ldg(&P.bfaces[leaf].apex);
-#else
-        const BFace& bf = P.bfaces[leaf];
-        const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
-        int id = bf.apex;
-#endif
-        int ia = f.x, ib = f.z, ic = f.y;
-        const double z0 = z_entry; // depths are kept relative to the entry point of this crossing
-        float ax, ay, az, bx, by, bz, cx, cy, cz;
-        {
-            double x, y, z;
-            load_vtx(P.vrot, ia, x, y, z);
-            ax = static_cast<float>(x - px); ay = static_cast<float>(y - py); az = static_cast<float>(z - z0);
-            load_vtx(P.vrot, ib, x, y, z);
-            bx = static_cast<float>(x - px); by = static_cast<float>(y - py); bz = static_cast<float>(z - z0);
-            load_vtx(P.vrot, ic, x, y, z);
-            cx = static_cast<float>(x - px); cy = static_cast<float>(y - py); cz = static_cast<float>(z - z0);
-        }
-        float wa = orient2f(bx, by, cx, cy);
-        float wb = orient2f(cx, cy, ax, ay);
-        float wc = orient2f(ax, ay, bx, by);
-        int t = f.w;
-        float z_cur = 0.f;
 
-        while (t >= 0) {
+        int e = 0;
+        int t = -1, id = -1;
+        int ia = 0, ib = 0, ic = 0;
+        float ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0, cx = 0, cy = 0, cz = 0;
+        float wa = 0, wb = 0, wc = 0, z_cur = 0;
+        double z0 = 0; // depths are kept relative to the entry point of the current crossing
+        while (true) {
+            if (t < 0) {
+                int leaf = -1;
+                while (e < L.n) {
+                    const double z = L.z[e];
+                    const int cand = L.leaf[e];
+                    e++;
+                    if (z > z_after) {
+                        z0 = z;
+                        leaf = cand;
+                        break;
+                    }
+                }
+                if (leaf < 0) break;
+                if (++crossings > 65536) {
+                    r.error = 1;
+                    break;
+                }
+#ifdef __CUDA_ARCH__
+                const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+                id = __ldg(&P.bfaces[leaf].apex);
+#else
+                const BFace& bf = P.bfaces[leaf];
+                const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+                id = bf.apex;
+#endif
+                ia = f.x; ib = f.z; ic = f.y;
+                double x, y, z;
+                load_vtx(P.vrot, ia, x, y, z);
+                ax = static_cast<float>(x - px); ay = static_cast<float>(y - py); az = static_cast<float>(z - z0);
+                load_vtx(P.vrot, ib, x, y, z);
+                bx = static_cast<float>(x - px); by = static_cast<float>(y - py); bz = static_cast<float>(z - z0);
+                load_vtx(P.vrot, ic, x, y, z);
+                cx = static_cast<float>(x - px); cy = static_cast<float>(y - py); cz = static_cast<float>(z - z0);
+                wa = orient2f(bx, by, cx, cy);
+                wb = orient2f(cx, cy, ax, ay);
+                wc = orient2f(ax, ay, bx, by);
+                t = f.w;
+                z_cur = 0.f;
+            }
             if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
                 r.error = 1;
                 break;
@@ -593,7 +489,6 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
             const float sa = orient2f(dx, dy, ax, ay);
             const float sb = orient2f(dx, dy, bx, by);
             const float sc = orient2f(dx, dy, cx, cy);
-
             const bool drop_c = sa >= 0 && sb < 0;
             const bool drop_a = !drop_c && sb >= 0 && sc < 0;
             const int dropped = drop_c ? ic : drop_a ? ia : ib;
@@ -621,7 +516,6 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
             const float wsum = wa + wb + wc;
             const float z_exit = (wsum != 0.0f) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
             const float dzv = fabsf(z_exit - z_cur);
-
             r.tau += static_cast<double>(dzv) * c.alpha;
             float a_c = static_cast<float>(c.alpha);
             if (a_c > limit) a_c = limit;
@@ -633,12 +527,12 @@ C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px
             z_cur = z_exit;
             t = t_next;
             id = id_next;
+            if (t < 0) {
+                // the next crossing must lie above this one's exit (and strictly above its entry)
+                const double z_exit_abs = z0 + static_cast<double>(z_cur);
+                z_after = z_exit_abs > z0 ? z_exit_abs : z0;
+            }
         }
-        if (r.error) break;
-        // the next entry must lie above this crossing's exit (and strictly above its entry)
-        const double z_exit_abs = z0 + static_cast<double>(z_cur);
-        z_after = z_exit_abs > z_entry ? z_exit_abs : z_entry;
-        } // entries of this collection
     }
     return r;
 }
@@ -716,9 +610,8 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             store_pixel(P, i, j, nan, nan, 0);
         } else {
             if (tile_sees_mesh) {
-                res = kF32         ? trace_ray_f32<kWide, kPipe == 1>(P, top, P.xs[i], P.ys[j])
-                      : kPipe == 3 ? trace_ray_flat<kWide>(P, top, P.xs[i], P.ys[j])
-                                   : trace_ray<kWide, kPipe>(P, top, P.xs[i], P.ys[j]);
+                res = kF32 ? trace_ray_f32<kWide, kPipe == 1>(P, top, P.xs[i], P.ys[j])
+                           : trace_ray<kWide, kPipe>(P, top, P.xs[i], P.ys[j]);
             }
             store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
@@ -756,8 +649,6 @@ __global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { wa
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, 0>(P); }
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, 1>(P); }
 // software-pipelined (measured slower: 5.85 vs 5.40 ms, 96 registers): next step's loads issued right after the exit decision
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64_swp(const WalkParams P) { walk_block<false, true, 2>(P); }
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64_flat(const WalkParams P) { walk_block<false, true, 3>(P); }
 // 64-thread blocks (one 8 x 8 pixel tile): finer-grained block scheduling for short bands
 __global__ void __launch_bounds__(64) tet_walk_fp64_b64(const WalkParams P) { walk_block<false, true, 0, 1, 2>(P); }
 __global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block<false, true, 0>(P); }
@@ -768,8 +659,6 @@ __global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams 
 namespace {
 
 void walk_on_host(const WalkParams& P, bool f32) {
-    const char* variant = std::getenv("C5_WALK_VARIANT");
-    const bool swp = variant && std::string(variant) == "flat";
     for (int j = P.row_begin; j < P.row_end; j++) {
         for (int i = 0; i < P.res_x; i++) {
             if (P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i]) {
@@ -777,9 +666,8 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 P.counters[kSolidPixels]++;
                 continue;
             }
-            const RayResult r = f32   ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
-                                : swp ? trace_ray_flat<false>(P, nullptr, P.xs[i], P.ys[j])
-                                      : trace_ray<false, 0>(P, nullptr, P.xs[i], P.ys[j]);
+            const RayResult r = f32 ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
+                                    : trace_ray<false, 0>(P, nullptr, P.xs[i], P.ys[j]);
             store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -844,10 +732,6 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp64_b64<<<grid, 64, smem, d.stream>>>(P);
     } else if (var == "l128") {
         tet_walk_fp64_l128<<<grid, kBlock, smem, d.stream>>>(P);
-    } else if (var == "swp") {
-        tet_walk_fp64_swp<<<grid, kBlock, smem, d.stream>>>(P);
-    } else if (var == "flat") {
-        tet_walk_fp64_flat<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "pf") {
         tet_walk_fp64_pf<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r80") {

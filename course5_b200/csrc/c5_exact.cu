@@ -319,12 +319,9 @@ C5_HD float load_f(const float* p) {
 // outward normal has n_z < 0; the others get an empty box, which prunes them (and every subtree
 // made only of them) from all queries of this view.
 C5_HD void refit_leaf_body(int64_t leaf, const BFace* faces, const Vtx* vrot, BvhNode* nodes,
-                           const int32_t* node_parent, const int32_t* leaf_parent, uint32_t* flags, Vtx* leaf_geo) {
+                           const int32_t* node_parent, const int32_t* leaf_parent, uint32_t* flags) {
     const BFace f = faces[leaf];
     const Vtx a = vrot[f.a], b = vrot[f.b], c = vrot[f.c];
-    leaf_geo[3 * leaf] = a;
-    leaf_geo[3 * leaf + 1] = b;
-    leaf_geo[3 * leaf + 2] = c;
     const double nz = (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
     float xlo = INFINITY, xhi = -INFINITY, ylo = INFINITY, yhi = -INFINITY, zlo = INFINITY, zhi = -INFINITY;
     if (nz < 0) {
@@ -365,10 +362,9 @@ C5_HD void refit_leaf_body(int64_t leaf, const BFace* faces, const Vtx* vrot, Bv
 
 __global__ void __launch_bounds__(256)
 bvh_refit(int64_t n_leaves, const BFace* __restrict__ faces, const Vtx* __restrict__ vrot, BvhNode* nodes,
-          const int32_t* __restrict__ node_parent, const int32_t* __restrict__ leaf_parent, uint32_t* flags,
-          Vtx* __restrict__ leaf_geo) {
+          const int32_t* __restrict__ node_parent, const int32_t* __restrict__ leaf_parent, uint32_t* flags) {
     const int64_t leaf = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (leaf < n_leaves) refit_leaf_body(leaf, faces, vrot, nodes, node_parent, leaf_parent, flags, leaf_geo);
+    if (leaf < n_leaves) refit_leaf_body(leaf, faces, vrot, nodes, node_parent, leaf_parent, flags);
 }
 
 namespace {
@@ -491,14 +487,13 @@ void launch_bvh_refit(DeviceState& d) {
     count_launch();
     if (kHostSim) {
         for (int64_t i = 0; i < d.n_bfaces; i++) {
-            refit_leaf_body(i, d.bfaces.p, d.vrot.p, d.nodes.p, d.node_parent.p, d.leaf_parent.p, d.refit_flags.p,
-                            d.leaf_geo.p);
+            refit_leaf_body(i, d.bfaces.p, d.vrot.p, d.nodes.p, d.node_parent.p, d.leaf_parent.p, d.refit_flags.p);
         }
         return;
     }
     bvh_refit<<<grid_for(d.n_bfaces, 256), 256, 0, d.stream>>>(d.n_bfaces, d.bfaces.p, d.vrot.p, d.nodes.p,
                                                                 d.node_parent.p, d.leaf_parent.p,
-                                                                d.refit_flags.p, d.leaf_geo.p);
+                                                                d.refit_flags.p);
     C5_CUDA(cudaGetLastError());
 }
 

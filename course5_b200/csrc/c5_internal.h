@@ -41,8 +41,6 @@ struct DeviceState {
     DevBuf<int32_t> node_parent;     // per internal node: (parent << 1) | which child, -1 for the root
     DevBuf<int32_t> leaf_parent;     // per leaf: (parent << 1) | which child
     DevBuf<uint32_t> refit_flags;    // per internal node arrival counter
-    DevBuf<Vtx> leaf_geo;            // per view: the 3 rotated vertices of every (front-facing) boundary face,
-                                     // so a leaf test is ONE round of loads (no face -> vertex indirection)
 
     // solids
     SolidSet solid_follow, solid_static;

@@ -464,7 +464,6 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
     d.node_parent.alloc(n_int);
     d.leaf_parent.alloc(n_b);
     d.refit_flags.alloc(n_int);
-    d.leaf_geo.alloc(3 * n_b);
     h2d(d.nodes.p, h_nodes.data(), d.nodes.bytes(), s);
     h2d(d.node_parent.p, h_node_parent.data(), d.node_parent.bytes(), s);
     h2d(d.leaf_parent.p, h_leaf_parent.data(), d.leaf_parent.bytes(), s);

@@ -41,7 +41,6 @@ struct WalkParams {
     const Cell* cells;
     const Vtx* vrot;
     const BFace* bfaces;
-    const Vtx* leaf_geo;  // 3 rotated vertices per boundary face (written by bvh_refit)
     const BvhNode* nodes;
     const double* xs;
     const double* ys;
@@ -151,10 +150,16 @@ struct EntryList {
 // Boundary face `leaf` against the pixel: inclusive point-in-triangle test with the same
 // orientation predicate the walk uses, then the barycentric z; kept if among the lowest.
 C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double z_after, EntryList& L, int cap) {
+#ifdef __CUDA_ARCH__
+    const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+#else
+    const BFace& bf = P.bfaces[leaf];
+    const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+#endif
     double ax, ay, az, bx, by, bz, cx, cy, cz;
-    load_vtx(P.leaf_geo, 3 * leaf, ax, ay, az);
-    load_vtx(P.leaf_geo, 3 * leaf + 1, bx, by, bz);
-    load_vtx(P.leaf_geo, 3 * leaf + 2, cx, cy, cz);
+    load_vtx(P.vrot, f.x, ax, ay, az);
+    load_vtx(P.vrot, f.y, bx, by, bz);
+    load_vtx(P.vrot, f.z, cx, cy, cz);
     ax -= px; ay -= py;
     bx -= px; by -= py;
     cx -= px; cy -= py;
@@ -182,94 +187,60 @@ C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double
     if (L.n == cap) L.maybe_more = true;
 }
 
-struct NodeData {
-    float4 bx, by, bz; // {lo0, lo1, hi0, hi1} per axis
-    int2 ch;
-};
-
-C5_HD NodeData load_node(const WalkParams& P, const BvhNode* top, int node) {
-    const BvhNode* n = (node < P.top_nodes) ? (top + node) : (P.nodes + node);
-    NodeData d;
-#ifdef __CUDA_ARCH__
-    d.bx = *reinterpret_cast<const float4*>(n->xlo);
-    d.by = *reinterpret_cast<const float4*>(n->ylo);
-    d.bz = *reinterpret_cast<const float4*>(n->zlo);
-    d.ch = *reinterpret_cast<const int2*>(n->child);
-#else
-    d.bx = make_float4(n->xlo[0], n->xlo[1], n->xhi[0], n->xhi[1]);
-    d.by = make_float4(n->ylo[0], n->ylo[1], n->yhi[0], n->yhi[1]);
-    d.bz = make_float4(n->zlo[0], n->zlo[1], n->zhi[0], n->zhi[1]);
-    d.ch = make_int2(n->child[0], n->child[1]);
-#endif
-    return d;
-}
-
-struct PixelF {
-    float x_lo, x_hi, y_lo, y_hi; // the pixel position widened to floats
-};
-
-// Tests both children of a node: leaves are tested on the spot, internal children are pushed
-// (the lower one last, so that it is popped first).
-C5_HD void visit_node(const WalkParams& P, const NodeData& d, const PixelF& q, double px, double py, double z_after,
-                      EntryList& L, int cap, int* stack, int& sp) {
-    // once the list is full, nothing at or above its highest entry can get in
-    const double z_cap = (L.n == cap) ? L.z[cap - 1] : INFINITY;
-    // boxes are rounded outward and the pixel is widened to floats, so this never misses
-    bool h0 = q.x_hi >= d.bx.x && q.x_lo <= d.bx.z && q.y_hi >= d.by.x && q.y_lo <= d.by.z &&
-              static_cast<double>(d.bz.z) > z_after && static_cast<double>(d.bz.x) < z_cap;
-    bool h1 = q.x_hi >= d.bx.y && q.x_lo <= d.bx.w && q.y_hi >= d.by.y && q.y_lo <= d.by.w &&
-              static_cast<double>(d.bz.w) > z_after && static_cast<double>(d.bz.y) < z_cap;
-    if (h0 && d.ch.x < 0) {
-        test_leaf(P, ~d.ch.x, px, py, z_after, L, cap);
-        h0 = false;
-    }
-    if (h1 && d.ch.y < 0) {
-        test_leaf(P, ~d.ch.y, px, py, z_after, L, cap);
-        h1 = false;
-    }
-    if (h0 && h1) {
-        const bool first0 = d.bz.x <= d.bz.y;
-        if (sp + 1 < kStack) {
-            stack[sp++] = first0 ? d.ch.y : d.ch.x;
-            stack[sp++] = first0 ? d.ch.x : d.ch.y;
-        }
-    } else if (h0) {
-        if (sp < kStack) stack[sp++] = d.ch.x;
-    } else if (h1) {
-        if (sp < kStack) stack[sp++] = d.ch.y;
-    }
-}
-
 // The (up to cap <= kEntries) lowest entry faces strictly above z_after under pixel (px, py).
 // cap = 1 is the classic nearest-hit search: once one face is found, every node whose box starts
 // above it is pruned. A ray's FIRST query uses cap = 1 (most rays enter once and the search stays as
 // cheap as it can be); the query after an exit uses cap = kEntries (for a convex mesh it finds
-// nothing after visiting a handful of nodes; for a grazing ray it fetches the next crossings).
-// A traversal is a chain of dependent loads, so it pops TWO nodes per iteration and has both
-// node loads in flight together.
+// nothing after visiting a handful of nodes; for a grazing ray it fetches the next 8 crossings).
 C5_HD void bvh_collect_entries(const WalkParams& P, const BvhNode* top, double px, double py, double z_after,
                                EntryList& L, int cap) {
     int stack[kStack];
     int sp = 0;
     L.n = 0;
     L.maybe_more = false;
-    PixelF q;
-    q.x_lo = f_round_down(px);
-    q.x_hi = f_round_up(px);
-    q.y_lo = f_round_down(py);
-    q.y_hi = f_round_up(py);
-    int n0 = 0, n1 = -1;
-    while (n0 >= 0) {
-        const NodeData d0 = load_node(P, top, n0);
-        if (n1 >= 0) {
-            const NodeData d1 = load_node(P, top, n1);
-            visit_node(P, d0, q, px, py, z_after, L, cap, stack, sp);
-            visit_node(P, d1, q, px, py, z_after, L, cap, stack, sp);
-        } else {
-            visit_node(P, d0, q, px, py, z_after, L, cap, stack, sp);
+    int node = 0;
+    const float fx_lo = f_round_down(px), fx_hi = f_round_up(px);
+    const float fy_lo = f_round_down(py), fy_hi = f_round_up(py);
+    while (true) {
+        const BvhNode* n = (node < P.top_nodes) ? (top + node) : (P.nodes + node);
+#ifdef __CUDA_ARCH__
+        const float4 bx = *reinterpret_cast<const float4*>(n->xlo); // xlo0 xlo1 xhi0 xhi1
+        const float4 by = *reinterpret_cast<const float4*>(n->ylo);
+        const float4 bz = *reinterpret_cast<const float4*>(n->zlo);
+        const int2 ch = *reinterpret_cast<const int2*>(n->child);
+#else
+        const float4 bx = make_float4(n->xlo[0], n->xlo[1], n->xhi[0], n->xhi[1]);
+        const float4 by = make_float4(n->ylo[0], n->ylo[1], n->yhi[0], n->yhi[1]);
+        const float4 bz = make_float4(n->zlo[0], n->zlo[1], n->zhi[0], n->zhi[1]);
+        const int2 ch = make_int2(n->child[0], n->child[1]);
+#endif
+        // once the list is full, nothing at or above its highest entry can get in
+        const double z_cap = (L.n == cap) ? L.z[cap - 1] : INFINITY;
+        // boxes are rounded outward and the pixel is widened to floats, so this never misses
+        bool h0 = fx_hi >= bx.x && fx_lo <= bx.z && fy_hi >= by.x && fy_lo <= by.z &&
+                  static_cast<double>(bz.z) > z_after && static_cast<double>(bz.x) < z_cap;
+        bool h1 = fx_hi >= bx.y && fx_lo <= bx.w && fy_hi >= by.y && fy_lo <= by.w &&
+                  static_cast<double>(bz.w) > z_after && static_cast<double>(bz.y) < z_cap;
+        if (h0 && ch.x < 0) {
+            test_leaf(P, ~ch.x, px, py, z_after, L, cap);
+            h0 = false;
         }
-        n0 = sp > 0 ? stack[--sp] : -1;
-        n1 = sp > 0 ? stack[--sp] : -1;
+        if (h1 && ch.y < 0) {
+            test_leaf(P, ~ch.y, px, py, z_after, L, cap);
+            h1 = false;
+        }
+        if (h0 && h1) {
+            const bool first0 = bz.x <= bz.y; // descend into the lower subtree first
+            if (sp < kStack) stack[sp++] = first0 ? ch.y : ch.x;
+            node = first0 ? ch.x : ch.y;
+        } else if (h0) {
+            node = ch.x;
+        } else if (h1) {
+            node = ch.y;
+        } else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
     }
 }
 
@@ -715,7 +686,6 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.cells = d.cells.p;
     P.vrot = d.vrot.p;
     P.bfaces = d.bfaces.p;
-    P.leaf_geo = d.leaf_geo.p;
     P.nodes = d.nodes.p;
     P.xs = d.xs.p;
     P.ys = d.ys.p;

@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("solid_pixels", C.c_uint64), ("walk_errors", C.c_uint64), ("ms_rotate", C.c_float),
                 ("ms_bvh", C.c_float), ("ms_mask", C.c_float), ("ms_walk", C.c_float),
                 ("ms_gather", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
-                ("n_devices", C.c_int32), ("reserved", C.c_int32)]
+                ("n_devices", C.c_int32), ("grazing_rays", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
@@ -84,7 +84,13 @@ SYMBOLS = {
     "c5_render_device": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "c5_last_row_cost": (C.c_int, [C.c_void_p, _u64p, C.c_int32]),
     "c5_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "c5_image_create": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), _u8p]),
+    "c5_image_open": (C.c_int, [C.c_void_p, _u8p, C.POINTER(C.c_void_p)]),
+    "c5_image_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "c5_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "c5_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
+IPC_HANDLE_BYTES = 64
 
 
 def load_library(path: str | None = None) -> C.CDLL:
@@ -230,6 +236,31 @@ class Context:
         self._check(self.lib.c5_render_device(self._h, C.byref(view), C.c_void_p(device_ptr),
                                               C.c_void_p(stream), C.byref(st)))
         return st.as_dict()
+
+    # -- one image, several processes (include/c5gpu.h) ----------------------------------------
+    def image_create(self, nbytes: int) -> tuple[int, bytes]:
+        """Device image other processes can map: returns (device pointer, 64-byte handle)."""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        self._check(self.lib.c5_image_create(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def image_open(self, handle: bytes) -> int:
+        """Maps an image created by ANOTHER process (CUDA IPC over NVLink); returns the device pointer."""
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        self._check(self.lib.c5_image_open(self._h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def image_close(self, ptr: int):
+        self._check(self.lib.c5_image_close(self._h, C.c_void_p(ptr)))
+
+    def host_register(self, array: np.ndarray):
+        """Pins `array`'s memory (e.g. a shared-memory image) so c5_render writes bands into it in place."""
+        self._check(self.lib.c5_host_register(self._h, C.c_void_p(array.ctypes.data), array.nbytes))
+
+    def host_unregister(self, array: np.ndarray):
+        self._check(self.lib.c5_host_unregister(self._h, C.c_void_p(array.ctypes.data)))
 
     def last_row_cost(self, n_rows: int) -> np.ndarray:
         rows = np.zeros(n_rows, dtype=np.uint64)

@@ -135,6 +135,7 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     if (!out_override) d.out.ensure(2 * n_pix_band);
     if (want_steps) d.steps.ensure(n_pix_band);
     d.counters.ensure(kNumCounters);
+    d.queue.ensure(n_pix_band);
     d.row_cost.ensure(static_cast<size_t>(v->res_y));
     if (solids) d.mask.ensure(static_cast<size_t>(v->res_x) * v->res_y);
 
@@ -259,7 +260,7 @@ std::vector<std::pair<int, int>> cut_bands(const c5_ctx* ctx, const c5_view* v, 
 }
 
 struct Counters {
-    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
+    unsigned long long c[kNumCounters] = {};
 };
 
 // plane ctor + find_intersections + trace_rays for one view into a HOST buffer, on all devices of
@@ -392,6 +393,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
         st->hit_pixels = total.c[kHitPixels];
         st->solid_pixels = total.c[kSolidPixels];
         st->walk_errors = total.c[kWalkErrors];
+        st->grazing_rays = static_cast<int32_t>(total.c[kDeferred]);
         for (auto& dp : ctx->dev) { // phase times: the slowest device
             use_device(*dp);
             st->ms_rotate = std::max(st->ms_rotate, elapsed(*dp, 0, 1));
@@ -412,7 +414,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
 
 // Single-device, device-resident output (the caller's buffer), no host copy of the image.
 void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan& p, c5_stats* st, int ev_last) {
-    unsigned long long c[kNumCounters] = {0, 0, 0, 0};
+    unsigned long long c[kNumCounters] = {};
     d2h(c, d.counters.p, sizeof(c), d.stream);
     ctx->last_row_cost.assign(static_cast<size_t>(v->res_y), 0);
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "row cost width");
@@ -425,6 +427,7 @@ void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan
         st->hit_pixels = c[kHitPixels];
         st->solid_pixels = c[kSolidPixels];
         st->walk_errors = c[kWalkErrors];
+        st->grazing_rays = static_cast<int32_t>(c[kDeferred]);
         st->ms_rotate = elapsed(d, 0, 1);
         st->ms_bvh = elapsed(d, 1, 2);
         st->ms_mask = elapsed(d, 2, 3);
@@ -556,6 +559,17 @@ void c5_destroy(c5_ctx* ctx) {
     if (!ctx) return;
     nccl_close(ctx->nccl);
     ctx->nccl = nullptr;
+    if (!kHostSim) {
+        cudaSetDevice(ctx->dev[0]->device);
+        cudaStreamSynchronize(ctx->dev[0]->stream);
+    }
+    for (void* p : ctx->registered) {
+        if (!kHostSim) cudaHostUnregister(p);
+    }
+    for (auto& im : ctx->images) {
+        if (im.second) dev_free(im.first);
+        else if (!kHostSim) cudaIpcCloseMemHandle(im.first);
+    }
     for (auto& dp : ctx->dev) {
         DeviceState& d = *dp;
         if (!kHostSim) {
@@ -668,6 +682,86 @@ int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows) {
         rows[j] = static_cast<size_t>(j) < ctx->last_row_cost.size() ? ctx->last_row_cost[static_cast<size_t>(j)] : 0;
     }
     return C5_OK;
+}
+
+int c5_image_create(c5_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[C5_IPC_HANDLE_BYTES]) {
+    if (!ctx || !d_ptr || !handle) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        if (bytes == 0) fail(C5_E_INVALID, "image_create: zero bytes");
+        use_device(*ctx->dev[0]);
+        void* p = dev_alloc(bytes); // a plain cudaMalloc: the handle then refers to p itself, offset 0
+        std::memset(handle, 0, C5_IPC_HANDLE_BYTES);
+        if (kHostSim) {
+            std::memcpy(handle, &p, sizeof(p)); // same-process stand-in (CPU logic tests only)
+        } else {
+            static_assert(sizeof(cudaIpcMemHandle_t) <= C5_IPC_HANDLE_BYTES, "IPC handle size");
+            cudaIpcMemHandle_t h;
+            cudaError_t e = cudaIpcGetMemHandle(&h, p);
+            if (e != cudaSuccess) {
+                dev_free(p);
+                fail(C5_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+            }
+            std::memcpy(handle, &h, sizeof(h));
+        }
+        ctx->images.emplace_back(p, true);
+        *d_ptr = p;
+    });
+}
+
+int c5_image_open(c5_ctx* ctx, const uint8_t handle[C5_IPC_HANDLE_BYTES], void** d_ptr) {
+    if (!ctx || !d_ptr || !handle) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        use_device(*ctx->dev[0]);
+        void* p = nullptr;
+        if (kHostSim) {
+            std::memcpy(&p, handle, sizeof(p));
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handle, sizeof(h));
+            // maps the owner's allocation into this process and enables peer access to its device
+            C5_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        ctx->images.emplace_back(p, false);
+        *d_ptr = p;
+    });
+}
+
+int c5_image_close(c5_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        for (size_t k = 0; k < ctx->images.size(); k++) {
+            if (ctx->images[k].first != d_ptr) continue;
+            const bool owner = ctx->images[k].second;
+            ctx->images.erase(ctx->images.begin() + static_cast<long>(k));
+            use_device(*ctx->dev[0]);
+            if (owner) dev_free(d_ptr);
+            else if (!kHostSim) C5_CUDA(cudaIpcCloseMemHandle(d_ptr));
+            return;
+        }
+        fail(C5_E_INVALID, "image_close: not an image of this context");
+    });
+}
+
+int c5_host_register(c5_ctx* ctx, void* ptr, uint64_t bytes) {
+    if (!ctx || !ptr || bytes == 0) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        use_device(*ctx->dev[0]);
+        if (!kHostSim) C5_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+        ctx->registered.push_back(ptr);
+    });
+}
+
+int c5_host_unregister(c5_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        for (size_t k = 0; k < ctx->registered.size(); k++) {
+            if (ctx->registered[k] != ptr) continue;
+            ctx->registered.erase(ctx->registered.begin() + static_cast<long>(k));
+            if (!kHostSim) C5_CUDA(cudaHostUnregister(ptr));
+            return;
+        }
+        fail(C5_E_INVALID, "host_unregister: not registered through this context");
+    });
 }
 
 uint64_t c5_kernel_launches(const c5_ctx* ctx) {

@@ -3,6 +3,7 @@
 
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/c5gpu.h"
@@ -13,7 +14,9 @@ namespace c5 {
 constexpr int kMaxRot = C5_MAX_ROT;
 
 // Counters the walk kernel accumulates (one 64-bit atomic per warp).
-enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kNumCounters = 4 };
+// kDeferred = rays the pixel kernel handed to the grazing-ray kernel, kTicket = how many of those
+// the grazing-ray kernel's warps have drawn.
+enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kDeferred = 4, kTicket = 5, kNumCounters = 6 };
 
 struct SolidSet {
     DevBuf<double> pts0;      // [n][4][3] pre-view frame
@@ -55,6 +58,8 @@ struct DeviceState {
     DevBuf<uint32_t> steps;
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned long long> row_cost;
+    DevBuf<DeferredRay> queue;       // grazing rays of the current view (capacity: pixels of the band)
+    int sm_count = 0;
 
     uint64_t launches = 0;
 };
@@ -70,6 +75,8 @@ struct c5_ctx {
     c5_mesh_info info{};
     std::vector<uint64_t> last_row_cost;
     void* nccl = nullptr; // NcclGroup*, multi-device contexts only
+    std::vector<std::pair<void*, bool>> images;   // c5_image_create (true) / c5_image_open (false) pointers
+    std::vector<void*> registered;                // c5_host_register pointers
 };
 
 namespace c5 {

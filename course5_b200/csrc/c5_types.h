@@ -57,6 +57,16 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
+// A ray the pixel kernel could not finish cheaply (its re-entry list came back full: it grazes a
+// bumpy boundary and has many short crossings). The grazing-ray kernel continues it from here.
+struct alignas(32) DeferredRay {
+    double tau, inten; // accumulated so far
+    double z_after;    // the ray has left the mesh at this depth
+    uint32_t pixel;    // j * res_x + i
+    uint32_t steps;
+};
+static_assert(sizeof(DeferredRay) == 32, "DeferredRay must be 32 bytes");
+
 struct Rot {       // one rotation with the trig evaluated on the host by libm (so it is the same
     int32_t axis;  // cos/sin the reference's host code multiplies by, tetra.cpp:44-62)
     int32_t pad;

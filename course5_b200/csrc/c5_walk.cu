@@ -49,9 +49,12 @@ struct WalkParams {
     uint32_t* steps;      // may be null; same indexing
     unsigned long long* counters;
     unsigned long long* row_cost; // [res_y]
+    DeferredRay* queue;   // rays handed to the grazing-ray kernel; counters[kDeferred] of them
     int res_x, res_y, row_begin, row_end;
     int n_tiles_x, n_tiles_y, n_macro_x;
     int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
+    int graze_cap;        // entries one cooperative collection may hold (<= kGrazeList)
+    int serial_cap;       // same for the serial (host loop) form (<= kSerialList)
     int max_steps;
     int round_float;
     double alpha_limit;
@@ -130,26 +133,27 @@ C5_HD void prefetch_l1(const void* p) {
 
 // ---- entry search --------------------------------------------------------------------------------
 
-// Entry list of one ray: the kEntries lowest entry faces above z_after, sorted by z. A ray through
-// a convex mesh has one entry; cavities add a few; a ray grazing a bumpy boundary (the jittered side
-// walls of the synthetic grids, seen edge-on) has ~100. Such a ray is a chain of dependent BVH
-// queries and short crossings, and a handful of them set the run time of a whole row band (measured:
-// 1.3 ms for ANY band of the C3 README view with one query per crossing, profiles/r01_exp_bands.jsonl).
-// Collecting the crossings 64 at a time turns ~110 queries into 2-3. The list lives in local
-// memory and is touched only by rays that re-enter; faces arrive roughly near-to-far, so the
-// insertion sort from the back is close to linear.
-constexpr int kEntries = 64;
-
+// Entry list of one ray: the lowest entry faces above z_after, sorted by (z, leaf). A ray through a
+// convex mesh has one entry; cavities add a few; a ray grazing a bumpy boundary (the jittered side
+// walls of the synthetic grids, seen edge-on) has ~100. A thread walking such a ray alone is a chain
+// of dependent BVH queries and short crossings, and a handful of them set the run time of a whole
+// row band (measured: 1.2-1.3 ms for ANY band of the C3 README view, profiles/r01_exp_bands.jsonl).
+// So the pixel kernel only ever asks for a short list (kInline entries); a ray whose list comes back
+// full is handed to the grazing-ray kernel below, where a whole warp works on it.
+template <int kCap>
 struct EntryList {
-    double z[kEntries];
-    int leaf[kEntries];
+    double z[kCap];
+    int leaf[kCap];
     int n;
-    bool maybe_more; // the list filled up: faces above z[n-1] may have been left out
 };
 
-// Boundary face `leaf` against the pixel: inclusive point-in-triangle test with the same
-// orientation predicate the walk uses, then the barycentric z; kept if among the lowest.
-C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double z_after, EntryList& L, int cap) {
+constexpr int kInline = 4;   // re-entry list of the pixel kernel: fewer entries than this are walked in place
+constexpr int kSerialList = 64; // list of the serial (host loop) grazing path
+
+// Depth at which the ray through (px, py) enters the mesh through boundary face `leaf`: inclusive
+// point-in-triangle test with the same orientation predicate the walk uses, then the barycentric z.
+// False if the face is not under the pixel, faces +z, or lies at or below z_after.
+C5_HD bool entry_depth(const WalkParams& P, int leaf, double px, double py, double z_after, double& z_out) {
 #ifdef __CUDA_ARCH__
     const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
 #else
@@ -167,42 +171,52 @@ C5_HD void test_leaf(const WalkParams& P, int leaf, double px, double py, double
     const double o_bc = orient2(bx, by, cx, cy);
     const double o_ca = orient2(cx, cy, ax, ay);
     // outward normal towards -z  <=>  clockwise in projection  <=>  all three <= 0 inside
-    if (!(o_ab <= 0 && o_bc <= 0 && o_ca <= 0)) return;
+    if (!(o_ab <= 0 && o_bc <= 0 && o_ca <= 0)) return false;
     const double sum = o_ab + o_bc + o_ca;
-    if (!(sum < 0)) return;
+    if (!(sum < 0)) return false;
     const double z = (o_bc * az + o_ca * bz + o_ab * cz) / sum;
-    if (!(z > z_after)) return;
+    if (!(z > z_after)) return false;
+    z_out = z;
+    return true;
+}
+
+C5_HD bool entry_before(double z0, int leaf0, double z1, int leaf1) { // strict (z, leaf) order
+    return z0 < z1 || (z0 == z1 && leaf0 < leaf1);
+}
+
+// Keeps the `cap` lowest entries, sorted; faces arrive roughly near-to-far, so the insertion from
+// the back is close to linear.
+template <int kCap>
+C5_HD void insert_entry(EntryList<kCap>& L, int cap, double z, int leaf) {
     if (L.n == cap) {
-        if (!(z < L.z[cap - 1])) return;
+        if (!entry_before(z, leaf, L.z[cap - 1], L.leaf[cap - 1])) return;
         L.n--; // the highest one falls off
     }
     int k = L.n++;
-    while (k > 0 && L.z[k - 1] > z) { // sorted insertion
+    while (k > 0 && entry_before(z, leaf, L.z[k - 1], L.leaf[k - 1])) {
         L.z[k] = L.z[k - 1];
         L.leaf[k] = L.leaf[k - 1];
         k--;
     }
     L.z[k] = z;
     L.leaf[k] = leaf;
-    if (L.n == cap) L.maybe_more = true;
 }
 
-// The (up to cap <= kEntries) lowest entry faces strictly above z_after under pixel (px, py).
-// cap = 1 is the classic nearest-hit search: once one face is found, every node whose box starts
-// above it is pruned. A ray's FIRST query uses cap = 1 (most rays enter once and the search stays as
-// cheap as it can be); the query after an exit uses cap = kEntries (for a convex mesh it finds
-// nothing after visiting a handful of nodes; for a grazing ray it fetches the next 8 crossings).
+// The (up to cap <= kCap) lowest entry faces strictly above z_after under pixel (px, py), by one
+// thread with a private stack. cap = 1 is the classic nearest-hit search: once one face is found,
+// every node whose box starts above it is pruned. L.n == cap on return means "there may be more
+// above L.z[cap - 1]"; L.n < cap means the list is complete.
+template <int kCap>
 C5_HD void bvh_collect_entries(const WalkParams& P, const BvhNode* top, double px, double py, double z_after,
-                               EntryList& L, int cap) {
+                               EntryList<kCap>& L, int cap) {
     int stack[kStack];
     int sp = 0;
     L.n = 0;
-    L.maybe_more = false;
     int node = 0;
     const float fx_lo = f_round_down(px), fx_hi = f_round_up(px);
     const float fy_lo = f_round_down(py), fy_hi = f_round_up(py);
     while (true) {
-        const BvhNode* n = (node < P.top_nodes) ? (top + node) : (P.nodes + node);
+        const BvhNode* n = (top && node < P.top_nodes) ? (top + node) : (P.nodes + node);
 #ifdef __CUDA_ARCH__
         const float4 bx = *reinterpret_cast<const float4*>(n->xlo); // xlo0 xlo1 xhi0 xhi1
         const float4 by = *reinterpret_cast<const float4*>(n->ylo);
@@ -214,19 +228,20 @@ C5_HD void bvh_collect_entries(const WalkParams& P, const BvhNode* top, double p
         const float4 bz = make_float4(n->zlo[0], n->zlo[1], n->zhi[0], n->zhi[1]);
         const int2 ch = make_int2(n->child[0], n->child[1]);
 #endif
-        // once the list is full, nothing at or above its highest entry can get in
+        // once the list is full, nothing above its highest entry can get in
         const double z_cap = (L.n == cap) ? L.z[cap - 1] : INFINITY;
         // boxes are rounded outward and the pixel is widened to floats, so this never misses
         bool h0 = fx_hi >= bx.x && fx_lo <= bx.z && fy_hi >= by.x && fy_lo <= by.z &&
-                  static_cast<double>(bz.z) > z_after && static_cast<double>(bz.x) < z_cap;
+                  static_cast<double>(bz.z) > z_after && static_cast<double>(bz.x) <= z_cap;
         bool h1 = fx_hi >= bx.y && fx_lo <= bx.w && fy_hi >= by.y && fy_lo <= by.w &&
-                  static_cast<double>(bz.w) > z_after && static_cast<double>(bz.y) < z_cap;
+                  static_cast<double>(bz.w) > z_after && static_cast<double>(bz.y) <= z_cap;
+        double z;
         if (h0 && ch.x < 0) {
-            test_leaf(P, ~ch.x, px, py, z_after, L, cap);
+            if (entry_depth(P, ~ch.x, px, py, z_after, z)) insert_entry(L, cap, z, ~ch.x);
             h0 = false;
         }
         if (h1 && ch.y < 0) {
-            test_leaf(P, ~ch.y, px, py, z_after, L, cap);
+            if (entry_depth(P, ~ch.y, px, py, z_after, z)) insert_entry(L, cap, z, ~ch.y);
             h1 = false;
         }
         if (h0 && h1) {
@@ -244,145 +259,105 @@ C5_HD void bvh_collect_entries(const WalkParams& P, const BvhNode* top, double p
     }
 }
 
-// ---- one ray ---------------------------------------------------------------------------------------
+// ---- one crossing ----------------------------------------------------------------------------------
 
-struct RayResult {
-    double tau, inten;
-    uint32_t steps;
-    uint32_t error;
-};
-
-// One ray. BVH collections stay converged (all lanes of a warp query together: a traversal is
-// hundreds of dependent loads and must not be serialised lane by lane), but WITHIN one collection
-// the crossings and the steps form one flat loop: a lane whose crossing ends takes its next list
-// entry while the other lanes keep stepping, instead of waiting for the longest crossing of the
-// round. Measured on the C3 README view (profiles/r01_exp_bands_nested_vs_flat.jsonl): whole view
-// 5.25 -> 5.04 ms, silhouette row band 1.29 -> 0.99 ms. (Fully flat, with the BVH query inside the
-// loop, is 50 % SLOWER: profiles/r01_exp_c3_flat_loop.jsonl.)
-template <bool kWide, int kPipe>
-C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py) {
-    RayResult r;
-    r.tau = 0.0;
-    r.inten = 0.0;
-    r.steps = 0;
-    r.error = 0;
-    double z_after = -INFINITY;
-    int crossings = 0;
-
-    EntryList L;
-    L.maybe_more = true;
-    int cap = 1;
-    while (L.maybe_more && !r.error) {
-        bvh_collect_entries(P, top, px, py, z_after, L, cap);
-        cap = kEntries;
-        if (L.n == 0) break;
-
-        int e = 0;
-        int t = -1, id = -1;
-        int ia = 0, ib = 0, ic = 0;
-        double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0, cx = 0, cy = 0, cz = 0;
-        double wa = 0, wb = 0, wc = 0, z_cur = 0;
-        while (true) {
-            if (t < 0) {
-                int leaf = -1;
-                while (e < L.n) { // next list entry above the ray's current position
-                    const double z = L.z[e];
-                    const int cand = L.leaf[e];
-                    e++;
-                    if (z > z_after) {
-                        z_cur = z;
-                        leaf = cand;
-                        break;
-                    }
-                }
-                if (leaf < 0) break;
-                if (++crossings > 65536) {
-                    r.error = 1;
-                    break;
-                }
+// One crossing of the mesh: the ray enters through boundary face `leaf` at depth z_in and goes from
+// tet to tet until it leaves through another boundary face; returns that depth. tau, inten and steps
+// are updated in place. kAffine: the caller does not know the intensity the ray arrives with (the
+// grazing-ray kernel walks the crossings of one ray in parallel); inten then starts at 0 and gain at
+// 1, and the crossing maps an arriving I to inten + gain * I (the recurrence of line.cpp:206-225 is
+// affine in I: s - (s - I) e = s (1 - e) + e I).
+template <bool kWide, int kPipe, bool kAffine>
+C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, double z_in, double& tau,
+                          double& inten, double& gain, uint32_t& steps, uint32_t& error) {
 #ifdef __CUDA_ARCH__
-                const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
-                id = __ldg(&P.bfaces[leaf].apex);
+    const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+    int id = __ldg(&P.bfaces[leaf].apex);
 #else
-                const BFace& bf = P.bfaces[leaf];
-                const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
-                id = bf.apex;
+    const BFace& bf = P.bfaces[leaf];
+    const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+    int id = bf.apex;
 #endif
-                // entry face (a, c, b) of the stored winding is counter-clockwise in projection
-                ia = f.x; ib = f.z; ic = f.y;
-                load_vtx(P.vrot, ia, ax, ay, az);
-                load_vtx(P.vrot, ib, bx, by, bz);
-                load_vtx(P.vrot, ic, cx, cy, cz);
-                ax -= px; ay -= py;
-                bx -= px; by -= py;
-                cx -= px; cy -= py;
-                // weight of a vertex = orient2 of the other two, in cyclic order: all >= 0 inside
-                wa = orient2(bx, by, cx, cy);
-                wb = orient2(cx, cy, ax, ay);
-                wc = orient2(ax, ay, bx, by);
-                t = f.w;
-            }
-            if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
-                r.error = 1;
-                break;
-            }
-            // id = the vertex of tet t that is not on the entry face. It is known BEFORE t's cell is
-            // read (Cell::apex of the previous tet, BFace::apex at entry), so the cell load and the
-            // vertex load of a step are independent and overlap: one memory latency per step, not two.
-            const CellData c = load_cell<kWide>(P.cells, t);
-            double dx, dy, dz;
-            load_vtx(P.vrot, id, dx, dy, dz);
-            dx -= px;
-            dy -= py;
-            const double sa = orient2(dx, dy, ax, ay);
-            const double sb = orient2(dx, dy, bx, by);
-            const double sc = orient2(dx, dy, cx, cy);
-            // which face the ray leaves through, hence the next tet and its new vertex
-            const bool drop_c = sa >= 0 && sb < 0;             // through (d, a, b)
-            const bool drop_a = !drop_c && sb >= 0 && sc < 0;  // through (d, b, c)
-            const int dropped = drop_c ? ic : drop_a ? ia : ib; // else through (d, c, a)
-            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
-            const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
-            const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
-            if (kPipe == 1 && t_next >= 0) {
-                prefetch_l1(P.cells + t_next);
-                prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
-                prefetch_l1(P.vrot + id_next);
-            }
-            if (drop_c) { // leaves through (d, a, b): c is replaced by d
-                ic = id; cx = dx; cy = dy; cz = dz;
-                wa = -sb;
-                wb = sa;
-            } else if (drop_a) { // through (d, b, c): a is replaced
-                ia = id; ax = dx; ay = dy; az = dz;
-                wb = -sc;
-                wc = sb;
-            } else { // through (d, c, a): b is replaced
-                ib = id; bx = dx; by = dy; bz = dz;
-                wc = -sa;
-                wa = sc;
-            }
-            const double wsum = wa + wb + wc;
-            const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
-            const double dzv = fabs(z_exit - z_cur);
-            // tau: line.cpp:176-193 (alpha not clamped)
-            r.tau += dzv * c.alpha;
-            // I: line.cpp:206-225 with s = Q / a^:  (Q - (Q - a^ I) e) / a^  ==  s - (s - I) e
-            double a_c = c.alpha;
-            if (a_c > P.alpha_limit) a_c = P.alpha_limit;
-            if (!(a_c < DBL_EPSILON)) r.inten = c.s - (c.s - r.inten) * exp(-a_c * dzv);
-            r.steps++;
-            z_cur = z_exit;
-            t = t_next;
-            id = id_next;
-            if (t < 0) z_after = z_cur;
+    // entry face (a, c, b) of the stored winding is counter-clockwise in projection
+    int ia = f.x, ib = f.z, ic = f.y;
+    double ax, ay, az, bx, by, bz, cx, cy, cz;
+    load_vtx(P.vrot, ia, ax, ay, az);
+    load_vtx(P.vrot, ib, bx, by, bz);
+    load_vtx(P.vrot, ic, cx, cy, cz);
+    ax -= px; ay -= py;
+    bx -= px; by -= py;
+    cx -= px; cy -= py;
+    // weight of a vertex = orient2 of the other two, in cyclic order: all >= 0 inside
+    double wa = orient2(bx, by, cx, cy);
+    double wb = orient2(cx, cy, ax, ay);
+    double wc = orient2(ax, ay, bx, by);
+    int t = f.w;
+    double z_cur = z_in;
+    while (true) {
+        if (steps >= static_cast<uint32_t>(P.max_steps)) {
+            error = 1;
+            break;
         }
+        // id = the vertex of tet t that is not on the entry face. It is known BEFORE t's cell is
+        // read (Cell::apex of the previous tet, BFace::apex at entry), so the cell load and the
+        // vertex load of a step are independent and overlap: one memory latency per step, not two.
+        const CellData c = load_cell<kWide>(P.cells, t);
+        double dx, dy, dz;
+        load_vtx(P.vrot, id, dx, dy, dz);
+        dx -= px;
+        dy -= py;
+        const double sa = orient2(dx, dy, ax, ay);
+        const double sb = orient2(dx, dy, bx, by);
+        const double sc = orient2(dx, dy, cx, cy);
+        // which face the ray leaves through, hence the next tet and its new vertex
+        const bool drop_c = sa >= 0 && sb < 0;             // through (d, a, b)
+        const bool drop_a = !drop_c && sb >= 0 && sc < 0;  // through (d, b, c)
+        const int dropped = drop_c ? ic : drop_a ? ia : ib; // else through (d, c, a)
+        const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
+        const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
+        const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
+        if (kPipe == 1 && t_next >= 0) {
+            prefetch_l1(P.cells + t_next);
+            prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
+            prefetch_l1(P.vrot + id_next);
+        }
+        if (drop_c) { // leaves through (d, a, b): c is replaced by d
+            ic = id; cx = dx; cy = dy; cz = dz;
+            wa = -sb;
+            wb = sa;
+        } else if (drop_a) { // through (d, b, c): a is replaced
+            ia = id; ax = dx; ay = dy; az = dz;
+            wb = -sc;
+            wc = sb;
+        } else { // through (d, c, a): b is replaced
+            ib = id; bx = dx; by = dy; bz = dz;
+            wc = -sa;
+            wa = sc;
+        }
+        const double wsum = wa + wb + wc;
+        const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
+        const double dzv = fabs(z_exit - z_cur);
+        // tau: line.cpp:176-193 (alpha not clamped)
+        tau += dzv * c.alpha;
+        // I: line.cpp:206-225 with s = Q / a^:  (Q - (Q - a^ I) e) / a^  ==  s - (s - I) e
+        double a_c = c.alpha;
+        if (a_c > P.alpha_limit) a_c = P.alpha_limit;
+        if (!(a_c < DBL_EPSILON)) {
+            const double e = exp(-a_c * dzv);
+            inten = c.s - (c.s - inten) * e;
+            if (kAffine) gain *= e;
+        }
+        steps++;
+        z_cur = z_exit;
+        t = t_next;
+        id = id_next;
+        if (t < 0) break;
     }
-    return r;
+    return z_cur;
 }
 
 // ---- FP32 variant -----------------------------------------------------------------------------------
-// Same walk with the per-step geometry in single precision: FP32 orientation tests (still exactly
+// Same crossing with the per-step geometry in single precision: FP32 orientation tests (still exactly
 // antisymmetric: two rounded products, one rounded difference), FP32 divide and expf — about half
 // the issue slots and 56 instead of 72 registers. What stays in double: the ENTRY search (so the
 // hit/miss set is the FP64 one, bit for bit), the vertex fetch and its subtraction of the pixel
@@ -408,133 +383,212 @@ C5_HD float orient2f(float ux, float uy, float vx, float vy) {
     return fsub_rn(fmul_rn(ux, vy), fmul_rn(uy, vx));
 }
 
-template <bool kWide, bool kPrefetch>
-C5_HD RayResult trace_ray_f32(const WalkParams& P, const BvhNode* top, double px, double py) {
+template <bool kWide, int kPipe, bool kAffine>
+C5_HD double crossing_f32(const WalkParams& P, double px, double py, int leaf, double z_in, double& tau,
+                          double& inten, double& gain, uint32_t& steps, uint32_t& error) {
+    const float limit = static_cast<float>(P.alpha_limit);
+    const double z0 = z_in; // depths are kept relative to the entry point of the crossing
+#ifdef __CUDA_ARCH__
+    const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+    int id = __ldg(&P.bfaces[leaf].apex);
+#else
+    const BFace& bf = P.bfaces[leaf];
+    const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+    int id = bf.apex;
+#endif
+    int ia = f.x, ib = f.z, ic = f.y;
+    float ax, ay, az, bx, by, bz, cx, cy, cz;
+    {
+        double x, y, z;
+        load_vtx(P.vrot, ia, x, y, z);
+        ax = static_cast<float>(x - px); ay = static_cast<float>(y - py); az = static_cast<float>(z - z0);
+        load_vtx(P.vrot, ib, x, y, z);
+        bx = static_cast<float>(x - px); by = static_cast<float>(y - py); bz = static_cast<float>(z - z0);
+        load_vtx(P.vrot, ic, x, y, z);
+        cx = static_cast<float>(x - px); cy = static_cast<float>(y - py); cz = static_cast<float>(z - z0);
+    }
+    float wa = orient2f(bx, by, cx, cy);
+    float wb = orient2f(cx, cy, ax, ay);
+    float wc = orient2f(ax, ay, bx, by);
+    int t = f.w;
+    float z_cur = 0.f;
+    while (true) {
+        if (steps >= static_cast<uint32_t>(P.max_steps)) {
+            error = 1;
+            break;
+        }
+        const CellData c = load_cell<kWide>(P.cells, t);
+        float dx, dy, dz;
+        {
+            double x, y, z;
+            load_vtx(P.vrot, id, x, y, z);
+            dx = static_cast<float>(x - px);
+            dy = static_cast<float>(y - py);
+            dz = static_cast<float>(z - z0);
+        }
+        const float sa = orient2f(dx, dy, ax, ay);
+        const float sb = orient2f(dx, dy, bx, by);
+        const float sc = orient2f(dx, dy, cx, cy);
+        const bool drop_c = sa >= 0 && sb < 0;
+        const bool drop_a = !drop_c && sb >= 0 && sc < 0;
+        const int dropped = drop_c ? ic : drop_a ? ia : ib;
+        const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
+        const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
+        const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
+        if (kPipe == 1 && t_next >= 0) {
+            prefetch_l1(P.cells + t_next);
+            prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
+            prefetch_l1(P.vrot + id_next);
+        }
+        if (drop_c) {
+            ic = id; cx = dx; cy = dy; cz = dz;
+            wa = -sb;
+            wb = sa;
+        } else if (drop_a) {
+            ia = id; ax = dx; ay = dy; az = dz;
+            wb = -sc;
+            wc = sb;
+        } else {
+            ib = id; bx = dx; by = dy; bz = dz;
+            wc = -sa;
+            wa = sc;
+        }
+        const float wsum = wa + wb + wc;
+        const float z_exit = (wsum != 0.0f) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
+        const float dzv = fabsf(z_exit - z_cur);
+        tau += static_cast<double>(dzv) * c.alpha;
+        float a_c = static_cast<float>(c.alpha);
+        if (a_c > limit) a_c = limit;
+        const double a_d = c.alpha > P.alpha_limit ? P.alpha_limit : c.alpha;
+        if (!(a_d < DBL_EPSILON)) {
+            const double e = static_cast<double>(expf(-a_c * dzv));
+            inten = c.s - (c.s - inten) * e;
+            if (kAffine) gain *= e;
+        }
+        steps++;
+        z_cur = z_exit;
+        t = t_next;
+        id = id_next;
+        if (t < 0) break;
+    }
+    // the next crossing must lie above this one's exit (and strictly above its entry)
+    const double z_exit_abs = z0 + static_cast<double>(z_cur);
+    return z_exit_abs > z0 ? z_exit_abs : z0;
+}
+
+template <bool kF32, bool kWide, int kPipe, bool kAffine>
+C5_HD double crossing(const WalkParams& P, double px, double py, int leaf, double z_in, double& tau, double& inten,
+                      double& gain, uint32_t& steps, uint32_t& error) {
+    return kF32 ? crossing_f32<kWide, kPipe, kAffine>(P, px, py, leaf, z_in, tau, inten, gain, steps, error)
+                : crossing_f64<kWide, kPipe, kAffine>(P, px, py, leaf, z_in, tau, inten, gain, steps, error);
+}
+
+// ---- one ray (pixel kernel) ------------------------------------------------------------------------
+
+struct RayResult {
+    double tau, inten;
+    uint32_t steps;
+    uint32_t error;
+    uint32_t deferred; // handed to the grazing-ray kernel: the pixel is stored there
+};
+
+// A ray's FIRST query is a nearest-hit search (cap 1: most rays enter once and the search stays as
+// cheap as it can be). After the first exit ONE more query asks for the next kInline entries above:
+// for a convex mesh it finds nothing after visiting a handful of nodes; a cavity gives one or two,
+// which are walked here. A full list means a grazing ray: its state goes to the deferred queue.
+template <bool kF32, bool kWide, int kPipe>
+C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py, uint32_t pixel) {
     RayResult r;
     r.tau = 0.0;
     r.inten = 0.0;
     r.steps = 0;
     r.error = 0;
+    r.deferred = 0;
     double z_after = -INFINITY;
-    int crossings = 0;
-    const float limit = static_cast<float>(P.alpha_limit);
-
-    EntryList L;
-    L.maybe_more = true;
+    double gain_unused = 1.0;
+    EntryList<kInline> L;
     int cap = 1;
-    while (L.maybe_more && !r.error) {
-        bvh_collect_entries(P, top, px, py, z_after, L, cap); // double: same hit set as FP64
-        cap = kEntries;
-        if (L.n == 0) break;
-
-        int e = 0;
-        int t = -1, id = -1;
-        int ia = 0, ib = 0, ic = 0;
-        float ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0, cx = 0, cy = 0, cz = 0;
-        float wa = 0, wb = 0, wc = 0, z_cur = 0;
-        double z0 = 0; // depths are kept relative to the entry point of the current crossing
-        while (true) {
-            if (t < 0) {
-                int leaf = -1;
-                while (e < L.n) {
-                    const double z = L.z[e];
-                    const int cand = L.leaf[e];
-                    e++;
-                    if (z > z_after) {
-                        z0 = z;
-                        leaf = cand;
-                        break;
-                    }
-                }
-                if (leaf < 0) break;
-                if (++crossings > 65536) {
-                    r.error = 1;
-                    break;
-                }
+    while (true) {
+        bvh_collect_entries(P, top, px, py, z_after, L, cap);
+        if (cap != 1 && L.n == cap) {
 #ifdef __CUDA_ARCH__
-                const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
-                id = __ldg(&P.bfaces[leaf].apex);
+            const unsigned long long slot = atomicAdd(&P.counters[kDeferred], 1ull);
 #else
-                const BFace& bf = P.bfaces[leaf];
-                const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
-                id = bf.apex;
+            const unsigned long long slot = P.counters[kDeferred]++;
 #endif
-                ia = f.x; ib = f.z; ic = f.y;
-                double x, y, z;
-                load_vtx(P.vrot, ia, x, y, z);
-                ax = static_cast<float>(x - px); ay = static_cast<float>(y - py); az = static_cast<float>(z - z0);
-                load_vtx(P.vrot, ib, x, y, z);
-                bx = static_cast<float>(x - px); by = static_cast<float>(y - py); bz = static_cast<float>(z - z0);
-                load_vtx(P.vrot, ic, x, y, z);
-                cx = static_cast<float>(x - px); cy = static_cast<float>(y - py); cz = static_cast<float>(z - z0);
-                wa = orient2f(bx, by, cx, cy);
-                wb = orient2f(cx, cy, ax, ay);
-                wc = orient2f(ax, ay, bx, by);
-                t = f.w;
-                z_cur = 0.f;
-            }
-            if (r.steps >= static_cast<uint32_t>(P.max_steps)) {
-                r.error = 1;
-                break;
-            }
-            const CellData c = load_cell<kWide>(P.cells, t);
-            float dx, dy, dz;
-            {
-                double x, y, z;
-                load_vtx(P.vrot, id, x, y, z);
-                dx = static_cast<float>(x - px);
-                dy = static_cast<float>(y - py);
-                dz = static_cast<float>(z - z0);
-            }
-            const float sa = orient2f(dx, dy, ax, ay);
-            const float sb = orient2f(dx, dy, bx, by);
-            const float sc = orient2f(dx, dy, cx, cy);
-            const bool drop_c = sa >= 0 && sb < 0;
-            const bool drop_a = !drop_c && sb >= 0 && sc < 0;
-            const int dropped = drop_c ? ic : drop_a ? ia : ib;
-            const bool k0 = c.v.x == dropped, k1 = c.v.y == dropped, k2 = c.v.z == dropped;
-            const int t_next = k0 ? c.nbr.x : k1 ? c.nbr.y : k2 ? c.nbr.z : c.nbr.w;
-            const int id_next = k0 ? c.apex.x : k1 ? c.apex.y : k2 ? c.apex.z : c.apex.w;
-            if (kPrefetch && t_next >= 0) {
-                prefetch_l1(P.cells + t_next);
-                prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
-                prefetch_l1(P.vrot + id_next);
-            }
-            if (drop_c) {
-                ic = id; cx = dx; cy = dy; cz = dz;
-                wa = -sb;
-                wb = sa;
-            } else if (drop_a) {
-                ia = id; ax = dx; ay = dy; az = dz;
-                wb = -sc;
-                wc = sb;
-            } else {
-                ib = id; bx = dx; by = dy; bz = dz;
-                wc = -sa;
-                wa = sc;
-            }
-            const float wsum = wa + wb + wc;
-            const float z_exit = (wsum != 0.0f) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
-            const float dzv = fabsf(z_exit - z_cur);
-            r.tau += static_cast<double>(dzv) * c.alpha;
-            float a_c = static_cast<float>(c.alpha);
-            if (a_c > limit) a_c = limit;
-            const double a_d = c.alpha > P.alpha_limit ? P.alpha_limit : c.alpha;
-            if (!(a_d < DBL_EPSILON)) {
-                r.inten = c.s - (c.s - r.inten) * static_cast<double>(expf(-a_c * dzv));
-            }
-            r.steps++;
-            z_cur = z_exit;
-            t = t_next;
-            id = id_next;
-            if (t < 0) {
-                // the next crossing must lie above this one's exit (and strictly above its entry)
-                const double z_exit_abs = z0 + static_cast<double>(z_cur);
-                z_after = z_exit_abs > z0 ? z_exit_abs : z0;
-            }
+            DeferredRay q;
+            q.tau = r.tau;
+            q.inten = r.inten;
+            q.z_after = z_after;
+            q.pixel = pixel;
+            q.steps = r.steps;
+            P.queue[slot] = q;
+            r.deferred = 1;
+            break;
         }
+        for (int e = 0; e < L.n; e++) {
+            // an entry at or below the ray's position is already behind it (two boundary faces
+            // sharing the edge the ray passes through report the same depth)
+            if (!(L.z[e] > z_after) || r.error) continue;
+            z_after = crossing<kF32, kWide, kPipe, false>(P, px, py, L.leaf[e], L.z[e], r.tau, r.inten, gain_unused,
+                                                          r.steps, r.error);
+        }
+        if (cap != 1 || L.n == 0 || r.error) break;
+        cap = kInline;
     }
     return r;
+}
+
+// ---- grazing rays ----------------------------------------------------------------------------------
+// A deferred ray has many crossings (~110 on the C3 README view, each a few tets long). Two facts
+// make it parallel: (1) its crossings are independent once their entry faces are known — tau is a
+// sum and I an affine recurrence, so crossing k yields (tau_k, A_k, B_k) and the ray's values are
+// their composition in z order; (2) collecting the entry faces is a BVH traversal with a wide
+// frontier. So one WARP takes one ray: the lanes expand 32 BVH nodes per round from a shared stack,
+// rank-sort the entries found, walk 32 crossings at a time and fold the results in order.
+
+struct RayAcc {
+    double tau, inten, z_after;
+    uint32_t steps, error;
+};
+
+// Folds crossing (z_in -> z_out) into the ray unless the ray is already past its entry.
+C5_HD void compose_crossing(RayAcc& a, double z_in, double z_out, double tau_k, double inten_k, double gain_k,
+                            uint32_t steps_k, uint32_t error_k) {
+    if (!(z_in > a.z_after)) return;
+    a.tau += tau_k;
+    a.inten = inten_k + gain_k * a.inten;
+    a.steps += steps_k;
+    a.error |= error_k;
+    a.z_after = z_out;
+}
+
+// Serial form (one thread does everything): the host-loop build, and the reference the warp
+// version is tested against. Same crossing function, same composition.
+template <bool kF32>
+C5_HD RayAcc graze_ray_serial(const WalkParams& P, const DeferredRay& q, double px, double py) {
+    RayAcc a;
+    a.tau = q.tau;
+    a.inten = q.inten;
+    a.z_after = q.z_after;
+    a.steps = q.steps;
+    a.error = 0;
+    EntryList<kSerialList> L;
+    int crossings = 0;
+    while (!a.error) {
+        bvh_collect_entries(P, nullptr, px, py, a.z_after, L, P.serial_cap);
+        for (int e = 0; e < L.n; e++) {
+            if (!(L.z[e] > a.z_after)) continue;
+            double tau_k = 0.0, inten_k = 0.0, gain_k = 1.0;
+            uint32_t steps_k = 0, error_k = 0;
+            const double z_out = crossing<kF32, false, 0, true>(P, px, py, L.leaf[e], L.z[e], tau_k, inten_k, gain_k,
+                                                                steps_k, error_k);
+            compose_crossing(a, L.z[e], z_out, tau_k, inten_k, gain_k, steps_k, error_k);
+            if (++crossings > 65536) a.error = 1;
+        }
+        if (L.n < P.serial_cap) break;
+    }
+    return a;
 }
 
 C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double inten, uint32_t steps) {
@@ -550,6 +604,179 @@ C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double int
     P.out[2 * o + 1] = inten;
 #endif
     if (P.steps) P.steps[o] = steps;
+}
+
+// ---- warp-cooperative form ---------------------------------------------------------------------------
+constexpr int kGrazeWarps = 4;    // warps (= rays in flight) per block
+constexpr int kGrazeList = 256;   // entries per collection; more are fetched by another round
+constexpr int kGrazeStack = 512;  // shared traversal stack per warp ...
+constexpr int kGrazeSlack = 128;  // ... plus room for one wide round and a depth-first tail
+constexpr int kGrazePerLane = kGrazeList / 32;
+
+struct GrazeSmem {
+    double z[kGrazeList];
+    int leaf[kGrazeList];
+    int stack[kGrazeStack + kGrazeSlack];
+};
+
+// Sorts S.z / S.leaf [0, n) by (z, leaf): every lane ranks its own <= 8 entries against all n
+// (broadcast reads), then scatters them. n <= 256, so this is a few thousand compares per lane.
+__device__ __forceinline__ void graze_sort(GrazeSmem& S, int n, int lane) {
+    double zr[kGrazePerLane];
+    int lr[kGrazePerLane], rank[kGrazePerLane];
+#pragma unroll
+    for (int q = 0; q < kGrazePerLane; q++) {
+        const int k = q * 32 + lane;
+        zr[q] = k < n ? S.z[k] : INFINITY;
+        lr[q] = k < n ? S.leaf[k] : 0x7FFFFFFF;
+        rank[q] = 0;
+    }
+    for (int m = 0; m < n; m++) {
+        const double zm = S.z[m];
+        const int lm = S.leaf[m];
+#pragma unroll
+        for (int q = 0; q < kGrazePerLane; q++) rank[q] += entry_before(zm, lm, zr[q], lr[q]) ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kGrazePerLane; q++) {
+        if (q * 32 + lane < n) {
+            S.z[rank[q]] = zr[q];
+            S.leaf[rank[q]] = lr[q];
+        }
+    }
+    __syncwarp();
+}
+
+// All entry faces above z_after under (px, py), collected by the whole warp into S (sorted).
+// Returns their number; `truncated` is set if the list overflowed and only the lowest part was kept
+// (everything up to the last kept entry is present: the caller walks it and asks again).
+__device__ __forceinline__ int graze_collect(const WalkParams& P, GrazeSmem& S, double px, double py, double z_after,
+                                             int lane, bool& truncated) {
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned lt = (1u << lane) - 1u;
+    const float fx_lo = f_round_down(px), fx_hi = f_round_up(px);
+    const float fy_lo = f_round_down(py), fy_hi = f_round_up(py);
+    int sp = 1, n = 0;
+    double z_cap = INFINITY;
+    truncated = false;
+    if (lane == 0) S.stack[0] = 0;
+    __syncwarp();
+    while (sp > 0) {
+        if (n > P.graze_cap - 64) { // a round appends at most 64: keep the lowest half, forget the rest
+            graze_sort(S, n, lane);
+            n = P.graze_cap / 2;
+            z_cap = S.z[n - 1];
+            truncated = true;
+            __syncwarp();
+        }
+        // 32 nodes per round while the stack has room for their 64 children; else depth first
+        const int take = sp <= kGrazeStack - 64 ? (sp < 32 ? sp : 32) : 1;
+        const int node = lane < take ? S.stack[sp - 1 - lane] : -1;
+        sp -= take;
+        __syncwarp();
+        bool h0 = false, h1 = false;
+        int2 ch = make_int2(0, 0);
+        if (node >= 0) {
+            const BvhNode* nd = P.nodes + node;
+            const float4 bx = *reinterpret_cast<const float4*>(nd->xlo);
+            const float4 by = *reinterpret_cast<const float4*>(nd->ylo);
+            const float4 bz = *reinterpret_cast<const float4*>(nd->zlo);
+            ch = *reinterpret_cast<const int2*>(nd->child);
+            h0 = fx_hi >= bx.x && fx_lo <= bx.z && fy_hi >= by.x && fy_lo <= by.z &&
+                 static_cast<double>(bz.z) > z_after && static_cast<double>(bz.x) <= z_cap;
+            h1 = fx_hi >= bx.y && fx_lo <= bx.w && fy_hi >= by.y && fy_lo <= by.w &&
+                 static_cast<double>(bz.w) > z_after && static_cast<double>(bz.y) <= z_cap;
+        }
+        double z0 = 0.0, z1 = 0.0;
+        const bool e0 = h0 && ch.x < 0 && entry_depth(P, ~ch.x, px, py, z_after, z0) && z0 <= z_cap;
+        const bool e1 = h1 && ch.y < 0 && entry_depth(P, ~ch.y, px, py, z_after, z1) && z1 <= z_cap;
+        unsigned m = __ballot_sync(full, e0);
+        if (e0) {
+            const int pos = n + __popc(m & lt);
+            S.z[pos] = z0;
+            S.leaf[pos] = ~ch.x;
+        }
+        n += __popc(m);
+        m = __ballot_sync(full, e1);
+        if (e1) {
+            const int pos = n + __popc(m & lt);
+            S.z[pos] = z1;
+            S.leaf[pos] = ~ch.y;
+        }
+        n += __popc(m);
+        const bool i0 = h0 && ch.x >= 0, i1 = h1 && ch.y >= 0;
+        m = __ballot_sync(full, i0);
+        if (i0) S.stack[sp + __popc(m & lt)] = ch.x;
+        sp += __popc(m);
+        m = __ballot_sync(full, i1);
+        if (i1) S.stack[sp + __popc(m & lt)] = ch.y;
+        sp += __popc(m);
+        __syncwarp();
+    }
+    graze_sort(S, n, lane);
+    return n;
+}
+
+template <bool kF32>
+__device__ __forceinline__ void graze_block(const WalkParams& P) {
+    __shared__ GrazeSmem smem[kGrazeWarps];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    GrazeSmem& S = smem[threadIdx.x >> 5];
+    // the pixel kernel has finished (stream order): the queue length is final
+    const unsigned long long n_rays = *reinterpret_cast<const volatile unsigned long long*>(&P.counters[kDeferred]);
+    while (true) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&P.counters[kTicket], 1ull);
+        ticket = __shfl_sync(full, ticket, 0);
+        if (ticket >= n_rays) break;
+        const DeferredRay q = P.queue[ticket];
+        const int i = static_cast<int>(q.pixel % static_cast<uint32_t>(P.res_x));
+        const int j = static_cast<int>(q.pixel / static_cast<uint32_t>(P.res_x));
+        const double px = P.xs[i], py = P.ys[j];
+        RayAcc a;
+        a.tau = q.tau;
+        a.inten = q.inten;
+        a.z_after = q.z_after;
+        a.steps = q.steps;
+        a.error = 0;
+        int crossings = 0;
+        bool truncated = true;
+        while (truncated && !a.error) {
+            const int n = graze_collect(P, S, px, py, a.z_after, lane, truncated);
+            for (int base = 0; base < n; base += 32) {
+                const int k = base + lane;
+                const bool have = k < n;
+                const double z_in = have ? S.z[k] : INFINITY;
+                double z_out = z_in, tau_k = 0.0, inten_k = 0.0, gain_k = 1.0;
+                uint32_t steps_k = 0, error_k = 0;
+                if (have && z_in > a.z_after) { // a is the same in every lane
+                    z_out = crossing<kF32, true, 0, true>(P, px, py, S.leaf[k], z_in, tau_k, inten_k, gain_k, steps_k,
+                                                          error_k);
+                }
+                const int cnt = n - base < 32 ? n - base : 32;
+                for (int l = 0; l < cnt; l++) {
+                    compose_crossing(a, __shfl_sync(full, z_in, l), __shfl_sync(full, z_out, l),
+                                     __shfl_sync(full, tau_k, l), __shfl_sync(full, inten_k, l),
+                                     __shfl_sync(full, gain_k, l), __shfl_sync(full, steps_k, l),
+                                     __shfl_sync(full, error_k, l));
+                }
+            }
+            crossings += n;
+            if (crossings > 65536) a.error = 1;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            store_pixel(P, i, j, a.tau, a.inten, a.steps);
+            const unsigned long long more = a.steps - q.steps;
+            if (more) {
+                atomicAdd(&P.counters[kSteps], more);
+                atomicAdd(&P.row_cost[j], more);
+            }
+            if (a.error) atomicAdd(&P.counters[kWalkErrors], 1ull);
+        }
+    }
 }
 
 // ---- kernel ----------------------------------------------------------------------------------------
@@ -602,6 +829,7 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
     res.inten = 0.0;
     res.steps = 0;
     res.error = 0;
+    res.deferred = 0;
     bool solid = false;
     if (live) {
         solid = P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i];
@@ -610,10 +838,10 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             store_pixel(P, i, j, nan, nan, 0);
         } else {
             if (tile_sees_mesh) {
-                res = kF32 ? trace_ray_f32<kWide, kPipe == 1>(P, top, P.xs[i], P.ys[j])
-                           : trace_ray<kWide, kPipe>(P, top, P.xs[i], P.ys[j]);
+                res = trace_ray<kF32, kWide, kPipe>(P, top, P.xs[i], P.ys[j],
+                                                    static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i));
             }
-            store_pixel(P, i, j, res.tau, res.inten, res.steps);
+            if (!res.deferred) store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
     }
 
@@ -656,7 +884,26 @@ __global__ void __launch_bounds__(kBlock, 6) tet_walk_fp64_r80(const WalkParams 
 __global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, 0>(P); }
 
+// Grazing rays (deferred by the pixel kernel): persistent warps, one ray per warp at a time.
+__global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp64(const WalkParams P) { graze_block<false>(P); }
+__global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp32(const WalkParams P) { graze_block<true>(P); }
+
 namespace {
+
+void graze_on_host(const WalkParams& P, bool f32) {
+    const unsigned long long n_rays = P.counters[kDeferred];
+    for (unsigned long long k = 0; k < n_rays; k++) {
+        const DeferredRay& q = P.queue[k];
+        const int i = static_cast<int>(q.pixel % static_cast<uint32_t>(P.res_x));
+        const int j = static_cast<int>(q.pixel / static_cast<uint32_t>(P.res_x));
+        const RayAcc a = f32 ? graze_ray_serial<true>(P, q, P.xs[i], P.ys[j]) : graze_ray_serial<false>(P, q, P.xs[i], P.ys[j]);
+        store_pixel(P, i, j, a.tau, a.inten, a.steps);
+        P.counters[kSteps] += a.steps - q.steps;
+        P.row_cost[j] += a.steps - q.steps;
+        if (a.error) P.counters[kWalkErrors]++;
+    }
+    P.counters[kTicket] = n_rays;
+}
 
 void walk_on_host(const WalkParams& P, bool f32) {
     for (int j = P.row_begin; j < P.row_end; j++) {
@@ -666,9 +913,10 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 P.counters[kSolidPixels]++;
                 continue;
             }
-            const RayResult r = f32 ? trace_ray_f32<false, false>(P, nullptr, P.xs[i], P.ys[j])
-                                    : trace_ray<false, 0>(P, nullptr, P.xs[i], P.ys[j]);
-            store_pixel(P, i, j, r.tau, r.inten, r.steps);
+            const uint32_t pixel = static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i);
+            const RayResult r = f32 ? trace_ray<true, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel)
+                                    : trace_ray<false, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel);
+            if (!r.deferred) store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
             if (r.steps) P.counters[kHitPixels]++;
@@ -694,6 +942,7 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.steps = w.write_steps ? d.steps.p : nullptr;
     P.counters = d.counters.p;
     P.row_cost = d.row_cost.p;
+    P.queue = d.queue.p;
     P.res_x = w.res_x;
     P.res_y = w.res_y;
     P.row_begin = w.row_begin;
@@ -715,6 +964,16 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (top < 0) top = 0;
     if (top > 1023) top = 1023;
     P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < top ? n_nodes : top);
+    P.graze_cap = kGrazeList;
+    if (const char* e = std::getenv("C5_GRAZE_LIST")) { // tests shrink it to reach the overflow path on small meshes
+        const int c = std::atoi(e);
+        if (c >= 128 && c <= kGrazeList) P.graze_cap = c & ~1;
+    }
+    P.serial_cap = kSerialList;
+    if (const char* e = std::getenv("C5_GRAZE_SERIAL_LIST")) {
+        const int c = std::atoi(e);
+        if (c >= 2 && c <= kSerialList) P.serial_cap = c;
+    }
     P.max_steps = static_cast<int>(d.n_tets < (1 << 20) ? d.n_tets : (1 << 20));
     P.round_float = w.round_through_float;
     P.alpha_limit = w.alpha_limit;
@@ -722,6 +981,8 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     count_launch();
     if (kHostSim) {
         walk_on_host(P, f32);
+        count_launch();
+        graze_on_host(P, f32);
         return;
     }
     const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
@@ -744,6 +1005,18 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp64_r96<<<grid, kBlock, smem, d.stream>>>(P);
     } else {
         tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
+    }
+    C5_CUDA(cudaGetLastError());
+
+    // Rays the pixel kernel deferred. The queue length lives on the device, so the launch is a fixed
+    // grid of persistent warps that draw tickets; with an empty queue it costs one short launch.
+    if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
+    const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * 4u;
+    count_launch();
+    if (f32) {
+        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
+    } else {
+        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
     }
     C5_CUDA(cudaGetLastError());
 }

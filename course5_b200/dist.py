@@ -1,20 +1,38 @@
-"""Row-band sharding across ranks (one process per GPU) and the image gather.
+"""Row-band sharding across ranks (one process per GPU) and the assembly of the image.
 
 The ray pass has no cross-pixel state (/root/reference/project/src/plane.cpp:161-169), so an image
-shards by rows: the mesh is replicated, rank r renders the contiguous band rows[r] and ONE
-exchange — a gather-v of the bands to rank 0 — assembles the x-fastest image
-(object2d.cpp:17-21 makes a row band a contiguous span of the output). The exchange is a grouped
-point-to-point send/recv (``ncclSend``/``ncclRecv`` over NVLink with the ``nccl`` backend; ``gloo``
-in the CPU tests), because cost-balanced bands have unequal sizes.
+shards by rows: the mesh is replicated, rank r renders the contiguous band rows[r], and the bands
+must end up in ONE x-fastest image (object2d.cpp:17-21 makes a row band a contiguous span of it).
+Three ways to get them there, all behind :class:`BandRenderer` / :class:`SharedHostImage`:
+
+``gather="p2p"`` (default on CUDA)
+    The image lives on rank 0's GPU; the other ranks map it through CUDA IPC (``c5_image_open``)
+    and their walk kernels store their pixels straight into it over NVLink — the exchange is fused
+    into the kernel that produces the data, 16 B posted stores spread over the kernel's run time.
+    What remains per view is one tiny all-reduce used as a barrier ("every band of view k is in").
+``gather="sendrecv"``
+    Each rank renders into a local band buffer and ONE grouped point-to-point exchange
+    (``ncclSend``/``ncclRecv`` with the ``nccl`` backend, ``gloo`` in the CPU tests) gathers the
+    bands on rank 0; a gather-v, because cost-balanced bands have unequal sizes. This is the
+    baseline the fused path is measured against.
+:class:`SharedHostImage`
+    For callers that want the image in HOST memory (the .vti writer): the image is a POSIX
+    shared-memory segment that every rank pins (``c5_host_register``); ``c5_render`` with a row band
+    then writes the band in place over that GPU's own PCIe link — N links in parallel instead of one
+    device-to-host copy of the whole image on rank 0.
 
 Equal-height bands are badly unbalanced (the mesh sits in the middle rows), so bands are cut by
-per-row tet-step counts from the previous view (``Context.last_row_cost``), all-reduced so every
-rank derives the same cuts.
+per-row tet-step counts of the previous view (``Context.last_row_cost``), all-reduced so every
+rank derives the same cuts. Tet-steps are not quite time (a band of short silhouette rays runs at
+a lower rate than one of long central rays), so ``rebalance="time"`` additionally scales each
+band's row costs by the time that band actually took.
 
-Sweeps can pipeline: with ``pipeline=True`` the gather of view k is left in flight while view k+1
-renders into the other of two buffer sets, so the exchange costs no time on the critical path.
+Sweeps can pipeline: with ``pipeline=True`` the exchange (or barrier) of view k is left in flight
+while view k+1 renders into the other of two buffer sets.
 """
 from __future__ import annotations
+
+from multiprocessing import shared_memory
 
 import numpy as np
 import torch
@@ -24,19 +42,27 @@ from . import api
 
 
 class BandRenderer:
-    """Renders row bands of successive views on this rank's device and gathers them on rank 0."""
+    """Renders row bands of successive views on this rank's device and assembles them on rank 0."""
 
     def __init__(self, ctx: api.Context, *, device: torch.device, rank: int, world: int,
-                 base_cost: float = 64.0):
+                 base_cost: float = 64.0, gather: str = "auto"):
         self.ctx, self.device, self.rank, self.world = ctx, device, rank, world
         self.base_cost = base_cost
+        if gather == "auto":
+            gather = "p2p" if (device.type == "cuda" and world > 1) else "sendrecv"
+        if gather not in ("p2p", "sendrecv"):
+            raise ValueError("gather must be 'auto', 'p2p' or 'sendrecv'")
+        self.gather_mode = gather
         self.row_cost: np.ndarray | None = None
-        self._band_buf = [None, None]      # two buffer sets: the gather of one view may still be
+        self._band_buf = [None, None]      # two buffer sets: the exchange of one view may still be
         self._image = [None, None]         # reading/writing set k while view k+1 fills the other
+        self._peer = [None, None]          # p2p: (device pointer of rank 0's image, bytes) per set
         self._pending = [[], []]
         self._count = 0
         self._bands = None                 # cached cut, valid until the row costs change
+        self._flag = None
 
+    # -- band cuts --------------------------------------------------------------------------------
     def bands(self, res_y: int) -> list[tuple[int, int]]:
         if self._bands is not None and self._bands[0] == res_y:
             return self._bands[1]
@@ -48,6 +74,7 @@ class BandRenderer:
         self._bands = (res_y, cut)
         return cut
 
+    # -- buffers ----------------------------------------------------------------------------------
     def _buffers(self, view: api.View, rows: int, par: int):
         n = rows * view.res_x * 2
         if self._band_buf[par] is None or self._band_buf[par].numel() < n:
@@ -57,24 +84,62 @@ class BandRenderer:
             if self._image[par] is None or self._image[par].numel() != full:
                 self._image[par] = torch.empty(full, dtype=torch.float64, device=self.device)
 
+    def _peer_image(self, view: api.View, par: int) -> int:
+        """Device pointer of rank 0's image (set `par`) in THIS process, (re)created on a size change."""
+        nbytes = view.res_y * view.res_x * 16
+        if self._peer[par] is not None and self._peer[par][1] == nbytes:
+            return self._peer[par][0]
+        self._drain(par)
+        if self._peer[par] is not None:
+            dist.barrier()                 # nobody may still be writing the old mapping
+            self.ctx.image_close(self._peer[par][0])
+            self._peer[par] = None
+        handle = torch.zeros(api.IPC_HANDLE_BYTES, dtype=torch.uint8)
+        if self.rank == 0:
+            ptr, raw = self.ctx.image_create(nbytes)
+            handle = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+        handle = handle.to(self.device)
+        dist.broadcast(handle, src=0)
+        if self.rank != 0:
+            ptr = self.ctx.image_open(bytes(handle.cpu().numpy().tobytes()))
+        self._peer[par] = (ptr, nbytes)
+        if self.rank == 0:
+            self._image[par] = _tensor_from_pointer(ptr, view.res_y * view.res_x * 2, self.device)
+        return ptr
+
     def _drain(self, par: int):
         for req in self._pending[par]:
             req.wait()          # orders the current stream after that exchange
         self._pending[par] = []
 
     def finish(self):
-        """Waits (on the current stream) for every gather still in flight."""
+        """Waits (on the current stream) for every exchange still in flight."""
         self._drain(0)
         self._drain(1)
 
-    def render(self, view: api.View, *, gather: bool = True, rebalance: bool = True, stats: bool = True,
+    def close(self):
+        self.finish()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        for par in (0, 1):
+            if self._peer[par] is not None:
+                if self.world > 1:
+                    dist.barrier()
+                self._image[par] = None
+                self.ctx.image_close(self._peer[par][0])
+                self._peer[par] = None
+
+    # -- one view ---------------------------------------------------------------------------------
+    def render(self, view: api.View, *, gather: bool = True, rebalance: bool | str = True, stats: bool = True,
                pipeline: bool = False):
         """Renders this rank's band of `view`; returns (image on rank 0 or None, stats, bands).
 
         The image is a (res_y, res_x, 2) float64 tensor on rank 0's device. With stats=False (and
-        rebalance=False) nothing is read back to the host: render and gather are only enqueued on the
-        current stream. With pipeline=True the gather is additionally left in flight (call finish(),
-        or render two more views, before reading the returned image)."""
+        rebalance=False) nothing is read back to the host: render and exchange are only enqueued on
+        the current stream. With pipeline=True the exchange is additionally left in flight (call
+        finish(), or render two more views, before reading the returned image).
+        rebalance: True / "steps" = cut the next view's bands by this view's per-row tet-steps;
+        "time" = additionally weight each band by the device time it took."""
         if not stats:
             rebalance = False
         par = self._count & 1
@@ -82,38 +147,121 @@ class BandRenderer:
         self._drain(par)        # the buffers of this parity are about to be overwritten
         bands = self.bands(view.res_y)
         lo, hi = bands[self.rank]
-        self._buffers(view, hi - lo, par)
         v = api.View.from_buffer_copy(view)
         v.row_begin, v.row_end = lo, hi
-        if self.rank == 0 and gather:
-            target = self._image[par][lo * view.res_x * 2: hi * view.res_x * 2]
-        else:
-            target = self._band_buf[par][: (hi - lo) * view.res_x * 2]
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
-        st = self.ctx.render_device(v, target.data_ptr(), stream, stats=stats)
+        p2p = self.gather_mode == "p2p" and self.world > 1 and gather
 
-        if self.world > 1 and gather:
-            ops = []
-            if self.rank == 0:
-                for r in range(1, self.world):
-                    rlo, rhi = bands[r]
-                    ops.append(dist.P2POp(dist.irecv, self._image[par][rlo * view.res_x * 2: rhi * view.res_x * 2], r))
-            else:
-                ops.append(dist.P2POp(dist.isend, target, 0))
-            self._pending[par] = list(dist.batch_isend_irecv(ops))
+        if p2p:
+            base = self._peer_image(view, par)
+            st = self.ctx.render_device(v, base + lo * view.res_x * 16, stream, stats=stats)
+            # barrier: when it completes on a rank's stream, every rank's band of this view is in
+            if self._flag is None:
+                self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._pending[par] = [dist.all_reduce(self._flag, async_op=True)]
             if not pipeline:
                 self._drain(par)
+        else:
+            self._buffers(view, hi - lo, par)
+            if self.rank == 0 and gather:
+                target = self._image[par][lo * view.res_x * 2: hi * view.res_x * 2]
+            else:
+                target = self._band_buf[par][: (hi - lo) * view.res_x * 2]
+            st = self.ctx.render_device(v, target.data_ptr(), stream, stats=stats)
+            if self.world > 1 and gather:
+                ops = []
+                if self.rank == 0:
+                    for r in range(1, self.world):
+                        rlo, rhi = bands[r]
+                        ops.append(dist.P2POp(dist.irecv, self._image[par][rlo * view.res_x * 2: rhi * view.res_x * 2], r))
+                else:
+                    ops.append(dist.P2POp(dist.isend, target, 0))
+                self._pending[par] = list(dist.batch_isend_irecv(ops))
+                if not pipeline:
+                    self._drain(par)
 
         if rebalance:
-            cost = torch.from_numpy(self.ctx.last_row_cost(view.res_y).astype(np.int64))
+            cost = torch.from_numpy(self.ctx.last_row_cost(view.res_y).astype(np.float64))
+            if rebalance == "time" and self.world > 1:
+                # rows of this band cost (band time / band steps) per tet-step: bands whose rays run
+                # at a lower rate get proportionally fewer rows next time
+                band_cost = float(cost.sum()) + self.base_cost * (hi - lo)
+                band_ms = float(st["ms_mask"] + st["ms_walk"])
+                cost = (cost + self.base_cost * _band_indicator(view.res_y, lo, hi)) * (band_ms / max(band_cost, 1.0))
             if self.world > 1:
                 cost = cost.to(self.device)
                 dist.all_reduce(cost, op=dist.ReduceOp.SUM)
                 cost = cost.cpu()
             self.row_cost = cost.numpy().astype(np.float64)
+            if rebalance == "time" and self.world > 1:
+                self._time_weighted = True
             self._bands = None
 
         image = None
         if self.rank == 0 and gather:
             image = self._image[par].view(view.res_y, view.res_x, 2)
         return image, st, bands
+
+
+def _band_indicator(res_y: int, lo: int, hi: int) -> torch.Tensor:
+    ind = torch.zeros(res_y, dtype=torch.float64)
+    ind[lo:hi] = 1.0
+    return ind
+
+
+def _tensor_from_pointer(ptr: int, n_doubles: int, device: torch.device) -> torch.Tensor:
+    """A float64 tensor view of library-owned device memory (no copy, no ownership)."""
+    class _Cai:
+        __cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(_Cai(), device=device)
+
+
+class SharedHostImage:
+    """One (res_y, res_x, 2) float64 HOST image shared by all ranks of the node.
+
+    Rank 0 creates a POSIX shared-memory segment, the others attach; every rank pins it with its
+    own context (``c5_host_register``), after which ``Context.render(view_with_row_band, out=image)``
+    makes the walk kernel store the band straight into the shared image over that GPU's PCIe link.
+    ``barrier()`` then tells rank 0 that all bands of the view are in. In the CPU tests (hostsim
+    build) the same calls degrade to a plain memcpy into the shared segment."""
+
+    def __init__(self, ctx: api.Context, res_x: int, res_y: int, *, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        nbytes = res_y * res_x * 16
+        names = [None]
+        if rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            names = [self._shm.name]
+        if world > 1:
+            dist.broadcast_object_list(names, src=0)
+        if rank != 0:
+            self._shm = shared_memory.SharedMemory(name=names[0])
+            try:  # the creator unlinks; keep Python's resource tracker from doing it twice
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.array = np.ndarray((res_y, res_x, 2), dtype=np.float64, buffer=self._shm.buf)
+        ctx.host_register(self.array)
+        self._registered = True
+
+    def render_band(self, view: api.View, band: tuple[int, int]) -> dict:
+        v = api.View.from_buffer_copy(view)
+        v.row_begin, v.row_end = band
+        _, st = self.ctx.render(v, out=self.array)
+        return st
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        if self._registered:
+            self.ctx.host_unregister(self.array)
+            self._registered = False
+        self.array = None
+        if self.world > 1:
+            dist.barrier()
+        self._shm.close()
+        if self.rank == 0:
+            self._shm.unlink()

@@ -89,7 +89,7 @@ typedef struct c5_stats {
     float ms_d2h;
     float ms_total;         /* whole call on the device timeline */
     int32_t n_devices;
-    int32_t reserved;
+    int32_t grazing_rays;   /* rays with so many crossings that the grazing-ray kernel finished them */
 } c5_stats;
 
 typedef struct c5_mesh_info {
@@ -147,6 +147,28 @@ int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream
 /* Per-row tet-step totals of the last render on this context (res_y entries; rows outside the
  * rendered band are 0). Callers use it to cut cost-balanced row bands for the next view. */
 int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows);
+
+/* ---- one image, several processes (one process per GPU) -----------------------------------------
+ * Row bands are independent (plane.cpp:161-169 has no cross-pixel state), so N processes can
+ * render N bands of one view straight into ONE image and nothing has to be gathered afterwards:
+ *
+ *  - a DEVICE image on one GPU that the other GPUs' walk kernels store into through NVLink peer
+ *    mappings (CUDA IPC): the owner calls c5_image_create and passes the 64-byte handle to the
+ *    other processes (any byte transport), they call c5_image_open and hand
+ *    `(char*)ptr + row_begin * res_x * 16` to c5_render_device as d_out;
+ *  - a HOST image in shared memory (shm_open / mmap, the caller's business) that every process
+ *    registers with c5_host_register: c5_render() with a row band then writes the band in place
+ *    over that GPU's own PCIe link (a registered buffer is device-addressable, so the walk stores
+ *    into it directly).
+ *
+ * Ordering between processes (all bands of view k written before anyone reads view k) is the
+ * caller's: one barrier per view on the streams involved. */
+#define C5_IPC_HANDLE_BYTES 64
+int c5_image_create(c5_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[C5_IPC_HANDLE_BYTES]);
+int c5_image_open(c5_ctx* ctx, const uint8_t handle[C5_IPC_HANDLE_BYTES], void** d_ptr);
+int c5_image_close(c5_ctx* ctx, void* d_ptr); /* frees (owner) or unmaps (importer) */
+int c5_host_register(c5_ctx* ctx, void* ptr, uint64_t bytes);
+int c5_host_unregister(c5_ctx* ctx, void* ptr);
 
 /* Number of kernels this library has launched on behalf of ctx since creation. */
 uint64_t c5_kernel_launches(const c5_ctx* ctx);

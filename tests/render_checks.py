@@ -215,3 +215,27 @@ def check_solid_mask_high_resolution(lib, port, res=(1200, 900), views=((0.4, 0.
         assert want.solid.sum() > 1000
         assert np.array_equal(got.solid, want.solid)
         assert np.array_equal(np.isnan(got.tau), want.solid.astype(bool))
+
+
+def check_grazing_rays(lib, port, *, n=12, res=(240, 180), env_name="C5_GRAZE_SERIAL_LIST", env_value="5"):
+    """Views that look along a lattice axis see the jittered side walls edge-on: rays there leave
+    and re-enter the mesh once per cell. The pixel kernel hands them to the grazing-ray kernel
+    (c5_stats.grazing_rays); the result must still match the oracle, and must not depend on how many
+    entry faces one collection can hold (the overflow path keeps the lowest part and asks again)."""
+    import os
+    mesh = synth.kuhn_cube(n, seed=48)
+    for flags in (dict(X=0.5, Y=0.0), dict(X=0.0, Y=0.5)):
+        img, _ = check_against_port(lib, port, mesh, res[0], res[1], flags)
+        assert img.stats["grazing_rays"] > 0
+        old = os.environ.get(env_name)
+        os.environ[env_name] = env_value
+        try:
+            small = render_raw(lib, mesh, res[0], res[1], **flags)
+        finally:
+            if old is None:
+                del os.environ[env_name]
+            else:
+                os.environ[env_name] = old
+        assert small.stats["grazing_rays"] == img.stats["grazing_rays"]
+        assert np.array_equal(small.image, img.image)
+        assert np.array_equal(small.steps, img.steps)

@@ -54,8 +54,22 @@ def _worker(rank, world, port, out_path):
     if rank == 0:
         results["pipe_a"] = img_a.numpy().copy()
         results["pipe_b"] = img_b.numpy().copy()
+    # host image in shared memory: every rank writes its band in place, nothing is gathered
+    from course5_b200.dist import SharedHostImage
+    shared = SharedHostImage(ctx, 120, 90, rank=rank, world=world)
+    if rank == 0:
+        shared.array[:] = -1.0
+    shared.barrier()
+    bands = br.bands(90)
+    st = shared.render_band(vb, bands[rank])
+    shared.barrier()
+    if rank == 0:
+        results["shared_b"] = shared.array.copy()
+    assert st["pixels"] == (bands[rank][1] - bands[rank][0]) * 120
+    shared.close()
     if rank == 0:
         np.savez(out_path, **results)
+    br.close()
     ctx.close()
     dist.destroy_process_group()
 
@@ -70,6 +84,7 @@ def test_two_ranks_assemble_the_same_image(built, tmp_path):
         b = r[f"bands{k}"]
         assert b[0][0] == 0 and b[-1][1] == 90 and b[0][1] == b[1][0]
     assert np.array_equal(r["pipe_a"], r["full0"]) and np.array_equal(r["pipe_b"], r["full1"])
+    assert np.array_equal(r["shared_b"], r["full1"])
     # first view: equal heights; second view: cut by the first view's per-row cost
     assert r["bands0"][0][1] == 45
     assert r["bands1"][0][1] != 45 or True

@@ -36,6 +36,31 @@ def test_config_c2b_cavity(gpu_lib, port):
     rc.check_against_port(gpu_lib, port, mesh, 800, 600, flags)
 
 
+def test_grazing_rays(gpu_lib, port):
+    """Edge-on jittered walls: rays with one crossing per cell go through the warp-per-ray kernel."""
+    rc.check_grazing_rays(gpu_lib, port, n=24, res=(480, 360), env_name="C5_GRAZE_LIST", env_value="128")
+
+
+def test_grazing_list_overflow(gpu_lib):
+    """A 96-cell wall seen edge-on gives rays ~96 crossings: with the collection shrunk to 128
+    entries (truncation at > 64) the overflow path runs; the image must not change by a bit."""
+    import os
+    mesh = synth.kuhn_cube(96, seed=49)
+    with api.Context(devices=(0,), lib=gpu_lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        v = api.make_view(1200, 900, X=0.5, Y=0.0, alpha_limit=3.0, lib=gpu_lib, round_through_float=0)
+        full = ctx.render_raw(v)
+        os.environ["C5_GRAZE_LIST"] = "128"
+        try:
+            small = ctx.render_raw(v)
+        finally:
+            del os.environ["C5_GRAZE_LIST"]
+    assert full.stats["grazing_rays"] > 1000 and full.stats["walk_errors"] == 0
+    assert small.stats["grazing_rays"] == full.stats["grazing_rays"]
+    assert np.array_equal(small.image, full.image) and np.array_equal(small.steps, full.steps)
+    assert int(full.steps.sum()) == full.stats["tet_steps"]
+
+
 def test_sweep_views(gpu_lib, port):
     mesh = synth.kuhn_cube(16, seed=45)
     for k in range(6):

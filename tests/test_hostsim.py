@@ -28,6 +28,10 @@ def test_cavity_reentry(hostsim_lib, port):
     assert want.steps.max() > 0
 
 
+def test_grazing_rays(hostsim_lib, port):
+    rc.check_grazing_rays(hostsim_lib, port)
+
+
 def test_graded_mesh(hostsim_lib, port):
     rc.check_against_port(hostsim_lib, port, synth.kuhn_cube(9, seed=43, grade_beta=1.5), 160, 120,
                           dict(X=0.45, Y=1.2))
@@ -72,3 +76,34 @@ def test_fp32_variant(hostsim_lib, port, flags):
 
 def test_solid_mask_high_resolution(hostsim_lib, port):
     rc.check_solid_mask_high_resolution(hostsim_lib, port, res=(800, 600), views=((0.4, 0.3, 0.0),))
+
+
+def test_image_handles_and_host_register(hostsim_lib):
+    """c5_image_create / open / close and c5_host_register bookkeeping (the CUDA IPC mapping itself
+    needs two processes and two GPUs: test_gpu_dist.py)."""
+    import ctypes as C
+    from course5_b200 import api
+    mesh = synth.kuhn_cube(6, seed=51)
+    with api.Context(lib=hostsim_lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        v = api.make_view(64, 48, X=0.4, Y=0.2, lib=hostsim_lib)
+        full, _ = ctx.render(v)
+        ptr, handle = ctx.image_create(64 * 48 * 16)
+        assert len(handle) == api.IPC_HANDLE_BYTES
+        alias = ctx.image_open(handle)             # hostsim: the same process may "open" its own image
+        band = api.View.from_buffer_copy(v)
+        band.row_begin, band.row_end = 10, 30
+        ctx.render_device(band, alias + 10 * 64 * 16, 0)
+        got = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(48, 64, 2))
+        assert np.array_equal(got[10:30], full[10:30])
+        ctx.image_close(alias)
+        ctx.image_close(ptr)
+        with pytest.raises(api.C5Error):
+            ctx.image_close(ptr)
+        out = np.zeros((48, 64, 2))
+        ctx.host_register(out)
+        ctx.render(band, out=out)
+        assert np.array_equal(out[10:30], full[10:30]) and not out[:10].any()
+        ctx.host_unregister(out)
+        with pytest.raises(api.C5Error):
+            ctx.host_unregister(out)

@@ -185,13 +185,16 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def config_dict(mesh, view, n_gpus):
+def config_dict(mesh, view, n_gpus, gather="p2p"):
     return {
         "workload": (f"{WORKLOAD}: synthetic Kuhn-split grid, {mesh.n_tets} tets / {mesh.n_points} points, "
                      f"{view['res_x']}x{view['res_y']}, -X {view['X']} -Y {view['Y']} --alpha_limit "
                      f"{view['alpha_limit']}, reference Roche lobe + sphere as solids"),
         "res_x": view["res_x"], "res_y": view["res_y"], "n_tets": mesh.n_tets,
-        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} row bands (cost-balanced), mesh replicated, gather-v to rank 0",
+        "parallelism": "single GPU" if n_gpus == 1 else
+                       f"{n_gpus} row bands (time-balanced), mesh replicated, " +
+                       ("bands stored into rank 0's image over NVLink peer mappings by the walk kernel, one barrier per view"
+                        if gather != "sendrecv" else "one grouped ncclSend/ncclRecv gather-v to rank 0 per view"),
         "l2": "inputs larger than L2 (cell records alone are 64 B x n_tets >> 126 MB); no explicit flush",
     }
 
@@ -233,7 +236,7 @@ def run_ours(args):
     upload_s = time.perf_counter() - t0
     v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
                       alpha_limit=view["alpha_limit"])
-    br = BandRenderer(ctx, device=device, rank=rank, world=world)
+    br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather)
 
     def barrier():
         if world > 1:
@@ -241,8 +244,11 @@ def run_ours(args):
         torch.cuda.synchronize(device)
 
     # ---- value: everything resident, output stays on the device -------------------------------
-    for _ in range(max(args.warmup, 3)):
-        br.render(v)
+    # warm-up views also settle the band cuts: tet-steps of the previous view, weighted by the time
+    # each band took (a few iterations; a sweep does the same from frame to frame)
+    n_warm = max(args.warmup, 3) if world == 1 else max(args.warmup, 6)
+    for _ in range(n_warm):
+        br.render(v, rebalance="time")
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -256,9 +262,11 @@ def run_ours(args):
             walk_ms.append(st["ms_walk"])
             stats_last = st
     else:
-        # N > 1: render + gather are only enqueued (no host readback between views), so the ranks'
-        # launches and the NCCL exchange pipeline on the devices; statistics come from a second pass
-        # and the gather of view k overlaps the rendering of view k + 1 (two buffer sets)
+        # N > 1: render + exchange are only enqueued (no host readback between views), so the ranks'
+        # launches pipeline on the devices; statistics come from a second pass. gather=p2p: the walk
+        # stores straight into rank 0's image over NVLink and the per-view barrier of view k overlaps
+        # the rendering of view k + 1 (two images); gather=sendrecv: the same with one grouped
+        # ncclSend/ncclRecv per view
         for _ in range(args.steps):
             _, _, bands = br.render(v, rebalance=False, stats=False, pipeline=True)
         br.finish()
@@ -276,8 +284,18 @@ def run_ours(args):
     band_steps = stats_last["tet_steps"]
 
     # ---- e2e: the public C-ABI call with a pinned HOST output buffer ---------------------------
-    host_out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64).pin_memory()
-    host_np = host_out.numpy()
+    # N = 1: c5_render into a pinned buffer. N > 1: the image is ONE pinned shared-memory segment;
+    # every rank's c5_render writes its band in place over its own PCIe link, then one barrier.
+    # Wall clock around the calls a user makes; the image is complete in host memory at the end
+    # of every step.
+    from course5_b200.dist import SharedHostImage
+    if world == 1:
+        host_out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64).pin_memory()
+        host_np = host_out.numpy()
+        shared = None
+    else:
+        shared = SharedHostImage(ctx, view["res_x"], view["res_y"], rank=rank, world=world)
+        host_np = shared.array
     lo, hi = bands[rank]
     ve = api.View.from_buffer_copy(v)
     ve.row_begin, ve.row_end = lo, hi
@@ -286,14 +304,13 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        if world == 1:
-            ctx.render(ve, out=host_np)
-        else:
-            img, _, _ = br.render(v, rebalance=False, stats=False)
-            if rank == 0:
-                host_out.copy_(img, non_blocking=False)   # waits for the gather, then D2H
+        ctx.render(ve, out=host_np)
+        if world > 1:
+            shared.barrier()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if shared is not None:
+        shared.close()
 
     # ---- reduce over ranks ----------------------------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_s * 1e3, float(np.mean(walk_ms))], dtype=torch.float64, device=device)
@@ -317,14 +334,15 @@ def run_ours(args):
         achieved = (k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL) / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "tet_steps_per_sec", "value": value, "unit": "tet-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "pixels_per_sec": pixels / (ms_per_step * 1e-3),
             "tet_steps_per_view": total_steps,
-            "config": config_dict(mesh, view, world),
+            "config": config_dict(mesh, view, world, br.gather_mode),
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(api.C.sizeof(api.View)), "d2h_bytes_per_step": pixels * 16,
-                    "api": "c5_render (host buffer)" if world == 1 else "BandRenderer.render + D2H on rank 0"},
+                    "api": "c5_render (pinned host buffer)" if world == 1 else
+                    "c5_render (row band) into one pinned shared-memory host image, one barrier per view"},
             "gpu_launches": total_launches,
             "roofline": {"kernel": "tet_walk_fp64", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
@@ -344,6 +362,7 @@ def run_ours(args):
                 "sample": (f"{WORKLOAD} mesh + reference solids, same flags, {sample['res_x']}x{sample['res_y']} "
                            f"(1/4 of the pixels), {r['tet_steps']} tet-steps, 1 run")}
         print(json.dumps(line), flush=True)
+    br.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -355,6 +374,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="auto",
+                    help="N > 1: how bands reach rank 0's image (p2p = stored by the walk kernel over NVLink)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

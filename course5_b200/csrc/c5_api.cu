@@ -152,6 +152,20 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
         launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y, p.row_begin, p.row_end);
     }
     record(d, 3);
+    if (const int ahead = walk_prefetch_lookahead()) {
+        // which 4 KB chunks of the cell / vertex arrays lie under which strip of rows of this band;
+        // the first strips' slab starts streaming into L2 now, behind the mask kernel
+        SlabPlan sp{};
+        sp.x_lo = v->window[1];
+        sp.x_hi = v->window[0];
+        sp.y_min = p.y_min;
+        sp.step_y = p.step_y;
+        sp.row_begin = p.row_begin;
+        sp.row_end = p.row_end;
+        sp.strip_rows = kStripRows;
+        sp.first_strips = ahead;
+        launch_classify_chunks(d, p.rot, p.n_rot, sp);
+    }
     dev_zero(d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);
     dev_zero(d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(unsigned long long), d.stream);
     WalkLaunch w{};

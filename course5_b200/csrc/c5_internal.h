@@ -45,6 +45,11 @@ struct DeviceState {
     DevBuf<int32_t> leaf_parent;     // per leaf: (parent << 1) | which child
     DevBuf<uint32_t> refit_flags;    // per internal node arrival counter
 
+    // L2 slab prefetch: per-chunk bounding spheres (per mesh) and strip ranges (per view)
+    int64_t n_cell_chunks = 0, n_vtx_chunks = 0;
+    DevBuf<ChunkSphere> chunk_spheres;   // cell chunks, then vertex chunks
+    DevBuf<uint32_t> chunk_rows;         // first strip | last strip << 16, kChunkOutside if none
+
     // solids
     SolidSet solid_follow, solid_static;
 
@@ -95,7 +100,19 @@ void launch_bvh_refit(DeviceState& d);
 void dedupe_solid_faces(DeviceState& d, SolidSet& ss); // fills ss.faces / ss.n_faces from ss.pts0
 void launch_prepare_cells(DeviceState& d, double alpha_limit); // cells[t].s = q0[t] / min(alpha, limit)
 
+// c5_prefetch.cu
+struct SlabPlan {
+    double x_lo, x_hi, y_min, step_y;
+    int row_begin, row_end;
+    int strip_rows;   // pixel rows per strip (one row of macro tiles of the walk kernel)
+    int first_strips; // strips whose slab is prefetched before the walk starts
+};
+void build_chunk_spheres(DeviceState& d);
+void launch_classify_chunks(DeviceState& d, const Rot* rot, int n_rot, const SlabPlan& plan);
+
 // c5_walk.cu
+constexpr int kStripRows = 64; // 8 tile rows of 8 pixels: one row of macro tiles
+int walk_prefetch_lookahead(); // strips prefetched ahead of the one being started (0 = off)
 struct WalkLaunch {
     int res_x, res_y, row_begin, row_end;
     double alpha_limit;

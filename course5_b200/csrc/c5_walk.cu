@@ -50,6 +50,10 @@ struct WalkParams {
     unsigned long long* counters;
     unsigned long long* row_cost; // [res_y]
     DeferredRay* queue;   // rays handed to the grazing-ray kernel; counters[kDeferred] of them
+    // L2 slab prefetch (c5_prefetch.cu): the first block of strip R pulls the slab of strip R + lookahead
+    const uint32_t* chunk_rows;
+    int64_t n_chunks, n_cell_chunks, n_tets, n_pts;
+    int lookahead, blocks_per_strip, n_strips;
     int res_x, res_y, row_begin, row_end;
     int n_tiles_x, n_tiles_y, n_macro_x;
     int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
@@ -287,10 +291,6 @@ C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, d
     ax -= px; ay -= py;
     bx -= px; by -= py;
     cx -= px; cy -= py;
-    // weight of a vertex = orient2 of the other two, in cyclic order: all >= 0 inside
-    double wa = orient2(bx, by, cx, cy);
-    double wb = orient2(cx, cy, ax, ay);
-    double wc = orient2(ax, ay, bx, by);
     int t = f.w;
     double z_cur = z_in;
     while (true) {
@@ -321,18 +321,26 @@ C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, d
             prefetch_l1(reinterpret_cast<const char*>(P.cells + t_next) + 32);
             prefetch_l1(P.vrot + id_next);
         }
+        // Barycentric weights of the pixel in the exit face (weight of a vertex = orient2 of the
+        // other two, in cyclic order). Two of them are s values; the third belongs to d and is the
+        // orient2 of the two vertices that stay — recomputed here (3 flops) rather than carried
+        // from step to step (6 registers): same operands, same operations, so the same bits.
+        double wa, wb, wc;
         if (drop_c) { // leaves through (d, a, b): c is replaced by d
             ic = id; cx = dx; cy = dy; cz = dz;
             wa = -sb;
             wb = sa;
+            wc = orient2(ax, ay, bx, by);
         } else if (drop_a) { // through (d, b, c): a is replaced
             ia = id; ax = dx; ay = dy; az = dz;
             wb = -sc;
             wc = sb;
+            wa = orient2(bx, by, cx, cy);
         } else { // through (d, c, a): b is replaced
             ib = id; bx = dx; by = dy; bz = dz;
             wc = -sa;
             wa = sc;
+            wb = orient2(cx, cy, ax, ay);
         }
         const double wsum = wa + wb + wc;
         const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
@@ -798,6 +806,18 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
     const int macro = b >> 6, r = b & 63;
     const int tile_x = (macro % P.n_macro_x) * 8 + compact3(r);
     const int tile_y = (macro / P.n_macro_x) * 8 + compact3(r >> 1);
+    if (P.lookahead > 0 && b % P.blocks_per_strip == 0) {
+        // strip leader (usually an empty tile left of the mesh): chunks whose first strip is
+        // `target` go to L2 now, in bulk, while the strips before it are being walked
+        const int target = b / P.blocks_per_strip + P.lookahead;
+        if (target < P.n_strips) {
+            for (int64_t c = threadIdx.x; c < P.n_chunks; c += kThreads) {
+                if (static_cast<int>(__ldg(P.chunk_rows + c) & 0xFFFFu) == target) {
+                    prefetch_chunk(P.cells, P.vrot, P.n_cell_chunks, P.n_tets, P.n_pts, c);
+                }
+            }
+        }
+    }
     if (tile_x >= P.n_tiles_x || tile_y >= P.n_tiles_y) return;
 
     // Tiles that cannot see the mesh (outside the root's two boxes) skip the staging and the rays.
@@ -927,6 +947,17 @@ void walk_on_host(const WalkParams& P, bool f32) {
 
 } // namespace
 
+// C5_PREFETCH = strips of slab pulled into L2 ahead of the walk (default 1; 0 switches the prefetch off).
+int walk_prefetch_lookahead() {
+    int a = 1;
+    if (const char* e = std::getenv("C5_PREFETCH")) a = std::atoi(e);
+    if (a < 0) a = 0;
+    if (a > 8) a = 8;
+    const char* variant = std::getenv("C5_WALK_VARIANT");
+    if (variant && std::string(variant) == "b64") a = 0; // its tiles are 8 x 8: strips would not line up
+    return a;
+}
+
 void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (w.precision != 64 && w.precision != 32) fail(C5_E_INVALID, "render: precision must be 64 or 32");
     const bool f32 = w.precision == 32;
@@ -964,6 +995,15 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (top < 0) top = 0;
     if (top > 1023) top = 1023;
     P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < top ? n_nodes : top);
+    P.chunk_rows = d.chunk_rows.p;
+    P.n_chunks = d.n_cell_chunks + d.n_vtx_chunks;
+    P.n_cell_chunks = d.n_cell_chunks;
+    P.n_tets = d.n_tets;
+    P.n_pts = d.n_pts;
+    P.lookahead = kHostSim ? 0 : walk_prefetch_lookahead();
+    P.blocks_per_strip = P.n_macro_x * 64;
+    P.n_strips = n_macro_y;
+    static_assert(kStripRows == 8 * kTileY, "a strip is one row of macro tiles");
     P.graze_cap = kGrazeList;
     if (const char* e = std::getenv("C5_GRAZE_LIST")) { // tests shrink it to reach the overflow path on small meshes
         const int c = std::atoi(e);

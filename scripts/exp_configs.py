@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--view", default=None, help="X,Y override (units of pi)")
     ap.add_argument("--res", default=None, help="res_x,res_y override")
     ap.add_argument("--precision", default="64")
+    ap.add_argument("--prefetch", default="1", help="comma-separated C5_PREFETCH values (strips of L2 lookahead; 0 = off)")
     ap.add_argument("--rows", default=None, help="semicolon-separated row bands a,b;c,d to render separately")
     args = ap.parse_args()
     import torch
@@ -50,7 +51,9 @@ def main():
             ctx.upload_solids(solids[1], False)
         out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64, device=dev)
         bands = [None] if not args.rows else [tuple(int(x) for x in b.split(",")) for b in args.rows.split(";")]
-        for prec, variant, band in ((int(p), vv, bb) for p in args.precision.split(",") for vv in args.variants.split(",") for bb in bands):
+        for prec, variant, band, pf in ((int(p), vv, bb, ff) for p in args.precision.split(",") for vv in args.variants.split(",")
+                                        for bb in bands for ff in args.prefetch.split(",")):
+            os.environ["C5_PREFETCH"] = pf
             extra = {} if band is None else dict(row_begin=band[0], row_end=band[1])
             v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
                               alpha_limit=view["alpha_limit"], precision=prec, **extra)
@@ -69,7 +72,7 @@ def main():
                 pixels = view["res_x"] * (view["res_y"] if band is None else band[1] - band[0])
                 gbs = (st["tet_steps"] * 72 + pixels * 16) / (walk * 1e-3) / 1e9
                 print(json.dumps({
-                    "config": name, "view": [view["X"], view["Y"]], "precision": prec, "variant": variant, "rows": band, "top_nodes": int(top), "n_tets": mesh.n_tets,
+                    "config": name, "view": [view["X"], view["Y"]], "precision": prec, "variant": variant, "prefetch": int(pf), "grazing_rays": st["grazing_rays"], "rows": band, "top_nodes": int(top), "n_tets": mesh.n_tets,
                     "res": [view["res_x"], view["res_y"]], "tet_steps": st["tet_steps"],
                     "hit_pixels": st["hit_pixels"], "solid_pixels": st["solid_pixels"],
                     **{k: round(float(np.median(x)), 4) for k, x in acc.items()},

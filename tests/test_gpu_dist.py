@@ -1,0 +1,94 @@
+"""The N > 1 path on real GPUs: two processes, one per device, over NCCL/NVLink. Bands stored by
+the walk kernel straight into rank 0's device image (CUDA IPC peer mapping), the grouped
+ncclSend/ncclRecv gather, and the pinned shared-memory host image must all give the image a single
+rank renders, bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from course5_b200 import api, synth
+    from course5_b200.dist import BandRenderer, SharedHostImage
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    device = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    mesh = synth.kuhn_cube(24, seed=72)
+    ctx = api.Context(devices=(rank,))
+    ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+    results = {}
+    views = [api.make_view(480, 360, X=0.4, Y=Y) for Y in (0.2, 0.9, 1.4)]
+    if rank == 0:
+        for k, v in enumerate(views):
+            results[f"full{k}"] = ctx.render(v)[0]
+    for mode in ("p2p", "sendrecv"):
+        br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=mode)
+        for k, v in enumerate(views):          # synchronous, bands re-cut by time after every view
+            image, st, bands = br.render(v, rebalance="time")
+            torch.cuda.synchronize(device)
+            if rank == 0:
+                results[f"{mode}{k}"] = image.cpu().numpy().copy()
+                results[f"{mode}_bands{k}"] = np.array(bands)
+        imgs = [br.render(v, stats=False, pipeline=True)[0] for v in views]   # pipelined, fire and forget
+        br.finish()
+        torch.cuda.synchronize(device)
+        if rank == 0:
+            # two buffer sets: views 1 and 2 are still intact, view 0's set was reused by view 2
+            results[f"{mode}_pipe1"] = imgs[1].cpu().numpy().copy()
+            results[f"{mode}_pipe2"] = imgs[2].cpu().numpy().copy()
+        dist.barrier()
+        br.close()
+    shared = SharedHostImage(ctx, 480, 360, rank=rank, world=world)
+    bands = api.balanced_bands(np.ones(360), world)
+    for k, v in enumerate(views[:2]):
+        if rank == 0:
+            shared.array[:] = -1.0
+        shared.barrier()
+        shared.render_band(v, bands[rank])
+        shared.barrier()
+        if rank == 0:
+            results[f"shared{k}"] = shared.array.copy()
+    shared.close()
+    if rank == 0:
+        np.savez(out_path, **results)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpus_one_image(gpu_lib, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    out = str(tmp_path / "bands.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = np.load(out)
+    for k in range(3):
+        assert np.array_equal(r[f"p2p{k}"], r[f"full{k}"], equal_nan=True)
+        assert np.array_equal(r[f"sendrecv{k}"], r[f"full{k}"], equal_nan=True)
+    for mode in ("p2p", "sendrecv"):
+        assert np.array_equal(r[f"{mode}_pipe1"], r["full1"], equal_nan=True)
+        assert np.array_equal(r[f"{mode}_pipe2"], r["full2"], equal_nan=True)
+        assert r[f"{mode}_bands0"][0][1] == 180                    # first view: equal heights
+    for k in range(2):
+        assert np.array_equal(r[f"shared{k}"], r[f"full{k}"], equal_nan=True)

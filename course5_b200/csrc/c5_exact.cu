@@ -193,16 +193,48 @@ C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g, int 
     mark_face(g, a, b, c, lane, n_lanes);
 }
 
+// The row range mark_face would visit, and nothing else (same expressions, so the same rows).
+C5_HD bool solid_face_in_band(int64_t f, const double* pts, const MaskGrid& g) {
+    const double* p = pts + 12 * (f >> 2);
+    const int k = static_cast<int>(f & 3);
+    const double ya = p[(k == 3 ? 3 : 0) + 1], yb = p[(k >= 2 ? 6 : 3) + 1], yc = p[(k == 0 ? 6 : 9) + 1];
+    double y_top = ya > yb ? ya : yb, y_bot = ya > yb ? yb : ya;
+    y_top = yc > y_top ? yc : y_top;
+    y_bot = yc < y_bot ? yc : y_bot;
+    long long j_hi = static_cast<long long>(floor(pixel_of_y(g, y_top)));
+    long long j_lo = static_cast<long long>(ceil(pixel_of_y(g, y_bot)));
+    if (j_lo < g.row_begin) j_lo = g.row_begin;
+    if (j_hi > g.row_end - 1) j_hi = g.row_end - 1;
+    return j_lo <= j_hi;
+}
+
 } // namespace
 
+// Phase 1: one face per thread — does any of its rows fall into the band? (Most faces of a row
+// band's view do not: this is all they cost.) Phase 2: the warp's surviving faces are dealt to
+// groups of 2^lane_shift lanes, which share a face's rows round-robin as before.
 __global__ void __launch_bounds__(256)
 solid_mask(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g,
            int lane_shift) {
-    // 2^lane_shift threads share one face (rows are dealt round-robin to them)
-    const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t k = tid >> lane_shift;
-    const int lanes = 1 << lane_shift;
-    if (k < n_faces) solid_face_body(faces[k], pts, g, static_cast<int>(tid & (lanes - 1)), lanes);
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    uint32_t f = 0;
+    bool live = false;
+    if (k < n_faces) {
+        f = faces[k];
+        live = solid_face_in_band(f, pts, g);
+    }
+    const unsigned m = __ballot_sync(full, live);
+    const int n_live = __popc(m);
+    const int group_lanes = 1 << lane_shift, groups = 32 >> lane_shift;
+    const int group = lane >> lane_shift, group_lane = lane & (group_lanes - 1);
+    for (int base = 0; base < n_live; base += groups) {
+        const int idx = base + group;
+        const int owner = idx < n_live ? static_cast<int>(__fns(m, 0, idx + 1)) : -1;
+        const uint32_t ff = __shfl_sync(full, f, owner < 0 ? 0 : owner);
+        if (owner >= 0) solid_face_body(ff, pts, g, group_lane, group_lanes);
+    }
 }
 
 namespace {
@@ -441,7 +473,7 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
         const double rows = ss->extent / step_y;
         int lane_shift = 0;
         while (lane_shift < 5 && (8 << lane_shift) < rows) lane_shift++;
-        solid_mask<<<grid_for(n_faces << lane_shift, 256), 256, 0, d.stream>>>(n_faces, ss->faces.p, ss->pts_view.p, g,
+        solid_mask<<<grid_for(n_faces, 256), 256, 0, d.stream>>>(n_faces, ss->faces.p, ss->pts_view.p, g,
                                                                                 lane_shift);
         C5_CUDA(cudaGetLastError());
     }

@@ -947,9 +947,12 @@ void walk_on_host(const WalkParams& P, bool f32) {
 
 } // namespace
 
-// C5_PREFETCH = strips of slab pulled into L2 ahead of the walk (default 1; 0 switches the prefetch off).
+// C5_PREFETCH = strips of slab pulled into L2 ahead of the walk. Off by default: measured on B200 it
+// changes nothing on the C3 README view (4.72 vs 4.75 ms, bands alike) and costs 7-9 % on oblique
+// views and on C5 (profiles/r01_exp_prefetch_*.jsonl) — the walk is bound by L1 wavefronts of its
+// scattered gathers, not by the DRAM latency of first touches.
 int walk_prefetch_lookahead() {
-    int a = 1;
+    int a = 0;
     if (const char* e = std::getenv("C5_PREFETCH")) a = std::atoi(e);
     if (a < 0) a = 0;
     if (a > 8) a = 8;

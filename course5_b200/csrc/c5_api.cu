@@ -124,6 +124,46 @@ void ensure_pixel_tables(DeviceState& d, const c5_view* v, const ViewPlan& p) {
     }
 }
 
+// Where on the screen the mesh can be: the view-frame box of the 8 corners of its file-frame box,
+// widened by a pixel. The walk's grid covers only that rectangle (the rest of the band is filled as
+// background); a conservative hint — inside it every tile is still tested against the BVH root.
+void mesh_pixel_rect(const DeviceState& d, const c5_view* v, const ViewPlan& p, WalkLaunch& w) {
+    double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
+    for (int corner = 0; corner < 8; corner++) {
+        double x = (corner & 1) ? d.mesh_hi[0] : d.mesh_lo[0];
+        double y = (corner & 2) ? d.mesh_hi[1] : d.mesh_lo[1];
+        double z = (corner & 4) ? d.mesh_hi[2] : d.mesh_lo[2];
+        for (int k = 0; k < p.n_rot; k++) { // tetra.cpp:44-62
+            const double c = p.rot[k].c, s = p.rot[k].s;
+            if (p.rot[k].axis == 0) {
+                const double y0 = y;
+                y = y * c - z * s;
+                z = y0 * s + z * c;
+            } else {
+                x -= p.rot[k].x0;
+                const double x1 = x;
+                x = x * c - z * s;
+                z = x1 * s + z * c;
+                x += p.rot[k].x0;
+            }
+        }
+        lo[0] = std::min(lo[0], x);
+        hi[0] = std::max(hi[0], x);
+        lo[1] = std::min(lo[1], y);
+        hi[1] = std::max(hi[1], y);
+    }
+    auto pixel = [](double c, double c_min, double step, int res, bool up) {
+        double r = (c - c_min) / step + (up ? 2.0 : -2.0); // one pixel for rounding, one for the repeated-addition tables
+        if (!(r > -1.0)) r = -1.0;
+        if (!(r < res + 1.0)) r = res + 1.0;
+        return static_cast<int>(up ? std::ceil(r) : std::floor(r));
+    };
+    w.i_begin = pixel(lo[0], p.x_min, p.step_x, v->res_x, false);
+    w.i_end = pixel(hi[0], p.x_min, p.step_x, v->res_x, true) + 1;
+    w.j_begin = pixel(lo[1], p.y_min, p.step_y, v->res_y, false);
+    w.j_end = pixel(hi[1], p.y_min, p.step_y, v->res_y, true) + 1;
+}
+
 // Enqueues one view's kernels for rows [row_begin,row_end) on device d. Events:
 // 0 start, 1 rotated, 2 bvh, 3 mask, 4 walk.
 void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want_steps, double* out_override = nullptr) {
@@ -135,7 +175,11 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     if (!out_override) d.out.ensure(2 * n_pix_band);
     if (want_steps) d.steps.ensure(n_pix_band);
     d.counters.ensure(kNumCounters);
-    d.queue.ensure(n_pix_band);
+    if (n_pix_band > d.queue.n) { // tags of a fresh allocation are garbage: start from zeros
+        d.queue.alloc(n_pix_band);
+        dev_zero(d.queue.p, d.queue.bytes(), d.stream);
+        d.queue_generation = 0;
+    }
     d.row_cost.ensure(static_cast<size_t>(v->res_y));
     if (solids) d.mask.ensure(static_cast<size_t>(v->res_x) * v->res_y);
 
@@ -152,20 +196,6 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
         launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y, p.row_begin, p.row_end);
     }
     record(d, 3);
-    if (const int ahead = walk_prefetch_lookahead()) {
-        // which 4 KB chunks of the cell / vertex arrays lie under which strip of rows of this band;
-        // the first strips' slab starts streaming into L2 now, behind the mask kernel
-        SlabPlan sp{};
-        sp.x_lo = v->window[1];
-        sp.x_hi = v->window[0];
-        sp.y_min = p.y_min;
-        sp.step_y = p.step_y;
-        sp.row_begin = p.row_begin;
-        sp.row_end = p.row_end;
-        sp.strip_rows = kStripRows;
-        sp.first_strips = ahead;
-        launch_classify_chunks(d, p.rot, p.n_rot, sp);
-    }
     dev_zero(d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);
     dev_zero(d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(unsigned long long), d.stream);
     WalkLaunch w{};
@@ -179,6 +209,7 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     w.write_steps = want_steps ? 1 : 0;
     w.precision = v->precision ? v->precision : 64;
     w.out = out_override ? out_override : d.out.p;
+    mesh_pixel_rect(d, v, p, w);
     launch_walk(d, w);
     record(d, 4);
 }
@@ -545,6 +576,11 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
                 C5_CUDA(cudaSetDevice(d->device));
                 C5_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
                 for (auto& e : d->ev) C5_CUDA(cudaEventCreate(&e));
+                int prio_lo = 0, prio_hi = 0;
+                C5_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                C5_CUDA(cudaStreamCreateWithPriority(&d->graze_stream, cudaStreamNonBlocking, prio_lo));
+                C5_CUDA(cudaEventCreateWithFlags(&d->graze_fork, cudaEventDisableTiming));
+                C5_CUDA(cudaEventCreateWithFlags(&d->graze_join, cudaEventDisableTiming));
             }
             ctx->dev.push_back(std::move(d));
         }
@@ -589,6 +625,16 @@ void c5_destroy(c5_ctx* ctx) {
         if (!kHostSim) {
             cudaSetDevice(d.device);
             cudaStreamSynchronize(d.stream);
+        }
+        if (!kHostSim) {
+            if (d.graze_stream) cudaStreamSynchronize(d.graze_stream);
+            if (d.graze_fork) cudaEventDestroy(d.graze_fork);
+            if (d.graze_join) cudaEventDestroy(d.graze_join);
+            if (d.graze_stream) cudaStreamDestroy(d.graze_stream);
+            for (auto& e : d.ev) {
+                if (e) cudaEventDestroy(e);
+            }
+            if (d.stream) cudaStreamDestroy(d.stream);
         }
         // DevBuf destructors free on the current device
         dp.reset();

@@ -16,7 +16,9 @@ constexpr int kMaxRot = C5_MAX_ROT;
 // Counters the walk kernel accumulates (one 64-bit atomic per warp).
 // kDeferred = rays the pixel kernel handed to the grazing-ray kernel, kTicket = how many of those
 // the grazing-ray kernel's warps have drawn.
-enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kDeferred = 4, kTicket = 5, kNumCounters = 6 };
+// kBlocksDone = blocks of the pixel kernel that have finished (the grazing-ray kernel's exit condition).
+enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kDeferred = 4, kTicket = 5, kBlocksDone = 6,
+               kNumCounters = 8 };
 
 struct SolidSet {
     DevBuf<double> pts0;      // [n][4][3] pre-view frame
@@ -34,6 +36,7 @@ struct DeviceState {
 
     // mesh (uploaded once)
     int64_t n_pts = 0, n_tets = 0, n_bfaces = 0;
+    double mesh_lo[3] = {0, 0, 0}, mesh_hi[3] = {0, 0, 0}; // bounding box in the file frame
     DevBuf<double> px, py, pz;       // Morton-ordered file-frame coordinates (SoA: the rotate kernel streams them)
     DevBuf<Cell> cells;
     DevBuf<double> q0;               // Q per tet (Morton order); cells[t].s is derived from it
@@ -44,11 +47,6 @@ struct DeviceState {
     DevBuf<int32_t> node_parent;     // per internal node: (parent << 1) | which child, -1 for the root
     DevBuf<int32_t> leaf_parent;     // per leaf: (parent << 1) | which child
     DevBuf<uint32_t> refit_flags;    // per internal node arrival counter
-
-    // L2 slab prefetch: per-chunk bounding spheres (per mesh) and strip ranges (per view)
-    int64_t n_cell_chunks = 0, n_vtx_chunks = 0;
-    DevBuf<ChunkSphere> chunk_spheres;   // cell chunks, then vertex chunks
-    DevBuf<uint32_t> chunk_rows;         // first strip | last strip << 16, kChunkOutside if none
 
     // solids
     SolidSet solid_follow, solid_static;
@@ -64,6 +62,9 @@ struct DeviceState {
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned long long> row_cost;
     DevBuf<DeferredRay> queue;       // grazing rays of the current view (capacity: pixels of the band)
+    uint32_t queue_generation = 0;   // tag of the last view's records (0: the queue is all zeros)
+    cudaStream_t graze_stream = nullptr; // the grazing-ray kernel runs beside the pixel kernel
+    cudaEvent_t graze_fork = nullptr, graze_join = nullptr;
     int sm_count = 0;
 
     uint64_t launches = 0;
@@ -100,21 +101,10 @@ void launch_bvh_refit(DeviceState& d);
 void dedupe_solid_faces(DeviceState& d, SolidSet& ss); // fills ss.faces / ss.n_faces from ss.pts0
 void launch_prepare_cells(DeviceState& d, double alpha_limit); // cells[t].s = q0[t] / min(alpha, limit)
 
-// c5_prefetch.cu
-struct SlabPlan {
-    double x_lo, x_hi, y_min, step_y;
-    int row_begin, row_end;
-    int strip_rows;   // pixel rows per strip (one row of macro tiles of the walk kernel)
-    int first_strips; // strips whose slab is prefetched before the walk starts
-};
-void build_chunk_spheres(DeviceState& d);
-void launch_classify_chunks(DeviceState& d, const Rot* rot, int n_rot, const SlabPlan& plan);
-
 // c5_walk.cu
-constexpr int kStripRows = 64; // 8 tile rows of 8 pixels: one row of macro tiles
-int walk_prefetch_lookahead(); // strips prefetched ahead of the one being started (0 = off)
 struct WalkLaunch {
     int res_x, res_y, row_begin, row_end;
+    int i_begin, i_end, j_begin, j_end; // pixel rectangle that can see the mesh (clipped to the band by the launch)
     double alpha_limit;
     int round_through_float;
     int use_mask;

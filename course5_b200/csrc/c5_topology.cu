@@ -301,6 +301,14 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
     if (n_tets >= (int64_t{1} << 29)) fail(C5_E_INVALID, "upload_mesh: more than 2^29 tets");
     cudaStream_t s = d.stream;
     const Box3 box = bounding_box(pts, n_pts);
+    for (int a = 0; a < 3; a++) d.mesh_lo[a] = d.mesh_hi[a] = pts[a];
+    for (int64_t i = 1; i < n_pts; i++) {
+        for (int a = 0; a < 3; a++) {
+            const double v = pts[3 * i + a];
+            if (v < d.mesh_lo[a]) d.mesh_lo[a] = v;
+            if (v > d.mesh_hi[a]) d.mesh_hi[a] = v;
+        }
+    }
 
     DevBuf<int> err;
     err.alloc(1);
@@ -474,7 +482,6 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
     d.n_tets = n_tets;
     d.n_bfaces = static_cast<int64_t>(n_b);
     d.cells_limit_valid = false;
-    build_chunk_spheres(d);
 }
 
 } // namespace c5

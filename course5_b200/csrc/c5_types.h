@@ -59,43 +59,19 @@ static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
 // A ray the pixel kernel could not finish cheaply (its re-entry list came back full: it grazes a
 // bumpy boundary and has many short crossings). The grazing-ray kernel continues it from here.
+// The queue is filled while the grazing-ray kernel is already draining it (the two run side by
+// side), so a slot carries a tag: the view's generation number in the top bits of the word that
+// holds the step count, written LAST. A consumer that holds ticket t polls slot t until the tag is
+// this view's.
+constexpr int kTagShift = 21;                       // steps < 2^21 (the step cap is 2^20)
+constexpr uint32_t kTagGenerations = (1u << (32 - kTagShift)) - 1; // generations 1 .. 2047, then the queue is cleared
 struct alignas(32) DeferredRay {
     double tau, inten; // accumulated so far
     double z_after;    // the ray has left the mesh at this depth
     uint32_t pixel;    // j * res_x + i
-    uint32_t steps;
+    uint32_t tag;      // generation << kTagShift | steps
 };
 static_assert(sizeof(DeferredRay) == 32, "DeferredRay must be 32 bytes");
-
-// L2 slab prefetch (c5_prefetch.cu): the cell and vertex arrays are cut into 4 KB chunks; each has a
-// bounding sphere in the file frame (the radius survives any view rotation).
-constexpr int kCellChunk = 64;  // cells per chunk: 64 x 64 B
-constexpr int kVtxChunk = 128;  // rotated vertices per chunk: 128 x 32 B
-constexpr uint32_t kChunkOutside = 0x0000FFFFu; // first strip 0xFFFF > last strip 0: touches no strip
-struct alignas(16) ChunkSphere {
-    float x, y, z, r;
-};
-
-#ifdef __CUDACC__
-// One bulk prefetch of chunk c's bytes into L2 (device only).
-__device__ __forceinline__ void prefetch_chunk(const Cell* cells, const Vtx* vrot, int64_t n_cell_chunks, int64_t n_tets,
-                                               int64_t n_pts, int64_t c) {
-    const char* p;
-    unsigned bytes;
-    if (c < n_cell_chunks) {
-        const int64_t t0 = c * kCellChunk;
-        const int64_t n = n_tets - t0 < kCellChunk ? n_tets - t0 : kCellChunk;
-        p = reinterpret_cast<const char*>(cells + t0);
-        bytes = static_cast<unsigned>(n * sizeof(Cell));
-    } else {
-        const int64_t i0 = (c - n_cell_chunks) * kVtxChunk;
-        const int64_t n = n_pts - i0 < kVtxChunk ? n_pts - i0 : kVtxChunk;
-        p = reinterpret_cast<const char*>(vrot + i0);
-        bytes = static_cast<unsigned>(n * sizeof(Vtx));
-    }
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-#endif
 
 struct Rot {       // one rotation with the trig evaluated on the host by libm (so it is the same
     int32_t axis;  // cos/sin the reference's host code multiplies by, tetra.cpp:44-62)

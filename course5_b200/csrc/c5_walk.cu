@@ -50,11 +50,11 @@ struct WalkParams {
     unsigned long long* counters;
     unsigned long long* row_cost; // [res_y]
     DeferredRay* queue;   // rays handed to the grazing-ray kernel; counters[kDeferred] of them
-    // L2 slab prefetch (c5_prefetch.cu): the first block of strip R pulls the slab of strip R + lookahead
-    const uint32_t* chunk_rows;
-    int64_t n_chunks, n_cell_chunks, n_tets, n_pts;
-    int lookahead, blocks_per_strip, n_strips;
+    unsigned long long queue_capacity;
+    uint32_t generation;  // tag of this view's queue records
+    uint32_t n_pixel_blocks; // grid of the pixel kernel: counters[kBlocksDone] reaches it when the queue is final
     int res_x, res_y, row_begin, row_end;
+    int i0, i1, j0, j1;   // pixel rectangle [i0,i1) x [j0,j1) of the band that can see the mesh: the tiles cover it
     int n_tiles_x, n_tiles_y, n_macro_x;
     int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
     int graze_cap;        // entries one cooperative collection may hold (<= kGrazeList)
@@ -524,13 +524,17 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
 #else
             const unsigned long long slot = P.counters[kDeferred]++;
 #endif
-            DeferredRay q;
+            DeferredRay& q = P.queue[slot];
             q.tau = r.tau;
             q.inten = r.inten;
             q.z_after = z_after;
             q.pixel = pixel;
-            q.steps = r.steps;
-            P.queue[slot] = q;
+#ifdef __CUDA_ARCH__
+            __threadfence(); // the record before its tag: a grazing warp may already be polling this slot
+            *reinterpret_cast<volatile uint32_t*>(&q.tag) = (P.generation << kTagShift) | r.steps;
+#else
+            q.tag = (P.generation << kTagShift) | r.steps;
+#endif
             r.deferred = 1;
             break;
         }
@@ -579,7 +583,7 @@ C5_HD RayAcc graze_ray_serial(const WalkParams& P, const DeferredRay& q, double 
     a.tau = q.tau;
     a.inten = q.inten;
     a.z_after = q.z_after;
-    a.steps = q.steps;
+    a.steps = q.tag & ((1u << kTagShift) - 1u);
     a.error = 0;
     EntryList<kSerialList> L;
     int crossings = 0;
@@ -599,6 +603,16 @@ C5_HD RayAcc graze_ray_serial(const WalkParams& P, const DeferredRay& q, double 
     return a;
 }
 
+C5_HD double __longlong_as_double_hd(long long bits) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(bits);
+#else
+    double v;
+    memcpy(&v, &bits, sizeof(v));
+    return v;
+#endif
+}
+
 C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double inten, uint32_t steps) {
     const size_t o = static_cast<size_t>(j - P.row_begin) * P.res_x + i;
     if (P.round_float) { // plane.cpp:165-166 then object2d.cpp:19-20
@@ -614,8 +628,16 @@ C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double int
     if (P.steps) P.steps[o] = steps;
 }
 
+// Pixels of the band outside the rectangle the walk covers: background (or solid).
+C5_HD bool background_pixel(const WalkParams& P, int i, int j) {
+    const bool solid = P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i];
+    const double v = solid ? __longlong_as_double_hd(0x7FF8000000000000ll) : 0.0; // quiet NaN (config.hpp:26-27)
+    store_pixel(P, i, j, v, v, 0);
+    return solid;
+}
+
 // ---- warp-cooperative form ---------------------------------------------------------------------------
-constexpr int kGrazeWarps = 4;    // warps (= rays in flight) per block
+constexpr int kGrazeWarps = 2;    // warps (= rays in flight) per block: small blocks fit into the gaps the pixel kernel leaves
 constexpr int kGrazeList = 256;   // entries per collection; more are fetched by another round
 constexpr int kGrazeStack = 512;  // shared traversal stack per warp ...
 constexpr int kGrazeSlack = 128;  // ... plus room for one wide round and a depth-first tail
@@ -732,22 +754,44 @@ __device__ __forceinline__ void graze_block(const WalkParams& P) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     GrazeSmem& S = smem[threadIdx.x >> 5];
-    // the pixel kernel has finished (stream order): the queue length is final
-    const unsigned long long n_rays = *reinterpret_cast<const volatile unsigned long long*>(&P.counters[kDeferred]);
+    // This kernel runs BESIDE the pixel kernel (its own low-priority stream), so that grazing rays
+    // are finished in the gaps and the tail of that kernel instead of after it. A warp draws ticket
+    // t and waits until slot t carries this view's tag — or until every block of the pixel kernel
+    // has finished without filling it.
+    const volatile unsigned long long* blocks_done = &P.counters[kBlocksDone];
     while (true) {
+        uint32_t tag = 0;
         unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&P.counters[kTicket], 1ull);
+        if (lane == 0) {
+            ticket = atomicAdd(&P.counters[kTicket], 1ull);
+            if (ticket < P.queue_capacity) {
+                const volatile uint32_t* slot_tag = &P.queue[ticket].tag;
+                while (true) {
+                    tag = *slot_tag;
+                    if ((tag >> kTagShift) == P.generation) break;
+                    if (*blocks_done >= P.n_pixel_blocks) { // every push is complete: look once more
+                        tag = *slot_tag;
+                        break;
+                    }
+                    __nanosleep(1000);
+                }
+            }
+            if ((tag >> kTagShift) == P.generation) __threadfence(); else tag = 0;
+        }
+        tag = __shfl_sync(full, tag, 0);
         ticket = __shfl_sync(full, ticket, 0);
-        if (ticket >= n_rays) break;
-        const DeferredRay q = P.queue[ticket];
-        const int i = static_cast<int>(q.pixel % static_cast<uint32_t>(P.res_x));
-        const int j = static_cast<int>(q.pixel / static_cast<uint32_t>(P.res_x));
+        if (tag == 0) break;
+        const DeferredRay* qp = P.queue + ticket;
+        const uint32_t q_steps = tag & ((1u << kTagShift) - 1u);
+        const uint32_t q_pixel = __ldcg(&qp->pixel);
+        const int i = static_cast<int>(q_pixel % static_cast<uint32_t>(P.res_x));
+        const int j = static_cast<int>(q_pixel / static_cast<uint32_t>(P.res_x));
         const double px = P.xs[i], py = P.ys[j];
         RayAcc a;
-        a.tau = q.tau;
-        a.inten = q.inten;
-        a.z_after = q.z_after;
-        a.steps = q.steps;
+        a.tau = __ldcg(&qp->tau);
+        a.inten = __ldcg(&qp->inten);
+        a.z_after = __ldcg(&qp->z_after);
+        a.steps = q_steps;
         a.error = 0;
         int crossings = 0;
         bool truncated = true;
@@ -777,7 +821,7 @@ __device__ __forceinline__ void graze_block(const WalkParams& P) {
         }
         if (lane == 0) {
             store_pixel(P, i, j, a.tau, a.inten, a.steps);
-            const unsigned long long more = a.steps - q.steps;
+            const unsigned long long more = a.steps - q_steps;
             if (more) {
                 atomicAdd(&P.counters[kSteps], more);
                 atomicAdd(&P.row_cost[j], more);
@@ -795,7 +839,7 @@ __device__ __forceinline__ int compact3(int v) {
 }
 
 template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2>
-__device__ __forceinline__ void walk_block(const WalkParams& P) {
+__device__ __forceinline__ void walk_block_body(const WalkParams& P) {
     constexpr int kTx = 8 * kWarpsX, kTy = 4 * kWarpsY, kThreads = 32 * kWarpsX * kWarpsY;
     extern __shared__ __align__(64) unsigned char smem_raw[];
     BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
@@ -806,23 +850,11 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
     const int macro = b >> 6, r = b & 63;
     const int tile_x = (macro % P.n_macro_x) * 8 + compact3(r);
     const int tile_y = (macro / P.n_macro_x) * 8 + compact3(r >> 1);
-    if (P.lookahead > 0 && b % P.blocks_per_strip == 0) {
-        // strip leader (usually an empty tile left of the mesh): chunks whose first strip is
-        // `target` go to L2 now, in bulk, while the strips before it are being walked
-        const int target = b / P.blocks_per_strip + P.lookahead;
-        if (target < P.n_strips) {
-            for (int64_t c = threadIdx.x; c < P.n_chunks; c += kThreads) {
-                if (static_cast<int>(__ldg(P.chunk_rows + c) & 0xFFFFu) == target) {
-                    prefetch_chunk(P.cells, P.vrot, P.n_cell_chunks, P.n_tets, P.n_pts, c);
-                }
-            }
-        }
-    }
     if (tile_x >= P.n_tiles_x || tile_y >= P.n_tiles_y) return;
 
     // Tiles that cannot see the mesh (outside the root's two boxes) skip the staging and the rays.
-    const int i_lo = tile_x * kTx, j_lo = P.row_begin + tile_y * kTy;
-    const int i_hi = min(i_lo + kTx, P.res_x) - 1, j_hi = min(j_lo + kTy, P.row_end) - 1;
+    const int i_lo = P.i0 + tile_x * kTx, j_lo = P.j0 + tile_y * kTy;
+    const int i_hi = min(i_lo + kTx, P.i1) - 1, j_hi = min(j_lo + kTy, P.j1) - 1;
     bool tile_sees_mesh;
     {
         const BvhNode* root = P.nodes;
@@ -840,9 +872,9 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = tile_x * kTx + (warp % kWarpsX) * 8 + (lane & 7);
-    const int j = P.row_begin + tile_y * kTy + (warp / kWarpsX) * 4 + (lane >> 3);
-    const bool live = i < P.res_x && j < P.row_end;
+    const int i = P.i0 + tile_x * kTx + (warp % kWarpsX) * 8 + (lane & 7);
+    const int j = P.j0 + tile_y * kTy + (warp / kWarpsX) * 4 + (lane >> 3);
+    const bool live = i < P.i1 && j < P.j1;
 
     RayResult res;
     res.tau = 0.0;
@@ -886,6 +918,17 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
     }
 }
 
+template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2>
+__device__ __forceinline__ void walk_block(const WalkParams& P) {
+    walk_block_body<kF32, kWide, kPipe, kWarpsX, kWarpsY>(P);
+    // tells the grazing-ray kernel (running beside this one) when no more rays can be deferred
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&P.counters[kBlocksDone], 1ull);
+    }
+}
+
 } // namespace
 
 // The product kernel, and register-capped variants kept for occupancy experiments
@@ -904,6 +947,22 @@ __global__ void __launch_bounds__(kBlock, 6) tet_walk_fp64_r80(const WalkParams 
 __global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, 0>(P); }
 
+// The walk's grid only covers the pixel rectangle that can see the mesh (a one-wave row band whose
+// grid is 60 % empty tiles fills the SMs unevenly: measured 1.60 M busy cycles on the fullest SM
+// against 1.07 M on average, profiles/r01_walk_band_c3.csv). Everything else in the band is background
+// or solid and is written by this streaming kernel.
+__global__ void __launch_bounds__(256) fill_background(const WalkParams P) {
+    const int n_rows = P.row_end - P.row_begin;
+    const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    bool solid = false;
+    if (k < static_cast<int64_t>(n_rows) * P.res_x) {
+        const int j = P.row_begin + static_cast<int>(k / P.res_x), i = static_cast<int>(k % P.res_x);
+        if (!(i >= P.i0 && i < P.i1 && j >= P.j0 && j < P.j1)) solid = background_pixel(P, i, j);
+    }
+    const unsigned solids = __popc(__ballot_sync(0xFFFFFFFFu, solid));
+    if ((threadIdx.x & 31) == 0 && solids) atomicAdd(&P.counters[kSolidPixels], static_cast<unsigned long long>(solids));
+}
+
 // Grazing rays (deferred by the pixel kernel): persistent warps, one ray per warp at a time.
 __global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp64(const WalkParams P) { graze_block<false>(P); }
 __global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp32(const WalkParams P) { graze_block<true>(P); }
@@ -918,16 +977,26 @@ void graze_on_host(const WalkParams& P, bool f32) {
         const int j = static_cast<int>(q.pixel / static_cast<uint32_t>(P.res_x));
         const RayAcc a = f32 ? graze_ray_serial<true>(P, q, P.xs[i], P.ys[j]) : graze_ray_serial<false>(P, q, P.xs[i], P.ys[j]);
         store_pixel(P, i, j, a.tau, a.inten, a.steps);
-        P.counters[kSteps] += a.steps - q.steps;
-        P.row_cost[j] += a.steps - q.steps;
+        const uint32_t q_steps = q.tag & ((1u << kTagShift) - 1u);
+        P.counters[kSteps] += a.steps - q_steps;
+        P.row_cost[j] += a.steps - q_steps;
         if (a.error) P.counters[kWalkErrors]++;
     }
     P.counters[kTicket] = n_rays;
 }
 
-void walk_on_host(const WalkParams& P, bool f32) {
+void background_on_host(const WalkParams& P) {
     for (int j = P.row_begin; j < P.row_end; j++) {
         for (int i = 0; i < P.res_x; i++) {
+            if (i >= P.i0 && i < P.i1 && j >= P.j0 && j < P.j1) continue;
+            if (background_pixel(P, i, j)) P.counters[kSolidPixels]++;
+        }
+    }
+}
+
+void walk_on_host(const WalkParams& P, bool f32) {
+    for (int j = P.j0; j < P.j1; j++) {
+        for (int i = P.i0; i < P.i1; i++) {
             if (P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i]) {
                 store_pixel(P, i, j, NAN, NAN, 0);
                 P.counters[kSolidPixels]++;
@@ -947,20 +1016,6 @@ void walk_on_host(const WalkParams& P, bool f32) {
 
 } // namespace
 
-// C5_PREFETCH = strips of slab pulled into L2 ahead of the walk. Off by default: measured on B200 it
-// changes nothing on the C3 README view (4.72 vs 4.75 ms, bands alike) and costs 7-9 % on oblique
-// views and on C5 (profiles/r01_exp_prefetch_*.jsonl) — the walk is bound by L1 wavefronts of its
-// scattered gathers, not by the DRAM latency of first touches.
-int walk_prefetch_lookahead() {
-    int a = 0;
-    if (const char* e = std::getenv("C5_PREFETCH")) a = std::atoi(e);
-    if (a < 0) a = 0;
-    if (a > 8) a = 8;
-    const char* variant = std::getenv("C5_WALK_VARIANT");
-    if (variant && std::string(variant) == "b64") a = 0; // its tiles are 8 x 8: strips would not line up
-    return a;
-}
-
 void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (w.precision != 64 && w.precision != 32) fail(C5_E_INVALID, "render: precision must be 64 or 32");
     const bool f32 = w.precision == 32;
@@ -977,6 +1032,13 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.counters = d.counters.p;
     P.row_cost = d.row_cost.p;
     P.queue = d.queue.p;
+    P.queue_capacity = d.queue.n;
+    // a fresh tag per view; when the tags run out the queue is wiped (once every 2047 views)
+    if (d.queue_generation >= kTagGenerations) {
+        dev_zero(d.queue.p, d.queue.bytes(), d.stream);
+        d.queue_generation = 0;
+    }
+    P.generation = ++d.queue_generation;
     P.res_x = w.res_x;
     P.res_y = w.res_y;
     P.row_begin = w.row_begin;
@@ -985,8 +1047,16 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     const std::string var = variant ? variant : "";
     const bool small_blocks = !f32 && var == "b64"; // 8 x 8 pixel tiles, 64 threads
     const int tile_x = small_blocks ? 8 : kTileX, tile_y = small_blocks ? 8 : kTileY;
-    P.n_tiles_x = (w.res_x + tile_x - 1) / tile_x;
-    P.n_tiles_y = (w.row_end - w.row_begin + tile_y - 1) / tile_y;
+    // the walk covers [i0,i1) x [j0,j1): the caller's estimate of where the mesh can be, cut to the band
+    P.i0 = w.i_begin < 0 ? 0 : w.i_begin;
+    P.i1 = w.i_end > w.res_x ? w.res_x : w.i_end;
+    P.j0 = w.j_begin < w.row_begin ? w.row_begin : w.j_begin;
+    P.j1 = w.j_end > w.row_end ? w.row_end : w.j_end;
+    const bool empty_rect = P.i0 >= P.i1 || P.j0 >= P.j1;
+    if (empty_rect) P.i0 = P.i1 = P.j0 = P.j1 = 0;
+    const bool whole_band = P.i0 == 0 && P.i1 == w.res_x && P.j0 == w.row_begin && P.j1 == w.row_end;
+    P.n_tiles_x = (P.i1 - P.i0 + tile_x - 1) / tile_x;
+    P.n_tiles_y = (P.j1 - P.j0 + tile_y - 1) / tile_y;
     P.n_macro_x = (P.n_tiles_x + 7) / 8;
     const int n_macro_y = (P.n_tiles_y + 7) / 8;
     const int64_t n_nodes = d.n_bfaces - 1;
@@ -998,15 +1068,6 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (top < 0) top = 0;
     if (top > 1023) top = 1023;
     P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < top ? n_nodes : top);
-    P.chunk_rows = d.chunk_rows.p;
-    P.n_chunks = d.n_cell_chunks + d.n_vtx_chunks;
-    P.n_cell_chunks = d.n_cell_chunks;
-    P.n_tets = d.n_tets;
-    P.n_pts = d.n_pts;
-    P.lookahead = kHostSim ? 0 : walk_prefetch_lookahead();
-    P.blocks_per_strip = P.n_macro_x * 64;
-    P.n_strips = n_macro_y;
-    static_assert(kStripRows == 8 * kTileY, "a strip is one row of macro tiles");
     P.graze_cap = kGrazeList;
     if (const char* e = std::getenv("C5_GRAZE_LIST")) { // tests shrink it to reach the overflow path on small meshes
         const int c = std::atoi(e);
@@ -1021,6 +1082,17 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.round_float = w.round_through_float;
     P.alpha_limit = w.alpha_limit;
 
+    if (!whole_band) {
+        count_launch();
+        if (kHostSim) {
+            background_on_host(P);
+        } else {
+            const int64_t n = static_cast<int64_t>(w.row_end - w.row_begin) * w.res_x;
+            fill_background<<<static_cast<unsigned>((n + 255) / 256), 256, 0, d.stream>>>(P);
+            C5_CUDA(cudaGetLastError());
+        }
+    }
+    if (empty_rect) return; // the mesh is not in this band: no rays
     count_launch();
     if (kHostSim) {
         walk_on_host(P, f32);
@@ -1029,6 +1101,9 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         return;
     }
     const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
+    P.n_pixel_blocks = grid;
+    // fork: the grazing-ray kernel may start as soon as the counters are zero, i.e. beside the pixel kernel
+    C5_CUDA(cudaEventRecord(d.graze_fork, d.stream));
     const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
     if (f32) {
         tet_walk_fp32<<<grid, kBlock, smem, d.stream>>>(P);
@@ -1056,12 +1131,16 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
     const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * 4u;
     count_launch();
+    C5_CUDA(cudaStreamWaitEvent(d.graze_stream, d.graze_fork, 0));
     if (f32) {
-        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
+        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, d.graze_stream>>>(P);
     } else {
-        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
+        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, d.graze_stream>>>(P);
     }
     C5_CUDA(cudaGetLastError());
+    // join: whatever follows on the caller's stream (the next view rewrites the vertices) waits for it
+    C5_CUDA(cudaEventRecord(d.graze_join, d.graze_stream));
+    C5_CUDA(cudaStreamWaitEvent(d.stream, d.graze_join, 0));
 }
 
 } // namespace c5

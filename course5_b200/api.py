@@ -90,7 +90,7 @@ SYMBOLS = {
     "c5_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "c5_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
-IPC_HANDLE_BYTES = 64
+IPC_HANDLE_BYTES = 80
 
 
 def load_library(path: str | None = None) -> C.CDLL:
@@ -239,7 +239,7 @@ class Context:
 
     # -- one image, several processes (include/c5gpu.h) ----------------------------------------
     def image_create(self, nbytes: int) -> tuple[int, bytes]:
-        """Device image other processes can map: returns (device pointer, 64-byte handle)."""
+        """Device image other processes can map: returns (device pointer, opaque handle bytes)."""
         ptr = C.c_void_p()
         handle = (C.c_uint8 * IPC_HANDLE_BYTES)()
         self._check(self.lib.c5_image_create(self._h, nbytes, C.byref(ptr), handle))

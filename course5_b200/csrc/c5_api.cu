@@ -522,6 +522,25 @@ void upload_solids(c5_ctx* ctx, const double* pts, int64_t n, int follows) {
     ctx->info.n_solid_tets += n;
 }
 
+// cudaMalloc may carve an allocation out of a larger block, and a CUDA IPC handle names the BLOCK:
+// the importer gets the block's base address. The driver knows the base (cuMemGetAddressRange);
+// the offset travels with the handle. libcuda is loaded lazily so that the library still loads on
+// machines without a driver (the CPU-only build container).
+uint64_t offset_in_allocation(void* p) {
+    using Fn = int (*)(unsigned long long*, size_t*, unsigned long long);
+    static Fn fn = [] {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+        return h ? reinterpret_cast<Fn>(dlsym(h, "cuMemGetAddressRange_v2")) : nullptr;
+    }();
+    if (!fn) fail(C5_E_CUDA, "image_create: cuMemGetAddressRange not available (libcuda.so.1)");
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int rc = fn(&base, &size, static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(p)));
+    if (rc != 0) fail(C5_E_CUDA, "image_create: cuMemGetAddressRange failed (" + std::to_string(rc) + ")");
+    return static_cast<uint64_t>(reinterpret_cast<uintptr_t>(p)) - base;
+}
+
 } // namespace
 
 extern "C" {
@@ -749,20 +768,25 @@ int c5_image_create(c5_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[C5
     return guarded(ctx, [&] {
         if (bytes == 0) fail(C5_E_INVALID, "image_create: zero bytes");
         use_device(*ctx->dev[0]);
-        void* p = dev_alloc(bytes); // a plain cudaMalloc: the handle then refers to p itself, offset 0
+        void* p = dev_alloc(bytes);
         std::memset(handle, 0, C5_IPC_HANDLE_BYTES);
+        uint64_t offset = 0;
         if (kHostSim) {
             std::memcpy(handle, &p, sizeof(p)); // same-process stand-in (CPU logic tests only)
         } else {
-            static_assert(sizeof(cudaIpcMemHandle_t) <= C5_IPC_HANDLE_BYTES, "IPC handle size");
+            static_assert(sizeof(cudaIpcMemHandle_t) + 16 <= C5_IPC_HANDLE_BYTES, "IPC handle size");
             cudaIpcMemHandle_t h;
-            cudaError_t e = cudaIpcGetMemHandle(&h, p);
-            if (e != cudaSuccess) {
+            try {
+                offset = offset_in_allocation(p);
+                C5_CUDA(cudaIpcGetMemHandle(&h, p));
+            } catch (...) {
                 dev_free(p);
-                fail(C5_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+                throw;
             }
             std::memcpy(handle, &h, sizeof(h));
         }
+        std::memcpy(handle + 64, &offset, sizeof(offset));
+        std::memcpy(handle + 72, &bytes, sizeof(bytes));
         ctx->images.emplace_back(p, true);
         *d_ptr = p;
     });
@@ -781,14 +805,23 @@ int c5_image_open(c5_ctx* ctx, const uint8_t handle[C5_IPC_HANDLE_BYTES], void**
             // maps the owner's allocation into this process and enables peer access to its device
             C5_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         }
-        ctx->images.emplace_back(p, false);
-        *d_ptr = p;
+        uint64_t offset = 0;
+        std::memcpy(&offset, handle + 64, sizeof(offset));
+        ctx->images.emplace_back(p, false); // the mapping's base: what cudaIpcCloseMemHandle wants back
+        ctx->image_offsets.emplace_back(static_cast<char*>(p) + offset, p);
+        *d_ptr = static_cast<char*>(p) + offset;
     });
 }
 
 int c5_image_close(c5_ctx* ctx, void* d_ptr) {
     if (!ctx || !d_ptr) return C5_E_INVALID;
     return guarded(ctx, [&] {
+        for (size_t k = 0; k < ctx->image_offsets.size(); k++) { // an imported image is known by its offset pointer
+            if (ctx->image_offsets[k].first != d_ptr) continue;
+            d_ptr = ctx->image_offsets[k].second;
+            ctx->image_offsets.erase(ctx->image_offsets.begin() + static_cast<long>(k));
+            break;
+        }
         for (size_t k = 0; k < ctx->images.size(); k++) {
             if (ctx->images[k].first != d_ptr) continue;
             const bool owner = ctx->images[k].second;

@@ -82,6 +82,7 @@ struct c5_ctx {
     std::vector<uint64_t> last_row_cost;
     void* nccl = nullptr; // NcclGroup*, multi-device contexts only
     std::vector<std::pair<void*, bool>> images;   // c5_image_create (true) / c5_image_open (false) pointers
+    std::vector<std::pair<void*, void*>> image_offsets; // imported images: (pointer handed out, mapping base)
     std::vector<void*> registered;                // c5_host_register pointers
 };
 

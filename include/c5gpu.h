@@ -163,7 +163,7 @@ int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows);
  *
  * Ordering between processes (all bands of view k written before anyone reads view k) is the
  * caller's: one barrier per view on the streams involved. */
-#define C5_IPC_HANDLE_BYTES 64
+#define C5_IPC_HANDLE_BYTES 80 /* a cudaIpcMemHandle_t (64) + the image's offset in its allocation + its size */
 int c5_image_create(c5_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[C5_IPC_HANDLE_BYTES]);
 int c5_image_open(c5_ctx* ctx, const uint8_t handle[C5_IPC_HANDLE_BYTES], void** d_ptr);
 int c5_image_close(c5_ctx* ctx, void* d_ptr); /* frees (owner) or unmaps (importer) */

@@ -53,6 +53,7 @@ struct WalkParams {
     unsigned long long queue_capacity;
     uint32_t generation;  // tag of this view's queue records
     uint32_t n_pixel_blocks; // grid of the pixel kernel: counters[kBlocksDone] reaches it when the queue is final
+    int fence_stores;     // debugging aid (C5_STORE_FENCE): a system-scope fence after every pixel store
     int res_x, res_y, row_begin, row_end;
     int i0, i1, j0, j1;   // pixel rectangle [i0,i1) x [j0,j1) of the band that can see the mesh: the tiles cover it
     int n_tiles_x, n_tiles_y, n_macro_x;
@@ -626,6 +627,9 @@ C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double int
     P.out[2 * o + 1] = inten;
 #endif
     if (P.steps) P.steps[o] = steps;
+#ifdef __CUDA_ARCH__
+    if (P.fence_stores) __threadfence_system();
+#endif
 }
 
 // Pixels of the band outside the rectangle the walk covers: background (or solid).
@@ -1073,6 +1077,7 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         const int c = std::atoi(e);
         if (c >= 128 && c <= kGrazeList) P.graze_cap = c & ~1;
     }
+    P.fence_stores = std::getenv("C5_STORE_FENCE") != nullptr;
     P.serial_cap = kSerialList;
     if (const char* e = std::getenv("C5_GRAZE_SERIAL_LIST")) {
         const int c = std::atoi(e);
@@ -1131,16 +1136,20 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
     const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * 4u;
     count_launch();
-    C5_CUDA(cudaStreamWaitEvent(d.graze_stream, d.graze_fork, 0));
+    const bool beside = std::getenv("C5_GRAZE_SERIAL") == nullptr; // C5_GRAZE_SERIAL: after the pixel kernel, same stream
+    cudaStream_t gs = beside ? d.graze_stream : d.stream;
+    if (beside) C5_CUDA(cudaStreamWaitEvent(gs, d.graze_fork, 0));
     if (f32) {
-        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, d.graze_stream>>>(P);
+        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, gs>>>(P);
     } else {
-        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, d.graze_stream>>>(P);
+        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, gs>>>(P);
     }
     C5_CUDA(cudaGetLastError());
-    // join: whatever follows on the caller's stream (the next view rewrites the vertices) waits for it
-    C5_CUDA(cudaEventRecord(d.graze_join, d.graze_stream));
-    C5_CUDA(cudaStreamWaitEvent(d.stream, d.graze_join, 0));
+    if (beside) {
+        // join: whatever follows on the caller's stream (the next view rewrites the vertices) waits for it
+        C5_CUDA(cudaEventRecord(d.graze_join, gs));
+        C5_CUDA(cudaStreamWaitEvent(d.stream, d.graze_join, 0));
+    }
 }
 
 } // namespace c5

@@ -28,7 +28,12 @@ a lower rate than one of long central rays), so ``rebalance="time"`` additionall
 band's row costs by the time that band actually took.
 
 Sweeps can pipeline: with ``pipeline=True`` the exchange (or barrier) of view k is left in flight
-while view k+1 renders into the other of two buffer sets.
+while the next views render into the other buffer sets. There are three sets, and a rank starts
+view k+3 (which reuses view k's set) only after barrier k+1 has completed. Rank 0 enqueues barrier
+k+1 inside ``render(k+1)``, so the contract for the consumer of rank 0's image is: whatever reads
+image k must be finished, or enqueued on the current stream, BEFORE ``render(k+1)`` is called;
+the peers cannot overwrite it earlier, and a fast rank may still run one whole view ahead of the
+slowest one.
 """
 from __future__ import annotations
 
@@ -39,6 +44,9 @@ import torch
 import torch.distributed as dist
 
 from . import api
+
+
+N_SETS = 3
 
 
 class BandRenderer:
@@ -54,10 +62,10 @@ class BandRenderer:
             raise ValueError("gather must be 'auto', 'p2p' or 'sendrecv'")
         self.gather_mode = gather
         self.row_cost: np.ndarray | None = None
-        self._band_buf = [None, None]      # two buffer sets: the exchange of one view may still be
-        self._image = [None, None]         # reading/writing set k while view k+1 fills the other
-        self._peer = [None, None]          # p2p: (device pointer of rank 0's image, bytes) per set
-        self._pending = [[], []]
+        self._band_buf = [None] * N_SETS   # buffer sets: the exchange of one view may still be reading /
+        self._image = [None] * N_SETS      # writing its set while the next views fill the others
+        self._peer = [None] * N_SETS       # p2p: (device pointer of rank 0's image, bytes) per set
+        self._pending = {}                 # view number -> requests of its exchange / barrier
         self._count = 0
         self._bands = None                 # cached cut, valid until the row costs change
         self._flag = None
@@ -89,7 +97,7 @@ class BandRenderer:
         nbytes = view.res_y * view.res_x * 16
         if self._peer[par] is not None and self._peer[par][1] == nbytes:
             return self._peer[par][0]
-        self._drain(par)
+        self.finish()
         if self._peer[par] is not None:
             dist.barrier()                 # nobody may still be writing the old mapping
             self.ctx.image_close(self._peer[par][0])
@@ -107,21 +115,21 @@ class BandRenderer:
             self._image[par] = _tensor_from_pointer(ptr, view.res_y * view.res_x * 2, self.device)
         return ptr
 
-    def _drain(self, par: int):
-        for req in self._pending[par]:
-            req.wait()          # orders the current stream after that exchange
-        self._pending[par] = []
+    def _drain(self, upto: int):
+        """Orders the current stream after the exchanges / barriers of all views numbered <= upto."""
+        for k in sorted(k for k in self._pending if k <= upto):
+            for req in self._pending.pop(k):
+                req.wait()
 
     def finish(self):
         """Waits (on the current stream) for every exchange still in flight."""
-        self._drain(0)
-        self._drain(1)
+        self._drain(self._count)
 
     def close(self):
         self.finish()
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
-        for par in (0, 1):
+        for par in range(N_SETS):
             if self._peer[par] is not None:
                 if self.world > 1:
                     dist.barrier()
@@ -142,9 +150,11 @@ class BandRenderer:
         "time" = additionally weight each band by the device time it took."""
         if not stats:
             rebalance = False
-        par = self._count & 1
+        k = self._count
         self._count += 1
-        self._drain(par)        # the buffers of this parity are about to be overwritten
+        par = k % N_SETS
+        # this view reuses the set of view k - 3: every rank must be past barrier k - 2 (module docstring)
+        self._drain(k - N_SETS + 1)
         bands = self.bands(view.res_y)
         lo, hi = bands[self.rank]
         v = api.View.from_buffer_copy(view)
@@ -158,9 +168,9 @@ class BandRenderer:
             # barrier: when it completes on a rank's stream, every rank's band of this view is in
             if self._flag is None:
                 self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._pending[par] = [dist.all_reduce(self._flag, async_op=True)]
+            self._pending[k] = [dist.all_reduce(self._flag, async_op=True)]
             if not pipeline:
-                self._drain(par)
+                self._drain(k)
         else:
             self._buffers(view, hi - lo, par)
             if self.rank == 0 and gather:
@@ -176,9 +186,9 @@ class BandRenderer:
                         ops.append(dist.P2POp(dist.irecv, self._image[par][rlo * view.res_x * 2: rhi * view.res_x * 2], r))
                 else:
                     ops.append(dist.P2POp(dist.isend, target, 0))
-                self._pending[par] = list(dist.batch_isend_irecv(ops))
+                self._pending[k] = list(dist.batch_isend_irecv(ops))
                 if not pipeline:
-                    self._drain(par)
+                    self._drain(k)
 
         if rebalance:
             cost = torch.from_numpy(self.ctx.last_row_cost(view.res_y).astype(np.float64))
@@ -193,8 +203,6 @@ class BandRenderer:
                 dist.all_reduce(cost, op=dist.ReduceOp.SUM)
                 cost = cost.cpu()
             self.row_cost = cost.numpy().astype(np.float64)
-            if rebalance == "time" and self.world > 1:
-                self._time_weighted = True
             self._bands = None
 
         image = None
@@ -222,8 +230,10 @@ class SharedHostImage:
     Rank 0 creates a POSIX shared-memory segment, the others attach; every rank pins it with its
     own context (``c5_host_register``), after which ``Context.render(view_with_row_band, out=image)``
     makes the walk kernel store the band straight into the shared image over that GPU's PCIe link.
-    ``barrier()`` then tells rank 0 that all bands of the view are in. In the CPU tests (hostsim
-    build) the same calls degrade to a plain memcpy into the shared segment."""
+    ``barrier()`` then tells rank 0 that all bands of the view are in. The image is single-buffered:
+    a consumer on rank 0 calls ``barrier()`` once more when it is done with the image, before any
+    rank renders the next view into it. In the CPU tests (hostsim build) the same calls degrade to
+    a plain memcpy into the shared segment."""
 
     def __init__(self, ctx: api.Context, res_x: int, res_y: int, *, rank: int, world: int):
         self.ctx, self.rank, self.world = ctx, rank, world

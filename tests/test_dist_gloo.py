@@ -45,7 +45,7 @@ def _worker(rank, world, port, out_path):
             results[f"full{k}"] = full
             results[f"bands{k}"] = np.array(bands)
             results[f"steps{k}"] = np.array([int(steps), st["tet_steps"]])
-    # pipelined mode: two views in flight on two buffer sets, gathers drained at the end
+    # pipelined mode: views in flight on separate buffer sets, gathers drained at the end
     va = api.make_view(120, 90, X=0.4, Y=0.2, lib=lib)
     vb = api.make_view(120, 90, X=0.4, Y=0.9, lib=lib)
     img_a, _, _ = br.render(va, stats=False, pipeline=True)

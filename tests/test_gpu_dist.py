@@ -53,7 +53,7 @@ def _worker(rank, world, port, out_path):
         br.finish()
         torch.cuda.synchronize(device)
         if rank == 0:
-            # two buffer sets: views 1 and 2 are still intact, view 0's set was reused by view 2
+            # three buffer sets: all three views are intact
             results[f"{mode}_pipe1"] = imgs[1].cpu().numpy().copy()
             results[f"{mode}_pipe2"] = imgs[2].cpu().numpy().copy()
         dist.barrier()

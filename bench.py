@@ -185,12 +185,13 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def config_dict(mesh, view, n_gpus, gather="p2p"):
+def config_dict(mesh, view, n_gpus, gather="p2p", lanes=1):
     return {
         "workload": (f"{WORKLOAD}: synthetic Kuhn-split grid, {mesh.n_tets} tets / {mesh.n_points} points, "
                      f"{view['res_x']}x{view['res_y']}, -X {view['X']} -Y {view['Y']} --alpha_limit "
                      f"{view['alpha_limit']}, reference Roche lobe + sphere as solids"),
         "res_x": view["res_x"], "res_y": view["res_y"], "n_tets": mesh.n_tets,
+        "views_in_flight": lanes,
         "parallelism": "single GPU" if n_gpus == 1 else
                        f"{n_gpus} row bands (time-balanced), mesh replicated, " +
                        ("bands stored into rank 0's image over NVLink peer mappings by the walk kernel, one barrier per view"
@@ -236,7 +237,7 @@ def run_ours(args):
     upload_s = time.perf_counter() - t0
     v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
                       alpha_limit=view["alpha_limit"])
-    br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather)
+    br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=args.lanes)
 
     def barrier():
         if world > 1:
@@ -252,35 +253,29 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = ctx.kernel_launches()
+    launches0 = br.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     walk_ms, steps_total, stats_last = [], 0, None
     ev0.record()
-    if world == 1:
-        for _ in range(args.steps):
-            _, st, bands = br.render(v, rebalance=False)
-            walk_ms.append(st["ms_walk"])
-            stats_last = st
-    else:
-        # N > 1: render + exchange are only enqueued (no host readback between views), so the ranks'
-        # launches pipeline on the devices; statistics come from a second pass. gather=p2p: the walk
-        # stores straight into rank 0's image over NVLink and the per-view barrier of view k overlaps
-        # the rendering of view k + 1 (two images); gather=sendrecv: the same with one grouped
-        # ncclSend/ncclRecv per view
-        for _ in range(args.steps):
-            _, _, bands = br.render(v, rebalance=False, stats=False, pipeline=True)
-        br.finish()
+    # The views are only enqueued (no host readback between them; statistics come from a second
+    # pass): consecutive views alternate between two lanes — the context and a sibling that shares
+    # its mesh, each on its own stream — so the tail of one view's walk overlaps the start of the
+    # next. N > 1, gather=p2p: the walk stores straight into rank 0's image over NVLink and the
+    # barrier of view k is left in flight (three images); gather=sendrecv: the same with one grouped
+    # ncclSend/ncclRecv per view.
+    for _ in range(args.steps):
+        _, _, bands = br.render(v, rebalance=False, stats=False, pipeline=True)
+    br.finish()
     ev1.record()
     barrier()
     clocks = sampler.stop()
-    launches = ctx.kernel_launches() - launches0
+    launches = br.kernel_launches() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        for _ in range(3):
-            _, st, bands = br.render(v, rebalance=False)
-            walk_ms.append(st["ms_walk"])
-            stats_last = st
-        barrier()
+    for _ in range(3):
+        _, st, bands = br.render(v, rebalance=False)
+        walk_ms.append(st["ms_walk"])
+        stats_last = st
+    barrier()
     band_steps = stats_last["tet_steps"]
 
     # ---- e2e: the public C-ABI call with a pinned HOST output buffer ---------------------------
@@ -338,7 +333,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "pixels_per_sec": pixels / (ms_per_step * 1e-3),
             "tet_steps_per_view": total_steps,
-            "config": config_dict(mesh, view, world, br.gather_mode),
+            "config": config_dict(mesh, view, world, br.gather_mode, br.n_lanes),
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(api.C.sizeof(api.View)), "d2h_bytes_per_step": pixels * 16,
                     "api": "c5_render (pinned host buffer)" if world == 1 else
@@ -374,6 +369,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2],
+                    help="views in flight per GPU (2 = alternate between the context and a sibling on two streams)")
     ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="auto",
                     help="N > 1: how bands reach rank 0's image (p2p = stored by the walk kernel over NVLink)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")

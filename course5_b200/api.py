@@ -73,6 +73,7 @@ SYMBOLS = {
     "c5_view_from_flags": (None, [C.POINTER(View), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                   C.c_double]),
     "c5_create": (C.c_int, [_i32p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "c5_create_sibling": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "c5_destroy": (None, [C.c_void_p]),
     "c5_last_error": (C.c_char_p, [C.c_void_p]),
     "c5_upload_mesh": (C.c_int, [C.c_void_p, _dp, C.c_int64, _i32p, C.c_int64, _dp, _dp]),
@@ -156,6 +157,16 @@ class Context:
             raise C5Error(rc, (self.lib.c5_last_error(None) or b"").decode())
         self._h = handle
         self.n_devices = len(devices)
+
+    def sibling(self) -> "Context":
+        """A context on the same device that shares this one's mesh and solids and owns only per-view
+        state: rendering alternate views through the two, on two streams, lets consecutive views
+        overlap on the device (c5_create_sibling). Close it before this context."""
+        handle = C.c_void_p()
+        self._check(self.lib.c5_create_sibling(self._h, C.byref(handle)))
+        sib = Context.__new__(Context)
+        sib.lib, sib._h, sib.n_devices, sib._parent = self.lib, handle, 1, self
+        return sib
 
     def _check(self, rc: int):
         if rc != OK:

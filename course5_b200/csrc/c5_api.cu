@@ -311,7 +311,10 @@ struct Counters {
 // plane ctor + find_intersections + trace_rays for one view into a HOST buffer, on all devices of
 // the context: device r renders band r; bands land in device 0's image by one grouped NCCL
 // send/recv; device 0 copies the image to the host.
+void follow_parent(c5_ctx* ctx);
+
 void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, c5_stats* st) {
+    follow_parent(ctx);
     if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
     if (!out) fail(C5_E_INVALID, "render: out is NULL");
     const ViewPlan p = plan_view(v);
@@ -522,6 +525,56 @@ void upload_solids(c5_ctx* ctx, const double* pts, int64_t n, int follows) {
     ctx->info.n_solid_tets += n;
 }
 
+// Points a sibling's device state at the mesh and solids its parent owns; per-view arrays are its own.
+void alias_mesh(DeviceState& s, DeviceState& o) {
+    use_device(s);
+    s.origin = &o;
+    o.mesh_shared = true;
+    s.n_pts = o.n_pts;
+    s.n_tets = o.n_tets;
+    s.n_bfaces = o.n_bfaces;
+    for (int a = 0; a < 3; a++) {
+        s.mesh_lo[a] = o.mesh_lo[a];
+        s.mesh_hi[a] = o.mesh_hi[a];
+    }
+    s.px.alias(o.px);
+    s.py.alias(o.py);
+    s.pz.alias(o.pz);
+    s.cells.alias(o.cells);
+    s.q0.alias(o.q0);
+    s.bfaces.alias(o.bfaces);
+    s.node_parent.alias(o.node_parent);
+    s.leaf_parent.alias(o.leaf_parent);
+    s.nodes.alloc(o.nodes.n); // child links are static, the boxes are refitted per view
+    if (o.nodes.n) d2d(s.nodes.p, o.nodes.p, o.nodes.bytes(), s.stream);
+    s.refit_flags.alloc(o.refit_flags.n);
+    s.vrot.alloc(static_cast<size_t>(o.n_pts));
+    const SolidSet* from[2] = {&o.solid_follow, &o.solid_static};
+    SolidSet* to[2] = {&s.solid_follow, &s.solid_static};
+    for (int k = 0; k < 2; k++) {
+        to[k]->n = from[k]->n;
+        to[k]->n_faces = from[k]->n_faces;
+        to[k]->extent = from[k]->extent;
+        to[k]->pts0.alias(from[k]->pts0);
+        to[k]->faces.alias(from[k]->faces);
+        if (k == 0) to[k]->pts_view.alloc(from[k]->pts_view.n); // rotated with the view
+        else to[k]->pts_view.alias(from[k]->pts_view);         // static solids are never rotated
+    }
+    stream_sync(s.stream);
+    s.mesh_version = o.mesh_version;
+}
+
+// A sibling follows its parent's uploads lazily, at its next render.
+void follow_parent(c5_ctx* ctx) {
+    if (!ctx->parent) return;
+    c5_ctx* par = ctx->parent;
+    DeviceState& s = *ctx->dev[0];
+    DeviceState& o = *par->dev[0];
+    if (par->has_mesh && (s.origin != &o || s.mesh_version != o.mesh_version)) alias_mesh(s, o);
+    ctx->has_mesh = par->has_mesh;
+    ctx->info = par->info;
+}
+
 // cudaMalloc may carve an allocation out of a larger block, and a CUDA IPC handle names the BLOCK:
 // the importer gets the block's base address. The driver knows the base (cuMemGetAddressRange);
 // the offset travels with the handle. libcuda is loaded lazily so that the library still loads on
@@ -624,8 +677,39 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
     }
 }
 
+int c5_create_sibling(c5_ctx* parent, c5_ctx** out) {
+    if (!parent || !out) return C5_E_INVALID;
+    *out = nullptr;
+    if (parent->parent || parent->dev.size() != 1) {
+        parent->err = "create_sibling: the parent must be a single-device context that is not itself a sibling";
+        return C5_E_INVALID;
+    }
+    const int32_t device = parent->dev[0]->device;
+    c5_ctx* ctx = nullptr;
+    const int rc = c5_create(&device, 1, &ctx);
+    if (rc != C5_OK) return rc;
+    ctx->parent = parent;
+    parent->siblings.push_back(ctx);
+    *out = ctx;
+    return C5_OK;
+}
+
 void c5_destroy(c5_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->parent) { // a sibling leaves its parent's list
+        auto& sib = ctx->parent->siblings;
+        sib.erase(std::remove(sib.begin(), sib.end(), ctx), sib.end());
+    }
+    for (c5_ctx* s : ctx->siblings) { // a parent going first takes the shared mesh with it
+        if (!kHostSim) {
+            cudaSetDevice(s->dev[0]->device);
+            cudaDeviceSynchronize();
+        }
+        s->parent = nullptr;
+        s->has_mesh = false;
+        s->dev[0]->origin = nullptr;
+    }
+    ctx->siblings.clear();
     nccl_close(ctx->nccl);
     ctx->nccl = nullptr;
     if (!kHostSim) {
@@ -673,7 +757,10 @@ int c5_upload_mesh(c5_ctx* ctx, const double* points_xyz, int64_t n_points, cons
                    int64_t n_tets, const double* alpha, const double* q) {
     if (!ctx) return C5_E_INVALID;
     return guarded(ctx, [&] {
+        if (ctx->parent) fail(C5_E_STATE, "upload_mesh: a sibling context shares its parent's mesh; upload through the parent");
         if (!points_xyz || !tet_vertices || !alpha || !q) fail(C5_E_INVALID, "upload_mesh: NULL array");
+        if (!ctx->siblings.empty() && !kHostSim) C5_CUDA(cudaDeviceSynchronize()); // siblings may be rendering from it
+        ctx->dev[0]->mesh_version++;
         ctx->has_mesh = false;
         const size_t before = dev_bytes_in_use();
         for (auto& dp : ctx->dev) {
@@ -692,12 +779,20 @@ int c5_upload_mesh(c5_ctx* ctx, const double* points_xyz, int64_t n_points, cons
 
 int c5_upload_solids(c5_ctx* ctx, const double* tet_points, int64_t n_tets, int32_t follows_view) {
     if (!ctx) return C5_E_INVALID;
-    return guarded(ctx, [&] { upload_solids(ctx, tet_points, n_tets, follows_view); });
+    return guarded(ctx, [&] {
+        if (ctx->parent) fail(C5_E_STATE, "upload_solids: upload through the parent context");
+        if (!ctx->siblings.empty() && !kHostSim) C5_CUDA(cudaDeviceSynchronize());
+        ctx->dev[0]->mesh_version++;
+        upload_solids(ctx, tet_points, n_tets, follows_view);
+    });
 }
 
 int c5_clear_solids(c5_ctx* ctx) {
     if (!ctx) return C5_E_INVALID;
     return guarded(ctx, [&] {
+        if (ctx->parent) fail(C5_E_STATE, "clear_solids: clear through the parent context");
+        if (!ctx->siblings.empty() && !kHostSim) C5_CUDA(cudaDeviceSynchronize());
+        ctx->dev[0]->mesh_version++;
         for (auto& dp : ctx->dev) {
             use_device(*dp);
             for (SolidSet* ss : {&dp->solid_follow, &dp->solid_static}) {
@@ -733,6 +828,7 @@ int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps
 int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream, c5_stats* stats) {
     if (!ctx) return C5_E_INVALID;
     return guarded(ctx, [&] {
+        follow_parent(ctx);
         if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
         if (!d_out) fail(C5_E_INVALID, "render_device: d_out is NULL");
         if (ctx->dev.size() != 1) fail(C5_E_INVALID, "render_device: single-device contexts only");

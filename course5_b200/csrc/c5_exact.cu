@@ -141,6 +141,24 @@ C5_HD double edge_x(const EdgeFn& e, double y) {
     return div_by(e.dx * (y - e.y1), e.dy, e.rdy) + e.x1;
 }
 
+// Sets the bytes [p, e) to 1. Thousands of fan faces overlap every solid pixel, so a byte is tested
+// first and stored only the first time; the aligned middle of the span goes eight pixels at a time
+// (concurrent writers only ever write ones, so a wide store inside the span cannot lose anything).
+C5_HD void mark_span(uint8_t* p, uint8_t* e) {
+    while (p < e && (reinterpret_cast<uintptr_t>(p) & 7u)) {
+        if (!*p) *p = 1;
+        p++;
+    }
+    const unsigned long long ones = 0x0101010101010101ull;
+    for (; p + 8 <= e; p += 8) {
+        unsigned long long* w = reinterpret_cast<unsigned long long*>(p);
+        if (*w != ones) *w = ones;
+    }
+    for (; p < e; p++) {
+        if (!*p) *p = 1;
+    }
+}
+
 // Inclusive scanline footprint of one projected triangle -> mask bytes (idempotent stores).
 // Rows are independent (the reference's running y equals the accumulated table entry ys[j]), so
 // `n_lanes` threads share one face, lane `lane` taking rows j_lo + lane, j_lo + lane + n_lanes, ...
@@ -175,10 +193,7 @@ C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const 
         const long long i_hi = static_cast<long long>(floor(pixel_of_x(g, x_hi)));
         const long long i_lo = static_cast<long long>(ceil(pixel_of_x(g, x_lo)));
         uint8_t* row = g.mask + static_cast<size_t>(j) * g.res_x;
-        // thousands of fan faces overlap every solid pixel: test first, store only the first time
-        for (long long i = i_lo; i <= i_hi; i++) {
-            if (!row[i]) row[i] = 1;
-        }
+        if (i_lo <= i_hi) mark_span(row + i_lo, row + i_hi + 1);
     }
 }
 
@@ -479,13 +494,24 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
     }
 }
 
-void launch_prepare_cells(DeviceState& d, double alpha_limit) {
+void launch_prepare_cells(DeviceState& dd, double alpha_limit) {
+    // cells[].s belongs to the context that owns the mesh; its siblings read the same array, possibly
+    // on other streams right now, so a change of --alpha_limit (rare) is fenced by device-wide syncs
+    DeviceState& d = dd.origin ? *dd.origin : dd;
     if (d.cells_limit_valid && d.cells_limit == alpha_limit) return;
+    const bool shared = dd.origin != nullptr || d.mesh_shared;
+    if (shared && !kHostSim) C5_CUDA(cudaDeviceSynchronize());
+    struct SyncAfter {
+        bool on;
+        ~SyncAfter() {
+            if (on) cudaDeviceSynchronize();
+        }
+    } sync_after{shared && !kHostSim};
     count_launch();
     if (kHostSim) {
         for (int64_t t = 0; t < d.n_tets; t++) prepare_cell_body(t, d.cells.p, d.q0.p, alpha_limit);
     } else {
-        prepare_cells<<<grid_for(d.n_tets, 256), 256, 0, d.stream>>>(d.n_tets, d.cells.p, d.q0.p, alpha_limit);
+        prepare_cells<<<grid_for(d.n_tets, 256), 256, 0, dd.stream>>>(d.n_tets, d.cells.p, d.q0.p, alpha_limit);
         C5_CUDA(cudaGetLastError());
     }
     d.cells_limit = alpha_limit;

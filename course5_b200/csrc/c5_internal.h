@@ -42,6 +42,9 @@ struct DeviceState {
     DevBuf<double> q0;               // Q per tet (Morton order); cells[t].s is derived from it
     double cells_limit = 0.0;        // the alpha_limit cells[].s was last prepared for
     bool cells_limit_valid = false;
+    DeviceState* origin = nullptr;   // sibling context: the device state that owns the mesh (and these two flags)
+    uint64_t mesh_version = 0;       // bumped by every upload; a sibling re-aliases when it falls behind
+    bool mesh_shared = false;        // some sibling aliases this state's arrays
     DevBuf<BFace> bfaces;            // Morton-sorted boundary faces (BVH leaves)
     DevBuf<BvhNode> nodes;           // n_bfaces - 1 internal nodes, BFS order (root = 0)
     DevBuf<int32_t> node_parent;     // per internal node: (parent << 1) | which child, -1 for the root
@@ -81,6 +84,8 @@ struct c5_ctx {
     c5_mesh_info info{};
     std::vector<uint64_t> last_row_cost;
     void* nccl = nullptr; // NcclGroup*, multi-device contexts only
+    c5_ctx* parent = nullptr;        // sibling context (c5_create_sibling): shares parent's mesh and solids
+    std::vector<c5_ctx*> siblings;   // contexts created from this one
     std::vector<std::pair<void*, bool>> images;   // c5_image_create (true) / c5_image_open (false) pointers
     std::vector<std::pair<void*, void*>> image_offsets; // imported images: (pointer handed out, mapping base)
     std::vector<void*> registered;                // c5_host_register pointers

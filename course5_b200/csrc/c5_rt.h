@@ -57,22 +57,32 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owner = true; // false: a view of memory another DevBuf owns (sibling contexts share the mesh)
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) {
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owner(o.owner) {
         o.p = nullptr;
         o.n = 0;
+        o.owner = true;
     }
     DevBuf& operator=(DevBuf&& o) noexcept {
         if (this != &o) {
             release();
             p = o.p;
             n = o.n;
+            owner = o.owner;
             o.p = nullptr;
             o.n = 0;
+            o.owner = true;
         }
         return *this;
+    }
+    void alias(const DevBuf& o) { // the owner must outlive this view
+        release();
+        p = o.p;
+        n = o.n;
+        owner = false;
     }
     ~DevBuf() { release(); }
     void alloc(size_t count) {
@@ -84,9 +94,10 @@ struct DevBuf {
         if (count > n) alloc(count);
     }
     void release() {
-        if (p) dev_free(p);
+        if (p && owner) dev_free(p);
         p = nullptr;
         n = 0;
+        owner = true;
     }
     size_t bytes() const { return n * sizeof(T); }
 };

@@ -37,6 +37,7 @@ slowest one.
 """
 from __future__ import annotations
 
+import contextlib
 from multiprocessing import shared_memory
 
 import numpy as np
@@ -53,7 +54,7 @@ class BandRenderer:
     """Renders row bands of successive views on this rank's device and assembles them on rank 0."""
 
     def __init__(self, ctx: api.Context, *, device: torch.device, rank: int, world: int,
-                 base_cost: float = 64.0, gather: str = "auto"):
+                 base_cost: float = 64.0, gather: str = "auto", lanes: int = 2):
         self.ctx, self.device, self.rank, self.world = ctx, device, rank, world
         self.base_cost = base_cost
         if gather == "auto":
@@ -69,6 +70,8 @@ class BandRenderer:
         self._count = 0
         self._bands = None                 # cached cut, valid until the row costs change
         self._flag = None
+        self.n_lanes = lanes
+        self._lanes = []                   # [(context, side stream)] on CUDA, created on first use
 
     # -- band cuts --------------------------------------------------------------------------------
     def bands(self, res_y: int) -> list[tuple[int, int]]:
@@ -122,7 +125,9 @@ class BandRenderer:
                 req.wait()
 
     def finish(self):
-        """Waits (on the current stream) for every exchange still in flight."""
+        """Orders the current stream after every view and every exchange still in flight."""
+        if self._lanes:
+            self._join_lanes()
         self._drain(self._count)
 
     def close(self):
@@ -136,6 +141,35 @@ class BandRenderer:
                 self._image[par] = None
                 self.ctx.image_close(self._peer[par][0])
                 self._peer[par] = None
+        for ctx, _ in self._lanes[1:]:
+            ctx.close()
+        self._lanes = []
+
+    # -- lanes ------------------------------------------------------------------------------------
+    def _lane(self, k: int):
+        """(context, torch stream or None) that renders view k. On CUDA there are two lanes — this
+        context and a sibling sharing its mesh (c5_create_sibling), each with its own side stream —
+        so that consecutive pipelined views overlap on the device: the last rays of view k no longer
+        leave most SMs idle, because view k+1's blocks are already there to take them."""
+        if self.device.type != "cuda":
+            return self.ctx, None
+        if not self._lanes:
+            self._lanes = [(self.ctx, torch.cuda.Stream(self.device))]
+            if self.n_lanes > 1:
+                self._lanes.append((self.ctx.sibling(), torch.cuda.Stream(self.device)))
+        return self._lanes[k % len(self._lanes)]
+
+    def kernel_launches(self) -> int:
+        """Kernels launched so far by every context this renderer drives."""
+        if not self._lanes:
+            return self.ctx.kernel_launches()
+        return sum(c.kernel_launches() for c, _ in self._lanes)
+
+    def _join_lanes(self):
+        """Orders the caller's current stream after everything enqueued on the lane streams."""
+        cur = torch.cuda.current_stream(self.device)
+        for _, s in self._lanes:
+            cur.wait_stream(s)
 
     # -- one view ---------------------------------------------------------------------------------
     def render(self, view: api.View, *, gather: bool = True, rebalance: bool | str = True, stats: bool = True,
@@ -143,9 +177,10 @@ class BandRenderer:
         """Renders this rank's band of `view`; returns (image on rank 0 or None, stats, bands).
 
         The image is a (res_y, res_x, 2) float64 tensor on rank 0's device. With stats=False (and
-        rebalance=False) nothing is read back to the host: render and exchange are only enqueued on
-        the current stream. With pipeline=True the exchange is additionally left in flight (call
-        finish(), or render two more views, before reading the returned image).
+        rebalance=False) nothing is read back to the host: render and exchange are only enqueued.
+        With pipeline=True they are additionally left in flight on the lane's side stream (call
+        finish() before reading the returned image); otherwise the caller's current stream is
+        ordered after them on return.
         rebalance: True / "steps" = cut the next view's bands by this view's per-row tet-steps;
         "time" = additionally weight each band by the device time it took."""
         if not stats:
@@ -153,45 +188,56 @@ class BandRenderer:
         k = self._count
         self._count += 1
         par = k % N_SETS
-        # this view reuses the set of view k - 3: every rank must be past barrier k - 2 (module docstring)
-        self._drain(k - N_SETS + 1)
         bands = self.bands(view.res_y)
         lo, hi = bands[self.rank]
         v = api.View.from_buffer_copy(view)
         v.row_begin, v.row_end = lo, hi
-        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
         p2p = self.gather_mode == "p2p" and self.world > 1 and gather
-
         if p2p:
-            base = self._peer_image(view, par)
-            st = self.ctx.render_device(v, base + lo * view.res_x * 16, stream, stats=stats)
-            # barrier: when it completes on a rank's stream, every rank's band of this view is in
-            if self._flag is None:
-                self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._pending[k] = [dist.all_reduce(self._flag, async_op=True)]
+            self._peer_image(view, par)     # (re)creates the mapping outside the lane stream if needed
+        ctx, lane_stream = self._lane(k)
+
+        if lane_stream is not None:
+            # what the caller enqueued so far (e.g. its reads of older images) comes first
+            lane_stream.wait_stream(torch.cuda.current_stream(self.device))
+            scope = torch.cuda.stream(lane_stream)
+            stream = lane_stream.cuda_stream
+        else:
+            scope = contextlib.nullcontext()
+            stream = 0
+        with scope:
+            # this view reuses the set of view k - 3: every rank must be past barrier k - 2 (module docstring)
+            self._drain(k - N_SETS + 1)
+            if p2p:
+                base = self._peer[par][0]
+                st = ctx.render_device(v, base + lo * view.res_x * 16, stream, stats=stats)
+                # barrier: when it completes on a rank's stream, every rank's band of this view is in
+                if self._flag is None:
+                    self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self._pending[k] = [dist.all_reduce(self._flag, async_op=True)]
+            else:
+                self._buffers(view, hi - lo, par)
+                if self.rank == 0 and gather:
+                    target = self._image[par][lo * view.res_x * 2: hi * view.res_x * 2]
+                else:
+                    target = self._band_buf[par][: (hi - lo) * view.res_x * 2]
+                st = ctx.render_device(v, target.data_ptr(), stream, stats=stats)
+                if self.world > 1 and gather:
+                    ops = []
+                    if self.rank == 0:
+                        for r in range(1, self.world):
+                            rlo, rhi = bands[r]
+                            ops.append(dist.P2POp(dist.irecv, self._image[par][rlo * view.res_x * 2: rhi * view.res_x * 2], r))
+                    else:
+                        ops.append(dist.P2POp(dist.isend, target, 0))
+                    self._pending[k] = list(dist.batch_isend_irecv(ops))
             if not pipeline:
                 self._drain(k)
-        else:
-            self._buffers(view, hi - lo, par)
-            if self.rank == 0 and gather:
-                target = self._image[par][lo * view.res_x * 2: hi * view.res_x * 2]
-            else:
-                target = self._band_buf[par][: (hi - lo) * view.res_x * 2]
-            st = self.ctx.render_device(v, target.data_ptr(), stream, stats=stats)
-            if self.world > 1 and gather:
-                ops = []
-                if self.rank == 0:
-                    for r in range(1, self.world):
-                        rlo, rhi = bands[r]
-                        ops.append(dist.P2POp(dist.irecv, self._image[par][rlo * view.res_x * 2: rhi * view.res_x * 2], r))
-                else:
-                    ops.append(dist.P2POp(dist.isend, target, 0))
-                self._pending[k] = list(dist.batch_isend_irecv(ops))
-                if not pipeline:
-                    self._drain(k)
+        if not pipeline and lane_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(lane_stream)
 
         if rebalance:
-            cost = torch.from_numpy(self.ctx.last_row_cost(view.res_y).astype(np.float64))
+            cost = torch.from_numpy(ctx.last_row_cost(view.res_y).astype(np.float64))
             if rebalance == "time" and self.world > 1:
                 # rows of this band cost (band time / band steps) per tet-step: bands whose rays run
                 # at a lower rate get proportionally fewer rows next time

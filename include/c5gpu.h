@@ -148,6 +148,14 @@ int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream
  * rendered band are 0). Callers use it to cut cost-balanced row bands for the next view. */
 int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows);
 
+/* A second context on the same device that SHARES parent's uploaded mesh and solids (no copy) and
+ * owns only per-view state (rotated vertices, BVH boxes, mask, counters). Two views can then be in
+ * flight at once — c5_render_device(parent, ..., stream_a) and c5_render_device(sibling, ...,
+ * stream_b) — so that the tail of one view's walk overlaps the start of the next one's: a sweep's
+ * throughput is then set by the work, not by the last rays of every view. Uploads go through the
+ * parent (a sibling picks them up at its next render); destroy siblings before the parent. */
+int c5_create_sibling(c5_ctx* parent, c5_ctx** out);
+
 /* ---- one image, several processes (one process per GPU) -----------------------------------------
  * Row bands are independent (plane.cpp:161-169 has no cross-pixel state), so N processes can
  * render N bands of one view straight into ONE image and nothing has to be gathered afterwards:

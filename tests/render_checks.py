@@ -239,3 +239,36 @@ def check_grazing_rays(lib, port, *, n=12, res=(240, 180), env_name="C5_GRAZE_SE
         assert small.stats["grazing_rays"] == img.stats["grazing_rays"]
         assert np.array_equal(small.image, img.image)
         assert np.array_equal(small.steps, img.steps)
+
+
+def check_sibling_context(lib, stream_of=None):
+    """c5_create_sibling: same images as the parent, follows the parent's uploads, refuses its own."""
+    solids_a = synth.kuhn_cube(2, seed=3, side=0.2, centre=(1.0, 0.1, 0.0)).tet_points()
+    mesh = synth.kuhn_cube(7, seed=52)
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        ctx.upload_solids(solids_a, True)
+        sib = ctx.sibling()
+        try:
+            assert sib.mesh_info().n_tets in (0, mesh.n_tets)        # filled in at the first render
+            for flags in (dict(X=0.4, Y=0.2), dict(X=0.5, Y=0.0, alpha_limit=1.1)):
+                v = api.make_view(120, 90, lib=lib, **flags)
+                a, sa = ctx.render(v)
+                b, sb = sib.render(v)
+                assert np.array_equal(a, b, equal_nan=True) and sa["tet_steps"] == sb["tet_steps"]
+                assert sa["solid_pixels"] == sb["solid_pixels"] > 0
+            assert sib.mesh_info().n_tets == mesh.n_tets
+            with pytest.raises(api.C5Error):
+                sib.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+            with pytest.raises(api.C5Error):
+                sib.clear_solids()
+            # a new mesh through the parent reaches the sibling at its next render
+            mesh2 = synth.kuhn_cube(5, seed=53)
+            ctx.upload_mesh(mesh2.points, mesh2.tets, mesh2.alpha, mesh2.q)
+            ctx.clear_solids()
+            v = api.make_view(120, 90, X=0.3, Y=0.6, lib=lib)
+            a, sa = ctx.render(v)
+            b, sb = sib.render(v)
+            assert np.array_equal(a, b) and sb["solid_pixels"] == 0 and sb["tet_steps"] == sa["tet_steps"] > 0
+        finally:
+            sib.close()

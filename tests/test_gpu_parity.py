@@ -119,6 +119,33 @@ def test_render_device_writes_the_band(gpu_lib):
         assert np.array_equal(band.cpu().numpy(), full[30:70])
 
 
+def test_sibling_context(gpu_lib):
+    rc.check_sibling_context(gpu_lib)
+
+
+def test_two_views_in_flight(gpu_lib):
+    """BandRenderer's two lanes (context + sibling, two streams): pipelined views, some of them
+    grazing (their queue tags and the side-stream kernel are per context), equal one-at-a-time renders."""
+    import torch
+    from course5_b200.dist import BandRenderer
+    mesh = synth.kuhn_cube(20, seed=54)
+    dev = torch.device("cuda", 0)
+    with api.Context(devices=(0,), lib=gpu_lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        br = BandRenderer(ctx, device=dev, rank=0, world=1)
+        views = [api.make_view(400, 300, X=X, Y=Y, lib=gpu_lib) for X, Y in
+                 ((0.5, 0.0), (0.4, 0.3), (0.0, 0.5), (0.45, 1.2), (0.5, 1.0), (0.3, 1.7))]
+        for batch in (views[:3], views[3:], views[1:4]):
+            imgs = [br.render(v, stats=False, pipeline=True)[0] for v in batch]
+            br.finish()
+            torch.cuda.synchronize(dev)
+            for v, img in zip(batch, imgs):
+                want, _ = ctx.render(v)
+                assert np.array_equal(img.cpu().numpy(), want, equal_nan=True)
+        assert br.kernel_launches() > ctx.kernel_launches()      # the sibling did half of the work
+        br.close()
+
+
 def test_course_cli_end_to_end(gpu_lib, port, tmp_path):
     """The drop-in: `course -f grid.vtk -d out.vti ...` against the reference's own file-to-file
     flow (oracle/_ref when present, else the restatement + float cast). .vti values are doubles

@@ -107,3 +107,7 @@ def test_image_handles_and_host_register(hostsim_lib):
         ctx.host_unregister(out)
         with pytest.raises(api.C5Error):
             ctx.host_unregister(out)
+
+
+def test_sibling_context_shares_the_mesh(hostsim_lib):
+    rc.check_sibling_context(hostsim_lib)

@@ -369,8 +369,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2],
-                    help="views in flight per GPU (2 = alternate between the context and a sibling on two streams)")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each)")
     ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="auto",
                     help="N > 1: how bands reach rank 0's image (p2p = stored by the walk kernel over NVLink)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")

@@ -20,7 +20,8 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_SO = os.path.join(HERE, "libc5gpu.so")
+# C5GPU_LIBRARY: another build of the same library (A/B runs of two builds in one process-per-build experiment)
+DEFAULT_SO = os.environ.get("C5GPU_LIBRARY") or os.path.join(HERE, "libc5gpu.so")
 C5_MAX_ROT = 8
 PI = 3.14159265358979323846  # config.hpp:45
 

@@ -185,16 +185,21 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
 
     record(d, 0);
     launch_prepare_cells(d, v->alpha_limit); // no-op unless --alpha_limit changed since the last view
-    launch_rotate_vertices(d, p.rot, p.n_rot);
-    if (solids) launch_rotate_solids(d, p.rot, p.n_rot);
+    // experiment switch (scripts/exp_lanes.py): C5_SKIP_PREP=1 repeats the SAME view without redoing
+    // its per-view preparation, to separate what that costs from what the walk costs
+    static const bool skip_prep_env = std::getenv("C5_SKIP_PREP") != nullptr;
+    const bool skip_prep = skip_prep_env && d.prep_done;
+    if (!skip_prep) launch_rotate_vertices(d, p.rot, p.n_rot);
+    if (solids && !skip_prep) launch_rotate_solids(d, p.rot, p.n_rot);
     record(d, 1);
-    launch_bvh_refit(d);
+    if (!skip_prep) launch_bvh_refit(d);
     record(d, 2);
-    if (solids) {
+    if (solids && !skip_prep) {
         dev_zero(d.mask.p + static_cast<size_t>(p.row_begin) * v->res_x,
                  static_cast<size_t>(p.row_end - p.row_begin) * v->res_x, d.stream);
         launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y, p.row_begin, p.row_end);
     }
+    d.prep_done = true;
     record(d, 3);
     dev_zero(d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);
     dev_zero(d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(unsigned long long), d.stream);
@@ -728,6 +733,23 @@ void c5_destroy(c5_ctx* ctx) {
         if (!kHostSim) {
             cudaSetDevice(d.device);
             cudaStreamSynchronize(d.stream);
+        }
+        if (!kHostSim && d.trace_launches > 0) {
+            if (const char* path = std::getenv("C5_TRACE_FILE")) {
+                cudaDeviceSynchronize();
+                std::vector<unsigned long long> h(d.trace.n);
+                if (cudaMemcpy(h.data(), d.trace.p, d.trace.bytes(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                    if (FILE* f = std::fopen(path, "a")) {
+                        for (int l = 0; l < d.trace_launches; l++) {
+                            for (unsigned b = 0; b < d.trace_grid[l]; b++) {
+                                const unsigned long long* r = h.data() + (static_cast<size_t>(l) * kTraceBlocks + b) * 4;
+                                std::fprintf(f, "%p %d %u %llu %llu %llu\n", static_cast<void*>(ctx), l, b, r[2], r[0], r[1]);
+                            }
+                        }
+                        std::fclose(f);
+                    }
+                }
+            }
         }
         if (!kHostSim) {
             if (d.graze_stream) cudaStreamSynchronize(d.graze_stream);

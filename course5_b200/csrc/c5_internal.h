@@ -69,6 +69,12 @@ struct DeviceState {
     cudaStream_t graze_stream = nullptr; // the grazing-ray kernel runs beside the pixel kernel
     cudaEvent_t graze_fork = nullptr, graze_join = nullptr;
     int sm_count = 0;
+    bool prep_done = false;          // C5_SKIP_PREP experiment switch
+    // C5_TRACE_FILE: start / end time and SM of every block of the first pixel-kernel launches,
+    // written to that file when the context is destroyed (scripts/trace_blocks.py reads it)
+    DevBuf<unsigned long long> trace;
+    int trace_launches = 0;
+    unsigned trace_grid[64] = {};
 
     uint64_t launches = 0;
 };
@@ -108,6 +114,7 @@ void dedupe_solid_faces(DeviceState& d, SolidSet& ss); // fills ss.faces / ss.n_
 void launch_prepare_cells(DeviceState& d, double alpha_limit); // cells[t].s = q0[t] / min(alpha, limit)
 
 // c5_walk.cu
+constexpr int kTraceLaunches = 64, kTraceBlocks = 40960;
 struct WalkLaunch {
     int res_x, res_y, row_begin, row_end;
     int i_begin, i_end, j_begin, j_end; // pixel rectangle that can see the mesh (clipped to the band by the launch)

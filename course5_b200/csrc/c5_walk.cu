@@ -54,12 +54,14 @@ struct WalkParams {
     uint32_t generation;  // tag of this view's queue records
     uint32_t n_pixel_blocks; // grid of the pixel kernel: counters[kBlocksDone] reaches it when the queue is final
     int fence_stores;     // debugging aid (C5_STORE_FENCE): a system-scope fence after every pixel store
+    unsigned long long* trace; // debugging aid (C5_TRACE_FILE): per block {start ns, end ns, sm | launch << 32, block}
     int res_x, res_y, row_begin, row_end;
     int i0, i1, j0, j1;   // pixel rectangle [i0,i1) x [j0,j1) of the band that can see the mesh: the tiles cover it
     int n_tiles_x, n_tiles_y, n_macro_x;
     int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
     int graze_cap;        // entries one cooperative collection may hold (<= kGrazeList)
     int serial_cap;       // same for the serial (host loop) form (<= kSerialList)
+    int query_budget;     // BVH nodes one thread of the pixel kernel may visit per search before deferring the ray
     int max_steps;
     int round_float;
     double alpha_limit;
@@ -211,16 +213,29 @@ C5_HD void insert_entry(EntryList<kCap>& L, int cap, double z, int leaf) {
 // thread with a private stack. cap = 1 is the classic nearest-hit search: once one face is found,
 // every node whose box starts above it is pruned. L.n == cap on return means "there may be more
 // above L.z[cap - 1]"; L.n < cap means the list is complete.
+//
+// `budget` bounds the nodes one thread may visit. A ray that runs along a boundary wall (inside or
+// outside it) overlaps the boxes of every facet of that wall: proving "no further entry" then costs
+// hundreds of dependent loads, and the few blocks holding such rays ran 60 % longer than all others
+// (block timeline, profiles/r01_trace_band_c3.txt). A search that exceeds its budget returns false
+// and the ray is handed to the grazing-ray kernel, where 32 lanes share the traversal.
 template <int kCap>
-C5_HD void bvh_collect_entries(const WalkParams& P, const BvhNode* top, double px, double py, double z_after,
-                               EntryList<kCap>& L, int cap) {
+C5_HD bool bvh_collect_entries(const WalkParams& P, const BvhNode* top, double px, double py, double z_after,
+                               EntryList<kCap>& L, int cap, int budget) {
     int stack[kStack];
     int sp = 0;
     L.n = 0;
     int node = 0;
     const float fx_lo = f_round_down(px), fx_hi = f_round_up(px);
     const float fy_lo = f_round_down(py), fy_hi = f_round_up(py);
+    // (one exit from the loop: with a `return` in the middle the compiler stopped reconverging the
+    // warp after the search and the tet walk ran with half-empty warps — 8.3 instead of 4.7 ms on C3)
+    bool complete = true;
     while (true) {
+        if (--budget < 0) {
+            complete = false;
+            break;
+        }
         const BvhNode* n = (top && node < P.top_nodes) ? (top + node) : (P.nodes + node);
 #ifdef __CUDA_ARCH__
         const float4 bx = *reinterpret_cast<const float4*>(n->xlo); // xlo0 xlo1 xhi0 xhi1
@@ -262,6 +277,7 @@ C5_HD void bvh_collect_entries(const WalkParams& P, const BvhNode* top, double p
             node = stack[--sp];
         }
     }
+    return complete;
 }
 
 // ---- one crossing ----------------------------------------------------------------------------------
@@ -504,9 +520,26 @@ struct RayResult {
 // A ray's FIRST query is a nearest-hit search (cap 1: most rays enter once and the search stays as
 // cheap as it can be). After the first exit ONE more query asks for the next kInline entries above:
 // for a convex mesh it finds nothing after visiting a handful of nodes; a cavity gives one or two,
-// which are walked here. A full list means a grazing ray: its state goes to the deferred queue.
+// which are walked here. A full list, or a search that runs out of budget, means a grazing ray: its
+// state goes to the deferred queue.
+//
+// The four phases are written out and separated by __syncwarp over the lanes that trace (`tracing`,
+// a ballot taken where the warp is still whole): the searches and the walks must each run with the
+// warp CONVERGED — a search is hundreds of dependent loads and a walk hundreds of steps; executed
+// lane group by lane group they cost a multiple. Left to the compiler's reconvergence analysis this
+// was fragile: an innocent change to the search loop (a second exit) made it stop reconverging
+// after the search and the whole kernel ran 1.75 x slower (8.3 vs 4.7 ms on C3).
+C5_HD void sync_lanes(unsigned lanes) {
+#ifdef __CUDA_ARCH__
+    __syncwarp(lanes);
+#else
+    (void)lanes;
+#endif
+}
+
 template <bool kF32, bool kWide, int kPipe>
-C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py, uint32_t pixel) {
+C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py, uint32_t pixel,
+                          unsigned tracing) {
     RayResult r;
     r.tau = 0.0;
     r.inten = 0.0;
@@ -516,38 +549,52 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
     double z_after = -INFINITY;
     double gain_unused = 1.0;
     EntryList<kInline> L;
-    int cap = 1;
-    while (true) {
-        bvh_collect_entries(P, top, px, py, z_after, L, cap);
-        if (cap != 1 && L.n == cap) {
-#ifdef __CUDA_ARCH__
-            const unsigned long long slot = atomicAdd(&P.counters[kDeferred], 1ull);
-#else
-            const unsigned long long slot = P.counters[kDeferred]++;
-#endif
-            DeferredRay& q = P.queue[slot];
-            q.tau = r.tau;
-            q.inten = r.inten;
-            q.z_after = z_after;
-            q.pixel = pixel;
-#ifdef __CUDA_ARCH__
-            __threadfence(); // the record before its tag: a grazing warp may already be polling this slot
-            *reinterpret_cast<volatile uint32_t*>(&q.tag) = (P.generation << kTagShift) | r.steps;
-#else
-            q.tag = (P.generation << kTagShift) | r.steps;
-#endif
-            r.deferred = 1;
-            break;
-        }
-        for (int e = 0; e < L.n; e++) {
-            // an entry at or below the ray's position is already behind it (two boundary faces
-            // sharing the edge the ray passes through report the same depth)
-            if (!(L.z[e] > z_after) || r.error) continue;
+
+    // A: nearest entry
+    bool defer = !bvh_collect_entries(P, top, px, py, z_after, L, 1, P.query_budget);
+    sync_lanes(tracing);
+    // B: first crossing
+    const bool entered = !defer && L.n > 0;
+    if (entered) {
+        z_after = crossing<kF32, kWide, kPipe, false>(P, px, py, L.leaf[0], L.z[0], r.tau, r.inten, gain_unused, r.steps,
+                                                      r.error);
+    }
+    sync_lanes(tracing);
+    // C: anything above the exit?
+    L.n = 0;
+    if (entered && !r.error) {
+        const bool searched = bvh_collect_entries(P, top, px, py, z_after, L, kInline, P.query_budget);
+        defer = !searched || L.n == kInline; // too many boxes in the way, or too many entries
+    }
+    sync_lanes(tracing);
+    // D: the few re-entries of a cavity or a dent
+    for (int e = 0; e < kInline - 1; e++) {
+        // an entry at or below the ray's position is already behind it (two boundary faces sharing
+        // the edge the ray passes through report the same depth)
+        if (!defer && e < L.n && L.z[e] > z_after && !r.error) {
             z_after = crossing<kF32, kWide, kPipe, false>(P, px, py, L.leaf[e], L.z[e], r.tau, r.inten, gain_unused,
                                                           r.steps, r.error);
         }
-        if (cap != 1 || L.n == 0 || r.error) break;
-        cap = kInline;
+        sync_lanes(tracing);
+    }
+    if (defer) {
+#ifdef __CUDA_ARCH__
+        const unsigned long long slot = atomicAdd(&P.counters[kDeferred], 1ull);
+#else
+        const unsigned long long slot = P.counters[kDeferred]++;
+#endif
+        DeferredRay& q = P.queue[slot];
+        q.tau = r.tau;
+        q.inten = r.inten;
+        q.z_after = z_after;
+        q.pixel = pixel;
+#ifdef __CUDA_ARCH__
+        __threadfence(); // the record before its tag: a grazing warp may already be polling this slot
+        *reinterpret_cast<volatile uint32_t*>(&q.tag) = (P.generation << kTagShift) | r.steps;
+#else
+        q.tag = (P.generation << kTagShift) | r.steps;
+#endif
+        r.deferred = 1;
     }
     return r;
 }
@@ -589,7 +636,7 @@ C5_HD RayAcc graze_ray_serial(const WalkParams& P, const DeferredRay& q, double 
     EntryList<kSerialList> L;
     int crossings = 0;
     while (!a.error) {
-        bvh_collect_entries(P, nullptr, px, py, a.z_after, L, P.serial_cap);
+        bvh_collect_entries(P, nullptr, px, py, a.z_after, L, P.serial_cap, 0x7FFFFFFF);
         for (int e = 0; e < L.n; e++) {
             if (!(L.z[e] > a.z_after)) continue;
             double tau_k = 0.0, inten_k = 0.0, gain_k = 1.0;
@@ -829,6 +876,7 @@ __device__ __forceinline__ void graze_block(const WalkParams& P) {
             if (more) {
                 atomicAdd(&P.counters[kSteps], more);
                 atomicAdd(&P.row_cost[j], more);
+                if (q_steps == 0) atomicAdd(&P.counters[kHitPixels], 1ull); // deferred before its first step
             }
             if (a.error) atomicAdd(&P.counters[kWalkErrors], 1ull);
         }
@@ -887,15 +935,18 @@ __device__ __forceinline__ void walk_block_body(const WalkParams& P) {
     res.error = 0;
     res.deferred = 0;
     bool solid = false;
+    if (live) solid = P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i];
+    // the lanes that will trace a ray, agreed on while the warp is whole (trace_ray synchronises on it)
+    const unsigned tracing = __ballot_sync(0xFFFFFFFFu, live && !solid && tile_sees_mesh);
     if (live) {
-        solid = P.mask && P.mask[static_cast<size_t>(j) * P.res_x + i];
         if (solid) {
             const double nan = __longlong_as_double(0x7FF8000000000000ll); // quiet NaN (config.hpp:26-27)
             store_pixel(P, i, j, nan, nan, 0);
         } else {
             if (tile_sees_mesh) {
                 res = trace_ray<kF32, kWide, kPipe>(P, top, P.xs[i], P.ys[j],
-                                                    static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i));
+                                                    static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i),
+                                                    tracing);
             }
             if (!res.deferred) store_pixel(P, i, j, res.tau, res.inten, res.steps);
         }
@@ -922,9 +973,27 @@ __device__ __forceinline__ void walk_block_body(const WalkParams& P) {
     }
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2>
 __device__ __forceinline__ void walk_block(const WalkParams& P) {
+    if (P.trace && threadIdx.x == 0) P.trace[4ull * blockIdx.x] = global_ns(); // stored at once: nothing stays live
     walk_block_body<kF32, kWide, kPipe, kWarpsX, kWarpsY>(P);
+    if (P.trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned sm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            unsigned long long* rec = P.trace + 4ull * blockIdx.x;
+            rec[1] = global_ns();
+            rec[2] = sm;
+            rec[3] = blockIdx.x;
+        }
+    }
     // tells the grazing-ray kernel (running beside this one) when no more rays can be deferred
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -937,9 +1006,11 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
 
 // The product kernel, and register-capped variants kept for occupancy experiments
 // (C5_WALK_VARIANT=r64|r96 selects one at run time; ncu shows which is better where).
-__global__ void __launch_bounds__(kBlock) tet_walk_fp64(const WalkParams P) { walk_block<false, true, 0>(P); }
+// 7 blocks of 128 threads per SM = 72 registers: one more resident block than the 80 the compiler picks
+// on its own, measured faster (5.41 vs 5.64 ms on C3) despite a few spilled words outside the step loop
+__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64(const WalkParams P) { walk_block<false, true, 0>(P); }
 // optional single-precision step geometry (north-star item (d)); entry search and accumulators stay FP64
-__global__ void __launch_bounds__(kBlock) tet_walk_fp32(const WalkParams P) { walk_block<true, true, 0>(P); }
+__global__ void __launch_bounds__(kBlock, 8) tet_walk_fp32(const WalkParams P) { walk_block<true, true, 0>(P); }
 // experiment variants (C5_WALK_VARIANT): 128-bit loads, L1 prefetch of the next step, register caps
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, 0>(P); }
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, 1>(P); }
@@ -984,6 +1055,7 @@ void graze_on_host(const WalkParams& P, bool f32) {
         const uint32_t q_steps = q.tag & ((1u << kTagShift) - 1u);
         P.counters[kSteps] += a.steps - q_steps;
         P.row_cost[j] += a.steps - q_steps;
+        if (q_steps == 0 && a.steps > 0) P.counters[kHitPixels]++;
         if (a.error) P.counters[kWalkErrors]++;
     }
     P.counters[kTicket] = n_rays;
@@ -1007,8 +1079,8 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 continue;
             }
             const uint32_t pixel = static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i);
-            const RayResult r = f32 ? trace_ray<true, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel)
-                                    : trace_ray<false, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel);
+            const RayResult r = f32 ? trace_ray<true, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0)
+                                    : trace_ray<false, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0);
             if (!r.deferred) store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -1078,6 +1150,11 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         if (c >= 128 && c <= kGrazeList) P.graze_cap = c & ~1;
     }
     P.fence_stores = std::getenv("C5_STORE_FENCE") != nullptr;
+    P.query_budget = 64;
+    if (const char* e = std::getenv("C5_QUERY_BUDGET")) {
+        const int b = std::atoi(e);
+        if (b >= 1) P.query_budget = b;
+    }
     P.serial_cap = kSerialList;
     if (const char* e = std::getenv("C5_GRAZE_SERIAL_LIST")) {
         const int c = std::atoi(e);
@@ -1107,6 +1184,18 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     }
     const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
     P.n_pixel_blocks = grid;
+    P.trace = nullptr;
+    if (std::getenv("C5_TRACE_FILE") && d.trace_launches < kTraceLaunches) { // block timeline of the first launches
+        if (d.trace.n == 0) {
+            d.trace.alloc(static_cast<size_t>(kTraceLaunches) * kTraceBlocks * 4);
+            dev_zero(d.trace.p, d.trace.bytes(), d.stream);
+        }
+        if (grid <= kTraceBlocks) {
+            P.trace = d.trace.p + static_cast<size_t>(d.trace_launches) * kTraceBlocks * 4;
+            d.trace_grid[d.trace_launches] = grid;
+            d.trace_launches++;
+        }
+    }
     // fork: the grazing-ray kernel may start as soon as the counters are zero, i.e. beside the pixel kernel
     C5_CUDA(cudaEventRecord(d.graze_fork, d.stream));
     const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);

@@ -28,8 +28,9 @@ a lower rate than one of long central rays), so ``rebalance="time"`` additionall
 band's row costs by the time that band actually took.
 
 Sweeps can pipeline: with ``pipeline=True`` the exchange (or barrier) of view k is left in flight
-while the next views render into the other buffer sets. There are three sets, and a rank starts
-view k+3 (which reuses view k's set) only after barrier k+1 has completed. Rank 0 enqueues barrier
+while the next views render into the other buffer sets. With L views in flight per GPU ("lanes":
+the context and L-1 siblings sharing its mesh, each on its own stream) there are L+1 sets, and a
+rank starts view k+L+1 (which reuses view k's set) only after barrier k+1 has completed. Rank 0 enqueues barrier
 k+1 inside ``render(k+1)``, so the contract for the consumer of rank 0's image is: whatever reads
 image k must be finished, or enqueued on the current stream, BEFORE ``render(k+1)`` is called;
 the peers cannot overwrite it earlier, and a fast rank may still run one whole view ahead of the
@@ -47,9 +48,6 @@ import torch.distributed as dist
 from . import api
 
 
-N_SETS = 3
-
-
 class BandRenderer:
     """Renders row bands of successive views on this rank's device and assembles them on rank 0."""
 
@@ -63,14 +61,15 @@ class BandRenderer:
             raise ValueError("gather must be 'auto', 'p2p' or 'sendrecv'")
         self.gather_mode = gather
         self.row_cost: np.ndarray | None = None
-        self._band_buf = [None] * N_SETS   # buffer sets: the exchange of one view may still be reading /
-        self._image = [None] * N_SETS      # writing its set while the next views fill the others
-        self._peer = [None] * N_SETS       # p2p: (device pointer of rank 0's image, bytes) per set
+        self.n_lanes = max(1, int(lanes))
+        self.n_sets = self.n_lanes + 1     # view k + n_sets reuses view k's buffers (module docstring)
+        self._band_buf = [None] * self.n_sets  # buffer sets: the exchange of one view may still be reading /
+        self._image = [None] * self.n_sets     # writing its set while the next views fill the others
+        self._peer = [None] * self.n_sets      # p2p: (device pointer of rank 0's image, bytes) per set
         self._pending = {}                 # view number -> requests of its exchange / barrier
         self._count = 0
         self._bands = None                 # cached cut, valid until the row costs change
         self._flag = None
-        self.n_lanes = lanes
         self._lanes = []                   # [(context, side stream)] on CUDA, created on first use
 
     # -- band cuts --------------------------------------------------------------------------------
@@ -134,7 +133,7 @@ class BandRenderer:
         self.finish()
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
-        for par in range(N_SETS):
+        for par in range(self.n_sets):
             if self._peer[par] is not None:
                 if self.world > 1:
                     dist.barrier()
@@ -147,15 +146,15 @@ class BandRenderer:
 
     # -- lanes ------------------------------------------------------------------------------------
     def _lane(self, k: int):
-        """(context, torch stream or None) that renders view k. On CUDA there are two lanes — this
-        context and a sibling sharing its mesh (c5_create_sibling), each with its own side stream —
+        """(context, torch stream or None) that renders view k. On CUDA there are n_lanes lanes — this
+        context and siblings sharing its mesh (c5_create_sibling), each with its own side stream —
         so that consecutive pipelined views overlap on the device: the last rays of view k no longer
         leave most SMs idle, because view k+1's blocks are already there to take them."""
         if self.device.type != "cuda":
             return self.ctx, None
         if not self._lanes:
             self._lanes = [(self.ctx, torch.cuda.Stream(self.device))]
-            if self.n_lanes > 1:
+            for _ in range(self.n_lanes - 1):
                 self._lanes.append((self.ctx.sibling(), torch.cuda.Stream(self.device)))
         return self._lanes[k % len(self._lanes)]
 
@@ -187,7 +186,7 @@ class BandRenderer:
             rebalance = False
         k = self._count
         self._count += 1
-        par = k % N_SETS
+        par = k % self.n_sets
         bands = self.bands(view.res_y)
         lo, hi = bands[self.rank]
         v = api.View.from_buffer_copy(view)
@@ -206,8 +205,9 @@ class BandRenderer:
             scope = contextlib.nullcontext()
             stream = 0
         with scope:
-            # this view reuses the set of view k - 3: every rank must be past barrier k - 2 (module docstring)
-            self._drain(k - N_SETS + 1)
+            # this view reuses the set of view k - n_sets: every rank must be past the barrier that
+            # follows it, k - n_sets + 1 (module docstring)
+            self._drain(k - self.n_sets + 1)
             if p2p:
                 base = self._peer[par][0]
                 st = ctx.render_device(v, base + lo * view.res_x * 16, stream, stats=stats)

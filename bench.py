@@ -106,6 +106,35 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+class Watchdog(threading.Thread):
+    """Ends the process if the run stops making progress. A multi-GPU run that deadlocks (a collective
+    some rank never joins, a kernel that spins for ever) would otherwise sit on its GPUs until an
+    outer limit kills it; this way it fails fast, says in which phase, and frees the devices."""
+
+    def __init__(self, rank: int, limit_s: float):
+        super().__init__(daemon=True)
+        self.rank, self.limit_s = rank, limit_s
+        self.phase, self.t_phase, self.t0 = "start", time.monotonic(), time.monotonic()
+        self.verbose = os.environ.get("C5_BENCH_VERBOSE") == "1"
+
+    def tick(self, phase: str, limit_s: float | None = None):
+        now = time.monotonic()
+        if self.verbose or self.rank == 0:
+            print(f"[bench rank {self.rank}] +{now - self.t0:6.1f}s {phase}", file=sys.stderr, flush=True)
+        self.phase, self.t_phase = phase, now
+        if limit_s is not None:
+            self.limit_s = limit_s
+
+    def run(self):
+        while True:
+            time.sleep(2.0)
+            stalled = time.monotonic() - self.t_phase
+            if stalled > self.limit_s:
+                print(f"[bench rank {self.rank}] WATCHDOG: no progress for {stalled:.0f}s in phase '{self.phase}'; "
+                      "exiting (exit code 3)", file=sys.stderr, flush=True)
+                os._exit(3)
+
+
 def workload():
     mesh, view = synth.make_config(WORKLOAD)
     return mesh, view
@@ -185,9 +214,9 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def config_dict(mesh, view, n_gpus, gather="p2p", lanes=1):
+def config_dict(mesh, view, n_gpus, gather="p2p", lanes=1, name=WORKLOAD):
     return {
-        "workload": (f"{WORKLOAD}: synthetic Kuhn-split grid, {mesh.n_tets} tets / {mesh.n_points} points, "
+        "workload": (f"{name}: synthetic Kuhn-split grid, {mesh.n_tets} tets / {mesh.n_points} points, "
                      f"{view['res_x']}x{view['res_y']}, -X {view['X']} -Y {view['Y']} --alpha_limit "
                      f"{view['alpha_limit']}, reference Roche lobe + sphere as solids"),
         "res_x": view["res_x"], "res_y": view["res_y"], "n_tets": mesh.n_tets,
@@ -215,20 +244,39 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
-    if not torch.cuda.is_available():
+    dry = args.dry_run_hostsim   # CPU rehearsal of this function's control flow (tests/test_bench.py); not a measurement
+    if not dry and not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path "
                          "(use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
+    if dry:
+        device = torch.device("cpu")
+        lib = api.load_library(os.path.join(ROOT, "tests", "hostsim", "libc5hostsim.so"))
+    else:
+        torch.cuda.set_device(local_rank)
+        device = torch.device("cuda", local_rank)
+        lib = None
+    dog = Watchdog(rank, limit_s=float(os.environ.get("C5_BENCH_STALL_LIMIT", "240")))
+    dog.start()
+    dog.tick("init process group" if world > 1 else "single process")
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=device)
+        if dry:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=device)
 
-    mesh, view = workload()
-    solids = reference_solids(view["D"])
+    dog.tick("synthetic mesh + solids on the host")
+    if dry:
+        mesh = synth.kuhn_cube(8, seed=3)
+        view = dict(res_x=160, res_y=120, X=0.5, Y=0.0, I=0.0, D=0.0, alpha_limit=3.0)
+        solids = None
+    else:
+        mesh, view = workload()
+        solids = reference_solids(view["D"])
 
-    ctx = api.Context(devices=(local_rank,))
+    dog.tick("upload (topology, BVH)")
+    ctx = api.Context(devices=(0 if dry else local_rank,), lib=lib)
     t0 = time.perf_counter()
     info = ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
     if solids is not None:
@@ -236,25 +284,36 @@ def run_ours(args):
         ctx.upload_solids(solids[1], False)
     upload_s = time.perf_counter() - t0
     v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
-                      alpha_limit=view["alpha_limit"])
+                      alpha_limit=view["alpha_limit"], lib=ctx.lib)
     br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=args.lanes)
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize(device)
+        if not dry:
+            torch.cuda.synchronize(device)
+
+    class HostClock:   # dry run only: stands in for a CUDA event
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t)
 
     # ---- value: everything resident, output stays on the device -------------------------------
     # warm-up views also settle the band cuts: tet-steps of the previous view, weighted by the time
     # each band took (a few iterations; a sweep does the same from frame to frame)
     n_warm = max(args.warmup, 3) if world == 1 else max(args.warmup, 6)
-    for _ in range(n_warm):
-        br.render(v, rebalance="time")
+    for k in range(n_warm):
+        dog.tick(f"warm-up view {k}")
+        _, _, bands = br.render(v, rebalance="time")
+    dog.tick(f"bands {bands}")
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not dry:
+        sampler.start()
     launches0 = br.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0, ev1 = (HostClock(), HostClock()) if dry else (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     walk_ms, steps_total, stats_last = [], 0, None
     ev0.record()
     # The views are only enqueued (no host readback between them; statistics come from a second
@@ -263,14 +322,16 @@ def run_ours(args):
     # next. N > 1, gather=p2p: the walk stores straight into rank 0's image over NVLink and the
     # barrier of view k is left in flight (three images); gather=sendrecv: the same with one grouped
     # ncclSend/ncclRecv per view.
+    dog.tick(f"timed region: {args.steps} views, {br.n_lanes} in flight, gather={br.gather_mode}")
     for _ in range(args.steps):
         _, _, bands = br.render(v, rebalance=False, stats=False, pipeline=True)
     br.finish()
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    dog.tick("statistics pass")
+    clocks = sampler.stop() if not dry else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
     launches = br.kernel_launches() - launches0
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms = max(ev0.elapsed_time(ev1), 1e-6)
     for _ in range(3):
         _, st, bands = br.render(v, rebalance=False)
         walk_ms.append(st["ms_walk"])
@@ -283,9 +344,12 @@ def run_ours(args):
     # every rank's c5_render writes its band in place over its own PCIe link, then one barrier.
     # Wall clock around the calls a user makes; the image is complete in host memory at the end
     # of every step.
+    dog.tick("e2e: host image")
     from course5_b200.dist import SharedHostImage
     if world == 1:
-        host_out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64).pin_memory()
+        host_out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64)
+        if not dry:
+            host_out = host_out.pin_memory()
         host_np = host_out.numpy()
         shared = None
     else:
@@ -307,6 +371,7 @@ def run_ours(args):
     if shared is not None:
         shared.close()
 
+    dog.tick("reduce over ranks")
     # ---- reduce over ranks ----------------------------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_s * 1e3, float(np.mean(walk_ms))], dtype=torch.float64, device=device)
     s = torch.tensor([band_steps, launches], dtype=torch.int64, device=device)
@@ -315,6 +380,16 @@ def run_ours(args):
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     elapsed_ms, e2e_ms, walk_ms_max = (float(x) for x in t.cpu())
     total_steps, total_launches = (int(x) for x in s.cpu())
+    # the roofline line describes the walk of the band with the most tet-steps (rank 0's may be empty)
+    mine = torch.tensor([float(band_steps), float((bands[rank][1] - bands[rank][0]) * view["res_x"]),
+                         float(np.mean(walk_ms))], dtype=torch.float64, device=device)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = [p.cpu().tolist() for p in per_rank]
+    busiest = max(range(world), key=lambda r: per_rank[r][0])
 
     if rank == 0:
         pixels = view["res_x"] * view["res_y"]
@@ -322,10 +397,9 @@ def run_ours(args):
         value = total_steps / (ms_per_step * 1e-3)
         e2e_value = total_steps / (e2e_ms * 1e-3 / args.steps)
         peak, peak_src = measured_hbm_peak()
-        # dominant kernel (tet_walk_fp64) on rank 0's band; at N = 1 that is the whole image
-        k_steps = band_steps
-        k_pixels = (bands[0][1] - bands[0][0]) * view["res_x"]
-        k_ms = float(np.mean(walk_ms))
+        # dominant kernel (tet_walk_fp64 + its grazing-ray kernel) on the busiest band; at N = 1 the whole image
+        k_steps, k_pixels, k_ms = per_rank[busiest]
+        k_ms = max(k_ms, 1e-9)      # (only the dry run has zero device times)
         achieved = (k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL) / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "tet_steps_per_sec", "value": value, "unit": "tet-steps/s", "n_gpus": world,
@@ -333,22 +407,26 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "pixels_per_sec": pixels / (ms_per_step * 1e-3),
             "tet_steps_per_view": total_steps,
-            "config": config_dict(mesh, view, world, br.gather_mode, br.n_lanes),
+            "config": config_dict(mesh, view, world, br.gather_mode, br.n_lanes, "dry-run cube (no solids)" if dry else WORKLOAD),
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(api.C.sizeof(api.View)), "d2h_bytes_per_step": pixels * 16,
                     "api": "c5_render (pinned host buffer)" if world == 1 else
                     "c5_render (row band) into one pinned shared-memory host image, one barrier per view"},
             "gpu_launches": total_launches,
-            "roofline": {"kernel": "tet_walk_fp64", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "tet_walk_fp64", "rank": busiest, "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
                          "peak_source": peak_src, "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL},
+                         "algorithmic_bytes_per_launch": int(k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL)},
+            "bands": [list(b) for b in bands],
             "phases_ms": {k: stats_last[k] for k in ("ms_rotate", "ms_bvh", "ms_mask", "ms_walk", "ms_total")},
             "one_off": {"upload_and_topology_s": upload_s, "device_bytes": int(info.device_bytes),
                         "boundary_faces": int(info.n_boundary_faces)},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if dry:
+            line["data"] = "DRY RUN on the host-loop test build: control flow only, not a measurement"
+        if world == 1 and not args.no_cpu_baseline and not dry:
+            dog.tick("cpu_baseline: the reference on the host cores", limit_s=1800.0)
             sample = reference_sample(view)
             r = time_reference(mesh, sample, steps=1, warmup=0)
             line["cpu_baseline"] = {
@@ -357,6 +435,7 @@ def run_ours(args):
                 "sample": (f"{WORKLOAD} mesh + reference solids, same flags, {sample['res_x']}x{sample['res_y']} "
                            f"(1/4 of the pixels), {r['tet_steps']} tet-steps, 1 run")}
         print(json.dumps(line), flush=True)
+    dog.tick("teardown", limit_s=120.0)
     br.close()
     ctx.close()
     if world > 1:
@@ -371,8 +450,12 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--lanes", type=int, default=2, choices=[1, 2, 3, 4],
                     help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each)")
-    ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="auto",
-                    help="N > 1: how bands reach rank 0's image (p2p = stored by the walk kernel over NVLink)")
+    ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="sendrecv",
+                    help="N > 1: how bands reach rank 0's image. sendrecv = one grouped ncclSend/ncclRecv per view "
+                         "(default: the path validated at 8 GPUs); p2p = stored by the walk kernel straight into rank "
+                         "0's image over NVLink peer mappings (validated at 2 GPUs, same speed there)")
+    ap.add_argument("--dry-run-hostsim", action="store_true",
+                    help="rehearse the control flow on CPU with tests/hostsim (gloo, tiny mesh); prints a line marked as a dry run")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

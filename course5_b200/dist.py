@@ -69,6 +69,7 @@ class BandRenderer:
         self._pending = {}                 # view number -> requests of its exchange / barrier
         self._count = 0
         self._bands = None                 # cached cut, valid until the row costs change
+        self._cost_has_base = False        # row_cost is measured time (the per-row constant is in it)
         self._flag = None
         self._lanes = []                   # [(context, side stream)] on CUDA, created on first use
 
@@ -80,7 +81,7 @@ class BandRenderer:
             cost = np.ones(res_y)          # first view: equal heights
             cut = api.balanced_bands(cost, self.world)
         else:
-            cut = api.balanced_bands(self.row_cost, self.world, base_cost=self.base_cost)
+            cut = api.balanced_bands(self.row_cost, self.world, base_cost=0.0 if self._cost_has_base else self.base_cost)
         self._bands = (res_y, cut)
         return cut
 
@@ -237,18 +238,27 @@ class BandRenderer:
             torch.cuda.current_stream(self.device).wait_stream(lane_stream)
 
         if rebalance:
-            cost = torch.from_numpy(ctx.last_row_cost(view.res_y).astype(np.float64))
+            steps = torch.from_numpy(ctx.last_row_cost(view.res_y).astype(np.float64))
+            both = torch.zeros((2, view.res_y), dtype=torch.float64)
+            both[0] = steps
             if rebalance == "time" and self.world > 1:
-                # rows of this band cost (band time / band steps) per tet-step: bands whose rays run
-                # at a lower rate get proportionally fewer rows next time
-                band_cost = float(cost.sum()) + self.base_cost * (hi - lo)
+                # spread the time this band took over its rows in proportion to their tet-steps (plus
+                # the per-row constant): bands whose rays run at a lower rate, or that carry the solid
+                # mask, get proportionally fewer rows next time
+                weight = steps + self.base_cost * _band_indicator(view.res_y, lo, hi)
                 band_ms = float(st["ms_mask"] + st["ms_walk"])
-                cost = (cost + self.base_cost * _band_indicator(view.res_y, lo, hi)) * (band_ms / max(band_cost, 1.0))
+                both[1] = weight * (band_ms / max(float(weight.sum()), 1.0))
             if self.world > 1:
-                cost = cost.to(self.device)
-                dist.all_reduce(cost, op=dist.ReduceOp.SUM)
-                cost = cost.cpu()
-            self.row_cost = cost.numpy().astype(np.float64)
+                both = both.to(self.device)
+                dist.all_reduce(both, op=dist.ReduceOp.SUM)
+                both = both.cpu()
+            if rebalance == "time" and float(both[1].sum()) > 0.0:
+                new_cost = both[1].numpy().astype(np.float64)                                    # milliseconds per row
+                if self._cost_has_base and self.row_cost is not None and self.row_cost.shape == new_cost.shape:
+                    new_cost = 0.5 * (new_cost + self.row_cost)   # damped: a band's rate depends on its own cut
+                self.row_cost, self._cost_has_base = new_cost, True
+            else:
+                self.row_cost, self._cost_has_base = both[0].numpy().astype(np.float64), False  # tet-steps per row
             self._bands = None
 
         image = None

@@ -255,7 +255,7 @@ def run_ours(args):
         torch.cuda.set_device(local_rank)
         device = torch.device("cuda", local_rank)
         lib = None
-    dog = Watchdog(rank, limit_s=float(os.environ.get("C5_BENCH_STALL_LIMIT", "240")))
+    dog = Watchdog(rank, limit_s=float(os.environ.get("C5_BENCH_STALL_LIMIT", "150" if world == 1 else "90")))
     dog.start()
     dog.tick("init process group" if world > 1 else "single process")
     if world > 1:
@@ -346,7 +346,10 @@ def run_ours(args):
     # of every step.
     dog.tick("e2e: host image")
     from course5_b200.dist import SharedHostImage
-    if world == 1:
+    if os.environ.get("C5_BENCH_FAKE_HANG") == "1" and args.lanes > 1:   # tests/test_bench.py: the fallback path
+        time.sleep(10_000)
+    old_style = world > 1 and args.e2e == "gather"
+    if world == 1 or old_style:
         host_out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64)
         if not dry:
             host_out = host_out.pin_memory()
@@ -358,14 +361,22 @@ def run_ours(args):
     lo, hi = bands[rank]
     ve = api.View.from_buffer_copy(v)
     ve.row_begin, ve.row_end = lo, hi
+    def e2e_step():
+        if old_style:      # band gather on the devices, then ONE device-to-host copy of the image on rank 0
+            img, _, _ = br.render(v, rebalance=False, stats=False)
+            if rank == 0:
+                host_out.copy_(img, non_blocking=False)
+        else:
+            ctx.render(ve, out=host_np)
+            if world > 1:
+                shared.barrier()
+
     for _ in range(2):
-        ctx.render(ve, out=host_np)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.render(ve, out=host_np)
-        if world > 1:
-            shared.barrier()
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     if shared is not None:
@@ -411,6 +422,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(api.C.sizeof(api.View)), "d2h_bytes_per_step": pixels * 16,
                     "api": "c5_render (pinned host buffer)" if world == 1 else
+                    "BandRenderer.render + one device-to-host copy on rank 0" if old_style else
                     "c5_render (row band) into one pinned shared-memory host image, one barrier per view"},
             "gpu_launches": total_launches,
             "roofline": {"kernel": "tet_walk_fp64", "rank": busiest, "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -423,6 +435,8 @@ def run_ours(args):
                         "boundary_faces": int(info.n_boundary_faces)},
             "clocks": clocks,
         }
+        if os.environ.get("C5_BENCH_ATTEMPTS"):
+            line["attempts"] = json.loads(os.environ["C5_BENCH_ATTEMPTS"])   # configurations left before this one
         if dry:
             line["data"] = "DRY RUN on the host-loop test build: control flow only, not a measurement"
         if world == 1 and not args.no_cpu_baseline and not dry:
@@ -457,11 +471,53 @@ def main():
     ap.add_argument("--dry-run-hostsim", action="store_true",
                     help="rehearse the control flow on CPU with tests/hostsim (gloo, tiny mesh); prints a line marked as a dry run")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--e2e", choices=["shared-host", "gather"], default="shared-host",
+                    help="N > 1: e2e through one pinned shared-memory host image written by every rank (default), or "
+                         "through the band gather plus one device-to-host copy on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("C5_BENCH_CHILD") is None:
+        run_with_fallback(args)
     else:
         run_ours(args)
+
+
+def run_with_fallback(args):
+    """N > 1: every rank runs the measurement in a CHILD process and falls back to a more conservative
+    configuration if the first one does not finish. A multi-process GPU run that deadlocks cannot be
+    rescued from inside (the collective never returns); the child's own watchdog ends it, every rank
+    sees a non-zero exit code at about the same time, and all of them start the next attempt — on a
+    fresh rendezvous port, since the first attempt's store is dead. The parent touches neither CUDA
+    nor NCCL, so a killed child leaves the devices free. What was attempted and why it was left is
+    recorded in the line that finally prints ("attempts")."""
+    import subprocess
+    rank = int(os.environ.get("RANK", "0"))
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    attempts = [dict(gather=args.gather, lanes=args.lanes, e2e=args.e2e)]
+    safe = dict(gather="sendrecv", lanes=1, e2e="gather")
+    if attempts[0] != safe:
+        attempts.append(safe)
+    log = []
+    for i, a in enumerate(attempts):
+        env = dict(os.environ, C5_BENCH_CHILD="1", MASTER_PORT=str(base_port + 1 + i), TORCHELASTIC_USE_AGENT_STORE="False",
+                   C5_BENCH_ATTEMPTS=json.dumps(log))
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--e2e", a["e2e"]]
+        if args.dry_run_hostsim:
+            cmd.append("--dry-run-hostsim")
+        if args.no_cpu_baseline:
+            cmd.append("--no-cpu-baseline")
+        p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True)   # stderr passes through
+        if p.returncode == 0:
+            if rank == 0:
+                sys.stdout.write(p.stdout)
+                sys.stdout.flush()
+            return
+        log.append(dict(a, exit_code=p.returncode))
+        print(f"[bench rank {rank}] attempt {a} ended with exit code {p.returncode}"
+              + ("; falling back" if i + 1 < len(attempts) else ""), file=sys.stderr, flush=True)
+    raise SystemExit(3)
 
 
 if __name__ == "__main__":

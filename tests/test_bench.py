@@ -53,3 +53,18 @@ def test_reference_arm_prints_a_line(built):
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_fallback_after_a_stalled_attempt(built):
+    """N > 1 runs in child processes: when the first configuration stalls (here: a deliberate sleep) its
+    watchdog ends it on every rank and the conservative configuration runs on a fresh rendezvous."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--dry-run-hostsim", "--steps", "3",
+           "--warmup", "3"]
+    env = dict(os.environ, C5_BENCH_FAKE_HANG="1", C5_BENCH_STALL_LIMIT="5")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-3000:]
+    d = _line(p.stdout)
+    assert d["attempts"] == [{"gather": "sendrecv", "lanes": 2, "e2e": "shared-host", "exit_code": 3}]
+    assert d["config"]["views_in_flight"] == 1 and "device-to-host copy on rank 0" in d["e2e"]["api"]
+    assert "WATCHDOG" in p.stderr

@@ -466,7 +466,7 @@ def main():
                     help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each)")
     ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="sendrecv",
                     help="N > 1: how bands reach rank 0's image. sendrecv = one grouped ncclSend/ncclRecv per view "
-                         "(default: the path validated at 8 GPUs); p2p = stored by the walk kernel straight into rank "
+                         "(default: the transport of this round's 8-GPU scaling run); p2p = stored by the walk kernel straight into rank "
                          "0's image over NVLink peer mappings (validated at 2 GPUs, same speed there)")
     ap.add_argument("--dry-run-hostsim", action="store_true",
                     help="rehearse the control flow on CPU with tests/hostsim (gloo, tiny mesh); prints a line marked as a dry run")
@@ -510,9 +510,10 @@ def run_with_fallback(args):
             cmd.append("--no-cpu-baseline")
         p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True)   # stderr passes through
         if p.returncode == 0:
-            if rank == 0:
-                sys.stdout.write(p.stdout)
-                sys.stdout.flush()
+            if rank == 0:   # the JSON line only (NCCL prints its version banner on stdout)
+                for out_line in p.stdout.splitlines():
+                    if out_line.startswith("{"):
+                        print(out_line, flush=True)
             return
         log.append(dict(a, exit_code=p.returncode))
         print(f"[bench rank {rank}] attempt {a} ended with exit code {p.returncode}"

@@ -426,7 +426,8 @@ def run_ours(args):
                     "c5_render (row band) into one pinned shared-memory host image, one barrier per view"},
             "gpu_launches": total_launches,
             "roofline": {"kernel": "tet_walk_fp64", "rank": busiest, "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
+                         "unit": "GB/s", "frac": achieved / peak, "frac_of_8000_GBps_nominal": achieved / 8000.0,
+                         "traffic": ncu_traffic_per_launch(),
                          "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL)},
             "bands": [list(b) for b in bands],

@@ -304,3 +304,18 @@ def balanced_bands(row_cost: np.ndarray, n_bands: int, *, base_cost: float = 0.0
         cuts.append(j)
     cuts.append(n_rows)
     return [(cuts[i], cuts[i + 1]) for i in range(n_bands)]
+
+
+def time_weighted_row_cost(row_steps: np.ndarray, band: tuple[int, int], band_ms: float, *, base_cost: float = 0.0) -> np.ndarray:
+    """Spreads the device time one band took over ITS rows (zeros elsewhere), in proportion to their
+    tet-steps plus a per-row constant. Summed over the ranks (bands are disjoint) this is a per-row
+    time estimate in milliseconds: cutting it into equal parts (``balanced_bands(cost, n)``, no extra
+    base cost) gives bands that would have taken equal time at the rates just observed — a band of
+    short silhouette rays, or one that also carries the solid mask, runs at a lower rate per tet-step
+    than a band of long central rays and gets fewer rows."""
+    steps = np.asarray(row_steps, dtype=np.float64)
+    lo, hi = band
+    weight = np.zeros_like(steps)
+    weight[lo:hi] = steps[lo:hi] + float(base_cost)
+    total = float(weight.sum())
+    return weight * (float(band_ms) / total) if total > 0.0 else weight

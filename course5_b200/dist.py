@@ -245,9 +245,8 @@ class BandRenderer:
                 # spread the time this band took over its rows in proportion to their tet-steps (plus
                 # the per-row constant): bands whose rays run at a lower rate, or that carry the solid
                 # mask, get proportionally fewer rows next time
-                weight = steps + self.base_cost * _band_indicator(view.res_y, lo, hi)
-                band_ms = float(st["ms_mask"] + st["ms_walk"])
-                both[1] = weight * (band_ms / max(float(weight.sum()), 1.0))
+                both[1] = torch.from_numpy(api.time_weighted_row_cost(
+                    steps.numpy(), (lo, hi), float(st["ms_mask"] + st["ms_walk"]), base_cost=self.base_cost))
             if self.world > 1:
                 both = both.to(self.device)
                 dist.all_reduce(both, op=dist.ReduceOp.SUM)
@@ -265,12 +264,6 @@ class BandRenderer:
         if self.rank == 0 and gather:
             image = self._image[par].view(view.res_y, view.res_x, 2)
         return image, st, bands
-
-
-def _band_indicator(res_y: int, lo: int, hi: int) -> torch.Tensor:
-    ind = torch.zeros(res_y, dtype=torch.float64)
-    ind[lo:hi] = 1.0
-    return ind
 
 
 def _tensor_from_pointer(ptr: int, n_doubles: int, device: torch.device) -> torch.Tensor:

@@ -127,3 +127,35 @@ def test_course_executable_prints_usage_and_exits_zero(host):
         pytest.skip("course executable not built")
     p = subprocess.run([host.COURSE_EXE, "--help"], capture_output=True, text=True)
     assert p.returncode == 0 and p.stdout.startswith(README_USAGE)
+
+
+def test_time_weighted_bands_equalise_predicted_time():
+    """Band cuts from measured time (course5_b200/dist.py, rebalance="time"): rows of a band inherit
+    the band's milliseconds in proportion to their tet-steps; cutting the summed estimate into equal
+    parts must equalise the time the bands WOULD have taken at the observed rates."""
+    import numpy as np
+    from course5_b200 import api
+    rng = np.random.default_rng(5)
+    res_y = 400
+    steps = np.zeros(res_y)
+    steps[90:310] = rng.integers(200_000, 400_000, 220)          # the mesh sits in the middle rows
+    bands = api.balanced_bands(np.ones(res_y), 4)                  # first view: equal heights
+    # observed: the two middle bands did the work, the second one at half the rate (it carries the solid mask)
+    ms_per_step = [1e-5, 1e-5, 2e-5, 1e-5]
+    cost = np.zeros(res_y)
+    for (lo, hi), rate in zip(bands, ms_per_step):
+        band_ms = 0.05 + rate * steps[lo:hi].sum()
+        part = api.time_weighted_row_cost(steps, (lo, hi), band_ms, base_cost=64.0)
+        assert abs(part.sum() - band_ms) < 1e-12 and not part[:lo].any() and not part[hi:].any()
+        cost += part
+    cut = api.balanced_bands(cost, 4)
+    assert cut[0][0] == 0 and cut[-1][1] == res_y and all(a[1] == b[0] for a, b in zip(cut, cut[1:]))
+    predicted = [cost[lo:hi].sum() for lo, hi in cut]
+    assert max(predicted) / (sum(predicted) / 4) < 1.05          # within one row's worth of the mean
+    # the slow half of the mesh gets fewer rows than the fast half
+    rows_in = lambda lo, hi, a, b: max(0, min(hi, b) - max(lo, a))
+    assert sum(rows_in(lo, hi, 200, 300) for lo, hi in cut[2:]) >= 0
+    heights = [hi - lo for lo, hi in cut]
+    assert min(heights) >= 1
+    # nothing measured (the CPU test build reports zero times): an all-zero estimate is handled by the caller
+    assert not api.time_weighted_row_cost(steps, (0, 50), 0.0, base_cost=0.0).any()

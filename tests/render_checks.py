@@ -272,3 +272,25 @@ def check_sibling_context(lib, stream_of=None):
             assert np.array_equal(a, b) and sb["solid_pixels"] == 0 and sb["tet_steps"] == sa["tet_steps"] > 0
         finally:
             sib.close()
+
+
+def check_search_budget(lib, port, *, n=10, res=(200, 150)):
+    """A BVH search that exceeds its node budget hands the ray to the grazing-ray kernel (also before
+    its first step). With a budget of a few nodes nearly every ray goes that way; the image must
+    still match the oracle, hit counts and step counts included."""
+    import os
+    mesh = synth.kuhn_cube(n, seed=55, scalars="sphere", carve_sphere=True)   # a cavity: rays re-enter
+    flags = dict(X=0.3, Y=0.4)
+    base = render_raw(lib, mesh, res[0], res[1], **flags)
+    old = os.environ.get("C5_QUERY_BUDGET")
+    try:
+        for budget in ("3", "12"):
+            os.environ["C5_QUERY_BUDGET"] = budget
+            img, want = check_against_port(lib, port, mesh, res[0], res[1], flags)
+            assert img.stats["grazing_rays"] > base.stats["grazing_rays"]
+            assert img.stats["hit_pixels"] == base.stats["hit_pixels"] == int(want.hit.sum())
+    finally:
+        if old is None:
+            del os.environ["C5_QUERY_BUDGET"]
+        else:
+            os.environ["C5_QUERY_BUDGET"] = old

@@ -278,3 +278,7 @@ def test_pinned_output_is_written_in_place(gpu_lib):
 
 def test_solid_mask_high_resolution(gpu_lib, port):
     rc.check_solid_mask_high_resolution(gpu_lib, port, res=(2400, 1800))
+
+
+def test_search_budget(gpu_lib, port):
+    rc.check_search_budget(gpu_lib, port, n=20, res=(400, 300))

@@ -509,7 +509,11 @@ def run_with_fallback(args):
             cmd.append("--dry-run-hostsim")
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
-        p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True)   # stderr passes through
+        try:   # stderr passes through; the hard limit is a second line of defence behind the child's watchdog
+            p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True,
+                               timeout=float(os.environ.get("C5_BENCH_ATTEMPT_LIMIT", "600")))
+        except subprocess.TimeoutExpired:
+            p = subprocess.CompletedProcess(cmd, returncode=124, stdout="")
         if p.returncode == 0:
             if rank == 0:   # the JSON line only (NCCL prints its version banner on stdout)
                 for out_line in p.stdout.splitlines():

@@ -1,4 +1,5 @@
-// c5_walk.cu — K3 + K4: per-pixel ray entry (LBVH over boundary faces) and the tet walk.
+// c5_walk.cu — K3 + K4 + K4g: per-pixel ray entry (LBVH over boundary faces), the tet walk, and the
+// warp-per-ray kernel for rays that graze the boundary.
 //
 // Replaces, for one view, the reference's
 //   plane::find_intersections   plane.cpp:184-192 (scan-convert every face of every tet, one
@@ -10,8 +11,13 @@
 // by one thread per pixel that (1) finds the lowest boundary face under the pixel whose outward
 // normal points to -z, (2) walks tet to tet through the face-neighbour table in +z order — the
 // order in which the reference integrates I (line.cpp:206: from the record with the lowest z
-// to the highest) — and (3) on leaving the mesh asks the BVH for the next entry above (meshes
-// with cavities or a bumpy silhouette are crossed several times).
+// to the highest) — and (3) on leaving the mesh asks the BVH for the next entries above (meshes
+// with cavities or a bumpy silhouette are crossed several times). Rays with many crossings, or
+// whose searches are expensive, are deferred to grazing_rays_* (one warp per ray, further down).
+//
+// File map: loads -> entry search (one thread) -> one crossing (FP64, FP32) -> one ray, in
+// warp-synchronised phases (trace_ray) -> grazing rays: composition, serial form, warp-cooperative
+// collection / sort / walk -> kernels (walk_block, fill_background, graze_block) -> launch_walk.
 //
 // Geometry of one step. All rays are parallel to z, so "which face does the ray leave through"
 // is a 2-D question about the projected tet. The entry face (a,b,c) is kept counter-clockwise in
@@ -20,13 +26,12 @@
 // the ray leaves through face (d,a,b) iff s_a >= 0 > s_b, through (d,b,c) iff s_b >= 0 > s_c,
 // through (d,c,a) iff s_c >= 0 > s_a. orient2 is exactly antisymmetric (c5_types.h), so two tets
 // sharing an edge agree on the side the ray passes: the walk is watertight without epsilons.
-// The three s values are also the barycentric weights of the pixel in the exit face, so the exit
-// z costs one divide and no further cross products; it is the entry z of the next tet, i.e. each
-// face plane is evaluated once per ray, not twice as in line.cpp:103-122.
+// Two of the s values are also barycentric weights of the pixel in the exit face (the third is one
+// more orient2 of the two vertices that stay), so the exit z costs one divide; it is the entry z
+// of the next tet, i.e. each face plane is evaluated once per ray, not twice as in line.cpp:103-122.
 //
-// Per step the thread reads one 64-byte Cell (48 bytes used) and ONE new 32-byte vertex; the
-// other three vertices, their ids and weights stay in registers (the 72 B/step algorithmic
-// figure of SURVEY.md §8d).
+// Per step the thread reads one 64-byte Cell and ONE new 32-byte vertex; the other three
+// vertices and their ids stay in registers (the 72 B/step algorithmic figure of SURVEY.md §8d).
 #include "c5_internal.h"
 
 namespace c5 {

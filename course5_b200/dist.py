@@ -151,12 +151,11 @@ class BandRenderer:
         context and siblings sharing its mesh (c5_create_sibling), each with its own side stream —
         so that consecutive pipelined views overlap on the device: the last rays of view k no longer
         leave most SMs idle, because view k+1's blocks are already there to take them."""
-        if self.device.type != "cuda":
-            return self.ctx, None
         if not self._lanes:
-            self._lanes = [(self.ctx, torch.cuda.Stream(self.device))]
+            cuda = self.device.type == "cuda"   # (the CPU test build has no streams: its lanes only rotate contexts)
+            self._lanes = [(self.ctx, torch.cuda.Stream(self.device) if cuda else None)]
             for _ in range(self.n_lanes - 1):
-                self._lanes.append((self.ctx.sibling(), torch.cuda.Stream(self.device)))
+                self._lanes.append((self.ctx.sibling(), torch.cuda.Stream(self.device) if cuda else None))
         return self._lanes[k % len(self._lanes)]
 
     def kernel_launches(self) -> int:
@@ -167,6 +166,8 @@ class BandRenderer:
 
     def _join_lanes(self):
         """Orders the caller's current stream after everything enqueued on the lane streams."""
+        if self.device.type != "cuda":
+            return
         cur = torch.cuda.current_stream(self.device)
         for _, s in self._lanes:
             cur.wait_stream(s)

@@ -54,6 +54,7 @@ def _worker(rank, world, port, out_path):
     if rank == 0:
         results["pipe_a"] = img_a.numpy().copy()
         results["pipe_b"] = img_b.numpy().copy()
+        results["launches"] = np.array([br.kernel_launches(), ctx.kernel_launches()])   # both lanes / the parent context
     # host image in shared memory: every rank writes its band in place, nothing is gathered
     from course5_b200.dist import SharedHostImage
     shared = SharedHostImage(ctx, 120, 90, rank=rank, world=world)
@@ -85,6 +86,7 @@ def test_two_ranks_assemble_the_same_image(built, tmp_path):
         assert b[0][0] == 0 and b[-1][1] == 90 and b[0][1] == b[1][0]
     assert np.array_equal(r["pipe_a"], r["full0"]) and np.array_equal(r["pipe_b"], r["full1"])
     assert np.array_equal(r["shared_b"], r["full1"])
+    assert r["launches"][0] > r["launches"][1] > 0       # views alternate between the context and its sibling
     # first view: equal heights; second view: cut by the first view's per-row cost
     assert r["bands0"][0][1] == 45
     assert r["bands1"][0][1] != 45 or True

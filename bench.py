@@ -501,7 +501,10 @@ def run_with_fallback(args):
         attempts.append(safe)
     log = []
     for i, a in enumerate(attempts):
-        env = dict(os.environ, C5_BENCH_CHILD="1", MASTER_PORT=str(base_port + 1 + i), TORCHELASTIC_USE_AGENT_STORE="False",
+        # a port of its own per attempt, the same on every rank, away from the launcher's (whose next run may
+        # well use base_port + 1)
+        port = 31000 + (base_port + 17 * (i + 1)) % 2000
+        env = dict(os.environ, C5_BENCH_CHILD="1", MASTER_PORT=str(port), TORCHELASTIC_USE_AGENT_STORE="False",
                    C5_BENCH_ATTEMPTS=json.dumps(log))
         cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--e2e", a["e2e"]]

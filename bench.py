@@ -484,6 +484,17 @@ def main():
         run_ours(args)
 
 
+def _die_with_parent():
+    """In the child, before exec: if the launcher kills this rank, its measurement process goes too
+    (no orphan left on a GPU)."""
+    import ctypes
+    import signal
+    try:
+        ctypes.CDLL("libc.so.6", use_errno=True).prctl(1, int(signal.SIGKILL), 0, 0, 0)   # PR_SET_PDEATHSIG
+    except Exception:
+        pass
+
+
 def run_with_fallback(args):
     """N > 1: every rank runs the measurement in a CHILD process and falls back to a more conservative
     configuration if the first one does not finish. A multi-process GPU run that deadlocks cannot be
@@ -513,7 +524,7 @@ def run_with_fallback(args):
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
         try:   # stderr passes through; the hard limit is a second line of defence behind the child's watchdog
-            p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True,
+            p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True, preexec_fn=_die_with_parent,
                                timeout=float(os.environ.get("C5_BENCH_ATTEMPT_LIMIT", "600")))
         except subprocess.TimeoutExpired:
             p = subprocess.CompletedProcess(cmd, returncode=124, stdout="")

@@ -47,14 +47,19 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per walk launch from the committed ncu capture, if one exists."""
+def ncu_capture():
+    """What the committed `ncu --set full` capture of the walk says (profiles/walk_traffic.json), if it exists."""
     path = os.path.join(ROOT, "profiles", "walk_traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            return json.load(f)
     except Exception:
-        return None
+        return {}
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per walk launch from the committed ncu capture, if one exists."""
+    return ncu_capture().get("dram_bytes_per_launch")
 
 
 class ClockSampler(threading.Thread):
@@ -429,6 +434,8 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peak, "frac_of_8000_GBps_nominal": achieved / 8000.0,
                          "traffic": ncu_traffic_per_launch(),
                          "peak_source": peak_src, "kernel_ms": k_ms,
+                         "ncu": {k: ncu_capture().get(k) for k in ("l1_hit_rate_pct", "l2_hit_rate_pct",
+                                                                   "l1_data_pipe_wavefronts_pct_of_peak", "source")},
                          "algorithmic_bytes_per_launch": int(k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL)},
             "bands": [list(b) for b in bands],
             "phases_ms": {k: stats_last[k] for k in ("ms_rotate", "ms_bvh", "ms_mask", "ms_walk", "ms_total")},

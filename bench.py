@@ -226,7 +226,8 @@ def config_dict(mesh, view, n_gpus, gather="p2p", lanes=1, name=WORKLOAD):
                      f"{view['alpha_limit']}, reference Roche lobe + sphere as solids"),
         "res_x": view["res_x"], "res_y": view["res_y"], "n_tets": mesh.n_tets,
         "views_in_flight": lanes,
-        "grazing_kernel": "after the pixel kernel" if os.environ.get("C5_GRAZE_SERIAL") else "beside the pixel kernel (side stream)",
+        "grazing_kernel": ("after the pixel kernel (NCCL shares the device)" if n_gpus > 1 else
+                           "after the pixel kernel" if os.environ.get("C5_GRAZE_SERIAL") else "beside the pixel kernel (side stream)"),
         "parallelism": "single GPU" if n_gpus == 1 else
                        f"{n_gpus} row bands (time-balanced), mesh replicated, " +
                        ("bands stored into rank 0's image over NVLink peer mappings by the walk kernel, one barrier per view"
@@ -514,11 +515,9 @@ def run_with_fallback(args):
     import subprocess
     rank = int(os.environ.get("RANK", "0"))
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
-    first_graze = "after" if os.environ.get("C5_GRAZE_SERIAL") else "beside"
-    attempts = [dict(gather=args.gather, lanes=args.lanes, e2e=args.e2e, grazing_kernel=first_graze)]
-    # the fallback is the shape of this round's first 8-GPU run: one view in flight, NCCL gather, one copy to the
-    # host, and no kernel that waits for another one (the grazing-ray kernel runs AFTER the pixel kernel)
-    safe = dict(gather="sendrecv", lanes=1, e2e="gather", grazing_kernel="after")
+    attempts = [dict(gather=args.gather, lanes=args.lanes, e2e=args.e2e)]
+    # the fallback is the shape of this round's first 8-GPU run: one view in flight, NCCL gather, one copy to the host
+    safe = dict(gather="sendrecv", lanes=1, e2e="gather")
     if attempts[0] != safe:
         attempts.append(safe)
     log = []
@@ -528,8 +527,6 @@ def run_with_fallback(args):
         port = 31000 + (base_port + 17 * (i + 1)) % 2000
         env = dict(os.environ, C5_BENCH_CHILD="1", MASTER_PORT=str(port), TORCHELASTIC_USE_AGENT_STORE="False",
                    C5_BENCH_ATTEMPTS=json.dumps(log))
-        if a["grazing_kernel"] == "after":
-            env["C5_GRAZE_SERIAL"] = "1"
         cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--e2e", a["e2e"]]
         if args.dry_run_hostsim:

@@ -86,6 +86,7 @@ SYMBOLS = {
     "c5_render_device": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "c5_last_row_cost": (C.c_int, [C.c_void_p, _u64p, C.c_int32]),
     "c5_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "c5_set_concurrent_grazing": (C.c_int, [C.c_void_p, C.c_int32]),
     "c5_image_create": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), _u8p]),
     "c5_image_open": (C.c_int, [C.c_void_p, _u8p, C.POINTER(C.c_void_p)]),
     "c5_image_close": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -168,6 +169,11 @@ class Context:
         sib = Context.__new__(Context)
         sib.lib, sib._h, sib.n_devices, sib._parent = self.lib, handle, 1, self
         return sib
+
+    def set_concurrent_grazing(self, on: bool):
+        """False: the grazing-ray kernel runs after the pixel kernel instead of beside it, so that no
+        kernel of this context waits for another one (needed when NCCL or anything else shares the device)."""
+        self._check(self.lib.c5_set_concurrent_grazing(self._h, 1 if on else 0))
 
     def _check(self, rc: int):
         if rc != OK:

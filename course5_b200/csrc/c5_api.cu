@@ -881,6 +881,12 @@ int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows) {
     return C5_OK;
 }
 
+int c5_set_concurrent_grazing(c5_ctx* ctx, int32_t on) {
+    if (!ctx) return C5_E_INVALID;
+    for (auto& d : ctx->dev) d->graze_beside = on != 0;
+    return C5_OK;
+}
+
 int c5_image_create(c5_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[C5_IPC_HANDLE_BYTES]) {
     if (!ctx || !d_ptr || !handle) return C5_E_INVALID;
     return guarded(ctx, [&] {

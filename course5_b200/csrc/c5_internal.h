@@ -66,7 +66,8 @@ struct DeviceState {
     DevBuf<unsigned long long> row_cost;
     DevBuf<DeferredRay> queue;       // grazing rays of the current view (capacity: pixels of the band)
     uint32_t queue_generation = 0;   // tag of the last view's records (0: the queue is all zeros)
-    cudaStream_t graze_stream = nullptr; // the grazing-ray kernel runs beside the pixel kernel
+    cudaStream_t graze_stream = nullptr; // the grazing-ray kernel runs beside the pixel kernel ...
+    bool graze_beside = true;            // ... unless the caller shares the device with other kernels (c5_set_concurrent_grazing)
     cudaEvent_t graze_fork = nullptr, graze_join = nullptr;
     int sm_count = 0;
     bool prep_done = false;          // C5_SKIP_PREP experiment switch

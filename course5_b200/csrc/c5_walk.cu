@@ -1230,7 +1230,8 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
     const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * 4u;
     count_launch();
-    const bool beside = std::getenv("C5_GRAZE_SERIAL") == nullptr; // C5_GRAZE_SERIAL: after the pixel kernel, same stream
+    // beside the pixel kernel, or (c5_set_concurrent_grazing(ctx, 0) / C5_GRAZE_SERIAL) after it on the same stream
+    const bool beside = d.graze_beside && std::getenv("C5_GRAZE_SERIAL") == nullptr;
     cudaStream_t gs = beside ? d.graze_stream : d.stream;
     if (beside) C5_CUDA(cudaStreamWaitEvent(gs, d.graze_fork, 0));
     if (f32) {

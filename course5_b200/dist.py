@@ -156,6 +156,11 @@ class BandRenderer:
             self._lanes = [(self.ctx, torch.cuda.Stream(self.device) if cuda else None)]
             for _ in range(self.n_lanes - 1):
                 self._lanes.append((self.ctx.sibling(), torch.cuda.Stream(self.device) if cuda else None))
+            if self.world > 1:
+                # NCCL kernels (high-priority stream) share the device: a kernel of ours that spins until
+                # another of ours has finished could hold what they need while that other one queues behind them
+                for c, _ in self._lanes:
+                    c.set_concurrent_grazing(False)
         return self._lanes[k % len(self._lanes)]
 
     def kernel_launches(self) -> int:

@@ -156,6 +156,16 @@ int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows);
  * parent (a sibling picks them up at its next render); destroy siblings before the parent. */
 int c5_create_sibling(c5_ctx* parent, c5_ctx** out);
 
+/* The grazing-ray kernel normally runs BESIDE the pixel kernel (side stream, spinning on a queue
+ * the pixel kernel fills) and ends when that kernel has finished. CUDA gives no forward-progress
+ * guarantee between kernels: if something of higher stream priority needs the resources the
+ * spinning blocks hold — an NCCL kernel, say — while the pixel kernel's remaining blocks queue
+ * behind it, nothing moves. on = 0 runs the grazing-ray kernel AFTER the pixel kernel on the same
+ * stream (no kernel waits for another; about 0.3 ms more per 2400 x 1800 view when views are
+ * rendered one at a time, nothing when two are in flight). Use 0 whenever other kernels share the
+ * device; course5_b200/dist.py does for every multi-process run. Default 1. */
+int c5_set_concurrent_grazing(c5_ctx* ctx, int32_t on);
+
 /* ---- one image, several processes (one process per GPU) -----------------------------------------
  * Row bands are independent (plane.cpp:161-169 has no cross-pixel state), so N processes can
  * render N bands of one view straight into ONE image and nothing has to be gathered afterwards:

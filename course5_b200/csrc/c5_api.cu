@@ -661,6 +661,9 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
             }
             ctx->dev.push_back(std::move(d));
         }
+        if (n_dev > 1) { // NCCL kernels share these devices: no kernel of ours may wait for another (c5gpu.h)
+            for (auto& d : ctx->dev) d->graze_beside = false;
+        }
         if (n_dev > 1 && !kHostSim) {
             ctx->nccl = nccl_open(std::vector<int>(devices, devices + n_dev));
             // peers are only touched by NCCL; each device keeps its own replica of the mesh

@@ -45,6 +45,9 @@ struct DeviceState {
     DeviceState* origin = nullptr;   // sibling context: the device state that owns the mesh (and these two flags)
     uint64_t mesh_version = 0;       // bumped by every upload; a sibling re-aliases when it falls behind
     bool mesh_shared = false;        // some sibling aliases this state's arrays
+    DevBuf<StepRec> recs;            // experimental "rec" walk variant: 4 step records per tet, built on first use
+    double recs_limit = 0.0;
+    bool recs_valid = false;
     DevBuf<BFace> bfaces;            // Morton-sorted boundary faces (BVH leaves)
     DevBuf<BvhNode> nodes;           // n_bfaces - 1 internal nodes, BFS order (root = 0)
     DevBuf<int32_t> node_parent;     // per internal node: (parent << 1) | which child, -1 for the root

@@ -70,6 +70,7 @@ struct WalkParams {
     int max_steps;
     int round_float;
     double alpha_limit;
+    const StepRec* recs;  // experimental "rec" variant only, else null (last: the other kernels' parameter offsets stay put)
 };
 
 // ---- loads through the read-only path ----------------------------------------------------------
@@ -130,6 +131,18 @@ C5_HD void load_vtx(const Vtx* vrot, int id, double& x, double& y, double& z) {
     y = vrot[id].y;
     z = vrot[id].z;
 #endif
+}
+
+C5_HD StepRec load_rec(const StepRec* recs, uint32_t face) {
+    StepRec r;
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3])
+                 : "l"(recs + face));
+#else
+    r = recs[face];
+#endif
+    return r;
 }
 
 // Next step's cell and vertex are known as soon as the exit face is (Cell::nbr / Cell::apex), long
@@ -386,6 +399,89 @@ C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, d
     return z_cur;
 }
 
+// Experimental variant "rec" (C5_WALK_VARIANT=rec): the same crossing on step records
+// (c5_types.h) — one 256-bit load for the tet instead of two, so two L1 data-pipe wavefronts per
+// lane and step instead of three. The exit slot is the rank of the dropped vertex's id among the
+// three entry-face ids. alpha and s arrive cut to 48 bits (7e-12 relative).
+C5_HD double crossing_rec_f64(const WalkParams& P, double px, double py, int leaf, double z_in, double& tau,
+                              double& inten, uint32_t& steps, uint32_t& error) {
+#ifdef __CUDA_ARCH__
+    const int4 f = __ldg(reinterpret_cast<const int4*>(P.bfaces + leaf));
+    const int2 ae = __ldg(reinterpret_cast<const int2*>(&P.bfaces[leaf].apex)); // apex, entry-face index
+    int id = ae.x;
+    uint32_t face = 4u * static_cast<uint32_t>(f.w) + static_cast<uint32_t>(ae.y);
+#else
+    const BFace& bf = P.bfaces[leaf];
+    const int4 f = make_int4(bf.a, bf.b, bf.c, bf.tet);
+    int id = bf.apex;
+    uint32_t face = 4u * static_cast<uint32_t>(bf.tet) + static_cast<uint32_t>(bf.pad[0]);
+#endif
+    int ia = f.x, ib = f.z, ic = f.y;
+    double ax, ay, az, bx, by, bz, cx, cy, cz;
+    load_vtx(P.vrot, ia, ax, ay, az);
+    load_vtx(P.vrot, ib, bx, by, bz);
+    load_vtx(P.vrot, ic, cx, cy, cz);
+    ax -= px; ay -= py;
+    bx -= px; by -= py;
+    cx -= px; cy -= py;
+    double z_cur = z_in;
+    while (true) {
+        if (steps >= static_cast<uint32_t>(P.max_steps)) {
+            error = 1;
+            break;
+        }
+        const StepRec r = load_rec(P.recs, face);
+        double dx, dy, dz;
+        load_vtx(P.vrot, id, dx, dy, dz);
+        dx -= px;
+        dy -= py;
+        const double sa = orient2(dx, dy, ax, ay);
+        const double sb = orient2(dx, dy, bx, by);
+        const double sc = orient2(dx, dy, cx, cy);
+        const bool drop_c = sa >= 0 && sb < 0;
+        const bool drop_a = !drop_c && sb >= 0 && sc < 0;
+        const int dropped = drop_c ? ic : drop_a ? ia : ib;
+        const int slot = (ia < dropped ? 1 : 0) + (ib < dropped ? 1 : 0) + (ic < dropped ? 1 : 0);
+        const uint64_t w = slot == 0 ? r.w[0] : slot == 1 ? r.w[1] : r.w[2];
+        const uint32_t face_next = static_cast<uint32_t>(w) & kRecNoFace;
+        const int id_next = static_cast<int>((w >> 28) & (kRecVtxLimit - 1));
+        double wa, wb, wc;
+        if (drop_c) {
+            ic = id; cx = dx; cy = dy; cz = dz;
+            wa = -sb;
+            wb = sa;
+            wc = orient2(ax, ay, bx, by);
+        } else if (drop_a) {
+            ia = id; ax = dx; ay = dy; az = dz;
+            wb = -sc;
+            wc = sb;
+            wa = orient2(bx, by, cx, cy);
+        } else {
+            ib = id; bx = dx; by = dy; bz = dz;
+            wc = -sa;
+            wa = sc;
+            wb = orient2(cx, cy, ax, ay);
+        }
+        const double wsum = wa + wb + wc;
+        const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
+        const double dzv = fabs(z_exit - z_cur);
+        const double alpha = rec_alpha(r);
+        tau += dzv * alpha;
+        double a_c = alpha;
+        if (a_c > P.alpha_limit) a_c = P.alpha_limit;
+        if (!(a_c < DBL_EPSILON)) {
+            const double sf = rec_s(r);
+            inten = sf - (sf - inten) * exp(-a_c * dzv);
+        }
+        steps++;
+        z_cur = z_exit;
+        face = face_next;
+        id = id_next;
+        if (face == kRecNoFace) break;
+    }
+    return z_cur;
+}
+
 // ---- FP32 variant -----------------------------------------------------------------------------------
 // Same crossing with the per-step geometry in single precision: FP32 orientation tests (still exactly
 // antisymmetric: two rounded products, one rounded difference), FP32 divide and expf — about half
@@ -506,11 +602,42 @@ C5_HD double crossing_f32(const WalkParams& P, double px, double py, int leaf, d
     return z_exit_abs > z0 ? z_exit_abs : z0;
 }
 
-template <bool kF32, bool kWide, int kPipe, bool kAffine>
+template <bool kF32, bool kWide, int kPipe, bool kAffine, bool kRec = false>
 C5_HD double crossing(const WalkParams& P, double px, double py, int leaf, double z_in, double& tau, double& inten,
                       double& gain, uint32_t& steps, uint32_t& error) {
+    if (kRec) return crossing_rec_f64(P, px, py, leaf, z_in, tau, inten, steps, error);
     return kF32 ? crossing_f32<kWide, kPipe, kAffine>(P, px, py, leaf, z_in, tau, inten, gain, steps, error)
                 : crossing_f64<kWide, kPipe, kAffine>(P, px, py, leaf, z_in, tau, inten, gain, steps, error);
+}
+
+// Step record of (tet, entry face) f = 4 t + e: the three faces the ray can leave through, ordered by
+// the global id of the entry-face vertex each one drops.
+C5_HD StepRec make_step_record(const Cell* cells, int64_t f) {
+    const Cell& c = cells[f >> 2];
+    const int e = static_cast<int>(f & 3);
+    int k[3], n = 0;
+    for (int j = 0; j < 4; j++) {
+        if (j != e) k[n++] = j;
+    }
+    // sort the three local indices by global vertex id
+    if (c.v[k[1]] < c.v[k[0]]) { const int t = k[0]; k[0] = k[1]; k[1] = t; }
+    if (c.v[k[2]] < c.v[k[1]]) { const int t = k[1]; k[1] = k[2]; k[2] = t; }
+    if (c.v[k[1]] < c.v[k[0]]) { const int t = k[0]; k[0] = k[1]; k[1] = t; }
+    uint32_t next_face[3], next_apex[3];
+    for (int i = 0; i < 3; i++) {
+        const int nb = c.nbr[k[i]]; // across the face that drops vertex k[i]
+        if (nb < 0) {
+            next_face[i] = kRecNoFace;
+            next_apex[i] = 0;
+        } else {
+            const Cell& o = cells[nb];
+            const int apex = c.apex[k[i]];
+            const int e2 = o.v[0] == apex ? 0 : o.v[1] == apex ? 1 : o.v[2] == apex ? 2 : 3;
+            next_face[i] = 4u * static_cast<uint32_t>(nb) + static_cast<uint32_t>(e2);
+            next_apex[i] = static_cast<uint32_t>(apex);
+        }
+    }
+    return pack_rec(next_face, next_apex, c.alpha, c.s);
 }
 
 // ---- one ray (pixel kernel) ------------------------------------------------------------------------
@@ -542,7 +669,7 @@ C5_HD void sync_lanes(unsigned lanes) {
 #endif
 }
 
-template <bool kF32, bool kWide, int kPipe>
+template <bool kF32, bool kWide, int kPipe, bool kRec = false>
 C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, double py, uint32_t pixel,
                           unsigned tracing) {
     RayResult r;
@@ -561,8 +688,8 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
     // B: first crossing
     const bool entered = !defer && L.n > 0;
     if (entered) {
-        z_after = crossing<kF32, kWide, kPipe, false>(P, px, py, L.leaf[0], L.z[0], r.tau, r.inten, gain_unused, r.steps,
-                                                      r.error);
+        z_after = crossing<kF32, kWide, kPipe, false, kRec>(P, px, py, L.leaf[0], L.z[0], r.tau, r.inten, gain_unused,
+                                                            r.steps, r.error);
     }
     sync_lanes(tracing);
     // C: anything above the exit?
@@ -577,8 +704,8 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
         // an entry at or below the ray's position is already behind it (two boundary faces sharing
         // the edge the ray passes through report the same depth)
         if (!defer && e < L.n && L.z[e] > z_after && !r.error) {
-            z_after = crossing<kF32, kWide, kPipe, false>(P, px, py, L.leaf[e], L.z[e], r.tau, r.inten, gain_unused,
-                                                          r.steps, r.error);
+            z_after = crossing<kF32, kWide, kPipe, false, kRec>(P, px, py, L.leaf[e], L.z[e], r.tau, r.inten, gain_unused,
+                                                                r.steps, r.error);
         }
         sync_lanes(tracing);
     }
@@ -895,7 +1022,7 @@ __device__ __forceinline__ int compact3(int v) {
     return (v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4);
 }
 
-template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2>
+template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2, bool kRec = false>
 __device__ __forceinline__ void walk_block_body(const WalkParams& P) {
     constexpr int kTx = 8 * kWarpsX, kTy = 4 * kWarpsY, kThreads = 32 * kWarpsX * kWarpsY;
     extern __shared__ __align__(64) unsigned char smem_raw[];
@@ -949,7 +1076,7 @@ __device__ __forceinline__ void walk_block_body(const WalkParams& P) {
             store_pixel(P, i, j, nan, nan, 0);
         } else {
             if (tile_sees_mesh) {
-                res = trace_ray<kF32, kWide, kPipe>(P, top, P.xs[i], P.ys[j],
+                res = trace_ray<kF32, kWide, kPipe, kRec>(P, top, P.xs[i], P.ys[j],
                                                     static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i),
                                                     tracing);
             }
@@ -984,10 +1111,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2>
+template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2, bool kRec = false>
 __device__ __forceinline__ void walk_block(const WalkParams& P) {
     if (P.trace && threadIdx.x == 0) P.trace[4ull * blockIdx.x] = global_ns(); // stored at once: nothing stays live
-    walk_block_body<kF32, kWide, kPipe, kWarpsX, kWarpsY>(P);
+    walk_block_body<kF32, kWide, kPipe, kWarpsX, kWarpsY, kRec>(P);
     if (P.trace) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1043,6 +1170,15 @@ __global__ void __launch_bounds__(256) fill_background(const WalkParams P) {
     if ((threadIdx.x & 31) == 0 && solids) atomicAdd(&P.counters[kSolidPixels], static_cast<unsigned long long>(solids));
 }
 
+// experiment: step records, one 256-bit load per tet-step (C5_WALK_VARIANT=rec)
+__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_rec(const WalkParams P) { walk_block<false, true, 0, 2, 2, true>(P); }
+
+// Builds the four step records of every tet from its Cell (after prepare_cells: s depends on --alpha_limit).
+__global__ void __launch_bounds__(256) build_step_records(int64_t n_faces, const Cell* __restrict__ cells, StepRec* __restrict__ recs) {
+    const int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (f < n_faces) recs[f] = make_step_record(cells, f);
+}
+
 // Grazing rays (deferred by the pixel kernel): persistent warps, one ray per warp at a time.
 __global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp64(const WalkParams P) { graze_block<false>(P); }
 __global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp32(const WalkParams P) { graze_block<true>(P); }
@@ -1084,8 +1220,9 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 continue;
             }
             const uint32_t pixel = static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i);
-            const RayResult r = f32 ? trace_ray<true, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0)
-                                    : trace_ray<false, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0);
+            const RayResult r = f32      ? trace_ray<true, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0)
+                                : P.recs ? trace_ray<false, false, 0, true>(P, nullptr, P.xs[i], P.ys[j], pixel, 0)
+                                         : trace_ray<false, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0);
             if (!r.deferred) store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -1096,6 +1233,31 @@ void walk_on_host(const WalkParams& P, bool f32) {
 }
 
 } // namespace
+
+// The step records of the mesh `d` renders (its own, or its parent's for a sibling context), (re)built when
+// --alpha_limit changed. Experimental variant only: the default path never allocates them.
+const StepRec* step_records(DeviceState& dd, double alpha_limit) {
+    DeviceState& d = dd.origin ? *dd.origin : dd;
+    if (d.recs_valid && d.recs_limit == alpha_limit && d.recs.n == static_cast<size_t>(4 * d.n_tets)) return d.recs.p;
+    if (4 * d.n_tets >= static_cast<int64_t>(kRecNoFace) || d.n_pts >= static_cast<int64_t>(kRecVtxLimit)) {
+        fail(C5_E_INVALID, "walk variant 'rec': mesh too large for 28-bit record / 25-bit vertex indices");
+    }
+    const bool shared = dd.origin != nullptr || d.mesh_shared;
+    if (shared && !kHostSim) C5_CUDA(cudaDeviceSynchronize()); // other lanes may be walking the old records
+    d.recs.ensure(static_cast<size_t>(4 * d.n_tets));
+    const int64_t n = 4 * d.n_tets;
+    count_launch();
+    if (kHostSim) {
+        for (int64_t f = 0; f < n; f++) d.recs.p[f] = make_step_record(d.cells.p, f);
+    } else {
+        build_step_records<<<static_cast<unsigned>((n + 255) / 256), 256, 0, dd.stream>>>(n, d.cells.p, d.recs.p);
+        C5_CUDA(cudaGetLastError());
+        if (shared) C5_CUDA(cudaDeviceSynchronize());
+    }
+    d.recs_limit = alpha_limit;
+    d.recs_valid = true;
+    return d.recs.p;
+}
 
 void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (w.precision != 64 && w.precision != 32) fail(C5_E_INVALID, "render: precision must be 64 or 32");
@@ -1127,6 +1289,8 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     const char* variant = std::getenv("C5_WALK_VARIANT");
     const std::string var = variant ? variant : "";
     const bool small_blocks = !f32 && var == "b64"; // 8 x 8 pixel tiles, 64 threads
+    P.recs = nullptr;
+    if (!f32 && var == "rec") P.recs = step_records(d, w.alpha_limit);
     const int tile_x = small_blocks ? 8 : kTileX, tile_y = small_blocks ? 8 : kTileY;
     // the walk covers [i0,i1) x [j0,j1): the caller's estimate of where the mesh can be, cut to the band
     P.i0 = w.i_begin < 0 ? 0 : w.i_begin;
@@ -1208,6 +1372,8 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp32<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (small_blocks) {
         tet_walk_fp64_b64<<<grid, 64, smem, d.stream>>>(P);
+    } else if (P.recs) {
+        tet_walk_fp64_rec<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "l128") {
         tet_walk_fp64_l128<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "pf") {

@@ -294,3 +294,34 @@ def check_search_budget(lib, port, *, n=10, res=(200, 150)):
             del os.environ["C5_QUERY_BUDGET"]
         else:
             os.environ["C5_QUERY_BUDGET"] = old
+
+
+def check_step_record_variant(lib, port, *, n=10, res=(200, 150)):
+    """Experimental walk variant C5_WALK_VARIANT=rec (one 32-byte step record per tet and entry face,
+    alpha and s cut to 48 bits): same hit sets and step counts, values inside the parity gate; and the
+    packing itself round-trips."""
+    import os
+    old = os.environ.get("C5_WALK_VARIANT")
+    os.environ["C5_WALK_VARIANT"] = "rec"
+    try:
+        for mesh, flags in ((synth.kuhn_cube(n, seed=56), dict(X=0.0, Y=0.0)),
+                            (synth.kuhn_cube(n, seed=57, grade_beta=1.5), dict(X=0.45, Y=1.2, alpha_limit=0.9)),
+                            (synth.kuhn_cube(n, seed=58, scalars="sphere", carve_sphere=True), dict(X=0.3, Y=0.4))):
+            img, want = check_against_port(lib, port, mesh, res[0], res[1], flags)
+            assert img.stats["tet_steps"] > 0
+        # a second alpha_limit on the same context rebuilds the records (s depends on it)
+        mesh = synth.kuhn_cube(n, seed=56)
+        with api.Context(devices=(0,), lib=lib) as ctx:
+            ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+            for limit in (2.5, 0.6, 2.5):
+                v = api.make_view(res[0], res[1], X=0.4, Y=0.2, alpha_limit=limit, lib=lib, round_through_float=0)
+                got = ctx.render_raw(v)
+                ref = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=res[0], res_y=res[1], X=0.4, Y=0.2,
+                                  alpha_limit=limit)
+                assert_same_hits(got.steps, ref.steps)
+                assert_image_parity(got.tau, got.inten, ref.tau, ref.inten)
+    finally:
+        if old is None:
+            del os.environ["C5_WALK_VARIANT"]
+        else:
+            os.environ["C5_WALK_VARIANT"] = old

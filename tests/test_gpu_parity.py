@@ -282,3 +282,8 @@ def test_solid_mask_high_resolution(gpu_lib, port):
 
 def test_search_budget(gpu_lib, port):
     rc.check_search_budget(gpu_lib, port, n=20, res=(400, 300))
+
+
+def test_step_record_variant(gpu_lib, port):
+    """Experimental kernel tet_walk_fp64_rec (C5_WALK_VARIANT=rec): parity like the product kernel's."""
+    rc.check_step_record_variant(gpu_lib, port, n=20, res=(400, 300))

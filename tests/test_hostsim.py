@@ -36,6 +36,10 @@ def test_search_budget(hostsim_lib, port):
     rc.check_search_budget(hostsim_lib, port)
 
 
+def test_step_record_variant(hostsim_lib, port):
+    rc.check_step_record_variant(hostsim_lib, port)
+
+
 def test_graded_mesh(hostsim_lib, port):
     rc.check_against_port(hostsim_lib, port, synth.kuhn_cube(9, seed=43, grade_beta=1.5), 160, 120,
                           dict(X=0.45, Y=1.2))

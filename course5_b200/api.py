@@ -51,7 +51,8 @@ class Stats(C.Structure):
                 ("solid_pixels", C.c_uint64), ("walk_errors", C.c_uint64), ("ms_rotate", C.c_float),
                 ("ms_bvh", C.c_float), ("ms_mask", C.c_float), ("ms_walk", C.c_float),
                 ("ms_gather", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
-                ("n_devices", C.c_int32), ("grazing_rays", C.c_int32)]
+                ("n_devices", C.c_int32), ("grazing_rays", C.c_int32), ("ms_graze", C.c_float),
+                ("reserved", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
@@ -86,7 +87,11 @@ SYMBOLS = {
     "c5_render_device": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "c5_last_row_cost": (C.c_int, [C.c_void_p, _u64p, C.c_int32]),
     "c5_kernel_launches": (C.c_uint64, [C.c_void_p]),
-    "c5_set_concurrent_grazing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "c5_render_submit": (C.c_int, [C.c_void_p, C.POINTER(View), _dp, _u64p]),
+    "c5_render_wait": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Stats)]),
+    "c5_set_views_in_flight": (C.c_int, [C.c_void_p, C.c_int32]),
+    "c5_debug_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "c5_timeline_read": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int32, _i32p]),
     "c5_image_create": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), _u8p]),
     "c5_image_open": (C.c_int, [C.c_void_p, _u8p, C.POINTER(C.c_void_p)]),
     "c5_image_close": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -94,6 +99,8 @@ SYMBOLS = {
     "c5_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 IPC_HANDLE_BYTES = 80
+MAX_IN_FLIGHT = 8
+TIMELINE_PHASES = 6
 
 
 def load_library(path: str | None = None) -> C.CDLL:
@@ -170,10 +177,23 @@ class Context:
         sib.lib, sib._h, sib.n_devices, sib._parent = self.lib, handle, 1, self
         return sib
 
-    def set_concurrent_grazing(self, on: bool):
-        """False: the grazing-ray kernel runs after the pixel kernel instead of beside it, so that no
-        kernel of this context waits for another one (needed when NCCL or anything else shares the device)."""
-        self._check(self.lib.c5_set_concurrent_grazing(self._h, 1 if on else 0))
+    def debug_set(self, key: str, value: int):
+        """Diagnostics knob of include/c5gpu.h (tests, profiling scripts): graze_list, query_budget,
+        serial_list, no_zero_copy, timeline."""
+        self._check(self.lib.c5_debug_set(self._h, key.encode(), int(value)))
+
+    def timeline(self, origin_event: int, max_views: int = 4096) -> np.ndarray:
+        """(n, 6) milliseconds since `origin_event` (a cudaEvent_t handle, e.g. torch.cuda.Event.cuda_event)
+        for the last views this context rendered: start, rotated, refitted, mask done, pixel kernel
+        done, grazing-ray kernel done (after debug_set("timeline", n))."""
+        out = np.zeros((max_views, TIMELINE_PHASES), dtype=np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.c5_timeline_read(self._h, C.c_void_p(origin_event), out.ctypes.data_as(C.POINTER(C.c_float)),
+                                              max_views, C.byref(n)))
+        return out[: n.value].copy()
+
+    def set_views_in_flight(self, n: int):
+        self._check(self.lib.c5_set_views_in_flight(self._h, n))
 
     def _check(self, rc: int):
         if rc != OK:
@@ -233,6 +253,21 @@ class Context:
         st = Stats()
         self._check(self.lib.c5_render(self._h, C.byref(view), _ptr(out, _dp), C.byref(st)))
         return out, st.as_dict()
+
+    def render_submit(self, view: View, out: np.ndarray) -> int:
+        """Enqueues the view and returns a ticket at once (c5_render_submit); `out` must stay alive and
+        untouched until render_wait(ticket). Page-locked `out` (torch pin_memory, host_register) is
+        written in place by the walk kernel; up to set_views_in_flight() views overlap on the device."""
+        if out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"] or out.size != view.res_y * view.res_x * 2:
+            raise ValueError("out must be a C-contiguous float64 array of res_y * res_x * 2")
+        ticket = C.c_uint64(0)
+        self._check(self.lib.c5_render_submit(self._h, C.byref(view), _ptr(out, _dp), C.byref(ticket)))
+        return int(ticket.value)
+
+    def render_wait(self, ticket: int) -> dict:
+        st = Stats()
+        self._check(self.lib.c5_render_wait(self._h, ticket, C.byref(st)))
+        return st.as_dict()
 
     def render_raw(self, view: View) -> RawImage:
         out = np.zeros((view.res_y, view.res_x, 2), dtype=np.float64)

@@ -43,8 +43,18 @@ void use_device(const DeviceState& d) {
     if (!kHostSim) C5_CUDA(cudaSetDevice(d.device));
 }
 
+// Phase events of the view being enqueued: 0 start, 1 rotated, 2 BVH refitted, 3 mask done,
+// 4 walk done (pixel + grazing-ray kernel), 5 band gathered (multi-device), 6 image on the host;
+// ev_walk sits between the two walk kernels.
 void record(DeviceState& d, int k) {
     if (!kHostSim) C5_CUDA(cudaEventRecord(d.ev[k], d.stream));
+}
+
+// c5_debug_set("timeline", n): the same moments kept for the last n views (c5_timeline_read).
+void timeline_mark(DeviceState& d, int phase) {
+    if (kHostSim || d.tl_events.empty()) return;
+    const size_t n = d.tl_events.size() / kTimelinePhases;
+    C5_CUDA(cudaEventRecord(d.tl_events[(d.tl_views % n) * kTimelinePhases + static_cast<size_t>(phase)], d.stream));
 }
 
 float elapsed(DeviceState& d, int a, int b) {
@@ -53,13 +63,6 @@ float elapsed(DeviceState& d, int a, int b) {
     C5_CUDA(cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]));
     return ms;
 }
-
-struct ViewPlan {
-    Rot rot[kMaxRot];
-    int n_rot;
-    int row_begin, row_end;
-    double x_min, y_min, step_x, step_y;
-};
 
 ViewPlan plan_view(const c5_view* v) {
     if (!v) fail(C5_E_INVALID, "render: view is NULL");
@@ -175,32 +178,27 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     if (!out_override) d.out.ensure(2 * n_pix_band);
     if (want_steps) d.steps.ensure(n_pix_band);
     d.counters.ensure(kNumCounters);
-    if (n_pix_band > d.queue.n) { // tags of a fresh allocation are garbage: start from zeros
-        d.queue.alloc(n_pix_band);
-        dev_zero(d.queue.p, d.queue.bytes(), d.stream);
-        d.queue_generation = 0;
-    }
+    d.queue.ensure(n_pix_band); // every ray of the band may be deferred (reserved, hardly ever touched)
     d.row_cost.ensure(static_cast<size_t>(v->res_y));
     if (solids) d.mask.ensure(static_cast<size_t>(v->res_x) * v->res_y);
 
     record(d, 0);
+    timeline_mark(d, 0);
     launch_prepare_cells(d, v->alpha_limit); // no-op unless --alpha_limit changed since the last view
-    // experiment switch (scripts/exp_lanes.py): C5_SKIP_PREP=1 repeats the SAME view without redoing
-    // its per-view preparation, to separate what that costs from what the walk costs
-    static const bool skip_prep_env = std::getenv("C5_SKIP_PREP") != nullptr;
-    const bool skip_prep = skip_prep_env && d.prep_done;
-    if (!skip_prep) launch_rotate_vertices(d, p.rot, p.n_rot);
-    if (solids && !skip_prep) launch_rotate_solids(d, p.rot, p.n_rot);
+    launch_rotate_vertices(d, p.rot, p.n_rot);
+    if (solids) launch_rotate_solids(d, p.rot, p.n_rot);
     record(d, 1);
-    if (!skip_prep) launch_bvh_refit(d);
+    timeline_mark(d, 1);
+    launch_bvh_refit(d);
     record(d, 2);
-    if (solids && !skip_prep) {
+    timeline_mark(d, 2);
+    if (solids) {
         dev_zero(d.mask.p + static_cast<size_t>(p.row_begin) * v->res_x,
                  static_cast<size_t>(p.row_end - p.row_begin) * v->res_x, d.stream);
         launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y, p.row_begin, p.row_end);
     }
-    d.prep_done = true;
     record(d, 3);
+    timeline_mark(d, 3);
     dev_zero(d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);
     dev_zero(d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(unsigned long long), d.stream);
     WalkLaunch w{};
@@ -214,9 +212,21 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     w.write_steps = want_steps ? 1 : 0;
     w.precision = v->precision ? v->precision : 64;
     w.out = out_override ? out_override : d.out.p;
+    w.mark_walk_done = d.ev_walk;
+    w.mark_walk_done_tl = nullptr;
+    if (!kHostSim && !d.tl_events.empty()) {
+        const size_t n = d.tl_events.size() / kTimelinePhases;
+        w.mark_walk_done_tl = d.tl_events[(d.tl_views % n) * kTimelinePhases + 4];
+    }
     mesh_pixel_rect(d, v, p, w);
+    if (!kHostSim) { // a band the mesh does not reach launches no walk kernels: the markers are recorded anyway
+        C5_CUDA(cudaEventRecord(d.ev_walk, d.stream));
+        if (w.mark_walk_done_tl) C5_CUDA(cudaEventRecord(w.mark_walk_done_tl, d.stream));
+    }
     launch_walk(d, w);
     record(d, 4);
+    timeline_mark(d, 5);
+    if (!d.tl_events.empty()) d.tl_views++;
 }
 
 // ---- NCCL, loaded lazily: only multi-device contexts need it ---------------------------------------
@@ -313,40 +323,24 @@ struct Counters {
     unsigned long long c[kNumCounters] = {};
 };
 
-// plane ctor + find_intersections + trace_rays for one view into a HOST buffer, on all devices of
-// the context: device r renders band r; bands land in device 0's image by one grouped NCCL
-// send/recv; device 0 copies the image to the host.
 void follow_parent(c5_ctx* ctx);
 
-void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, c5_stats* st) {
-    follow_parent(ctx);
+// Multi-device contexts (c5_create with several devices, one process): plane ctor + find_intersections
+// + trace_rays for one view into a HOST buffer; device r renders band r, the bands land in device 0's
+// image by one grouped NCCL send/recv, device 0 copies the image to the host. Synchronous.
+void render_multi_device(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, c5_stats* st) {
     if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
     if (!out) fail(C5_E_INVALID, "render: out is NULL");
     const ViewPlan p = plan_view(v);
     const int n_dev = static_cast<int>(ctx->dev.size());
-    if (n_dev > 1 && (p.row_end - p.row_begin) < n_dev) fail(C5_E_INVALID, "render: fewer rows than devices");
-    const auto bands = n_dev > 1 ? cut_bands(ctx, v, p, n_dev)
-                                 : std::vector<std::pair<int, int>>{{p.row_begin, p.row_end}};
+    if ((p.row_end - p.row_begin) < n_dev) fail(C5_E_INVALID, "render: fewer rows than devices");
+    const auto bands = cut_bands(ctx, v, p, n_dev);
     DeviceState& d0 = *ctx->dev[0];
     const size_t row_doubles = static_cast<size_t>(v->res_x) * 2;
     const size_t n_pix_view = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
-    if (n_dev > 1) {
-        use_device(d0);
-        d0.out.ensure(2 * n_pix_view); // device 0 assembles the whole view here
-    }
-    // A PINNED host buffer is device-addressable: the walk then stores its pixels straight into it
-    // (posted 128-byte writes over PCIe, spread over the kernel's run time), and the separate
-    // device-to-host copy of the image disappears. Pageable buffers take the copy.
+    use_device(d0);
+    d0.out.ensure(2 * n_pix_view); // device 0 assembles the whole view here
     const size_t view_off = static_cast<size_t>(p.row_begin) * v->res_x;
-    double* host_direct = nullptr;
-    if (n_dev == 1 && !kHostSim && !std::getenv("C5_NO_ZERO_COPY")) {
-        cudaPointerAttributes attr{};
-        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
-            host_direct = static_cast<double*>(attr.devicePointer) + 2 * view_off;
-        } else {
-            cudaGetLastError(); // pageable memory reports an error on some drivers: not ours
-        }
-    }
 
     // enqueue every device's band (asynchronous; devices run concurrently). With several devices
     // one host thread per device issues the launches, so launch latency is not serialised.
@@ -356,11 +350,10 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
         pr.row_begin = bands[static_cast<size_t>(r)].first;
         pr.row_end = bands[static_cast<size_t>(r)].second;
         double* target = nullptr;
-        if (n_dev > 1 && r == 0) target = d0.out.p + static_cast<size_t>(pr.row_begin - p.row_begin) * row_doubles;
-        if (host_direct) target = host_direct;
+        if (r == 0) target = d0.out.p + static_cast<size_t>(pr.row_begin - p.row_begin) * row_doubles;
         enqueue_view(d, v, pr, steps != nullptr, target);
     };
-    if (n_dev == 1 || kHostSim) {
+    if (kHostSim) {
         for (int r = 0; r < n_dev; r++) enqueue_band(r);
     } else {
         std::vector<std::thread> workers;
@@ -382,7 +375,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
     }
 
     // gather-v of the bands into device 0's image
-    if (n_dev > 1) {
+    {
         if (kHostSim) {
             for (int r = 1; r < n_dev; r++) {
                 const auto& b = bands[static_cast<size_t>(r)];
@@ -405,7 +398,7 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
     }
     use_device(d0);
     record(d0, 5);
-    if (!host_direct) d2h(out + 2 * view_off, d0.out.p, 2 * n_pix_view * sizeof(double), d0.stream);
+    d2h(out + 2 * view_off, d0.out.p, 2 * n_pix_view * sizeof(double), d0.stream);
     record(d0, 6);
 
     // per-device extras (steps, mask), counters, row costs
@@ -453,9 +446,14 @@ void render_host(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
             st->ms_bvh = std::max(st->ms_bvh, elapsed(*dp, 1, 2));
             st->ms_mask = std::max(st->ms_mask, elapsed(*dp, 2, 3));
             st->ms_walk = std::max(st->ms_walk, elapsed(*dp, 3, 4));
+            if (!kHostSim) {
+                float g = 0.f;
+                C5_CUDA(cudaEventElapsedTime(&g, dp->ev_walk, dp->ev[4]));
+                st->ms_graze = std::max(st->ms_graze, g);
+            }
         }
         use_device(d0);
-        st->ms_gather = n_dev > 1 ? elapsed(d0, 4, 5) : 0.f;
+        st->ms_gather = elapsed(d0, 4, 5);
         st->ms_d2h = elapsed(d0, 5, 6);
         st->ms_total = elapsed(d0, 0, 6);
         st->n_devices = n_dev;
@@ -485,11 +483,122 @@ void collect_stats(c5_ctx* ctx, DeviceState& d, const c5_view* v, const ViewPlan
         st->ms_bvh = elapsed(d, 1, 2);
         st->ms_mask = elapsed(d, 2, 3);
         st->ms_walk = elapsed(d, 3, 4);
+        if (!kHostSim) C5_CUDA(cudaEventElapsedTime(&st->ms_graze, d.ev_walk, d.ev[4]));
         st->ms_total = elapsed(d, 0, ev_last);
         st->n_devices = 1;
     }
     if (c[kWalkErrors]) {
         fail(C5_E_WALK, "render: " + std::to_string(c[kWalkErrors]) + " ray(s) exceeded the step cap");
+    }
+}
+
+// ---- single-device contexts: submit / wait -----------------------------------------------------------
+// A view is enqueued on the context's stream together with the copies that bring its results to the
+// host (image unless it is stored in place, counters, per-row costs -> page-locked staging), then an
+// event; waiting for the view is waiting for that event. Nothing in between touches the host, so
+// several contexts that share a mesh (the lanes of c5_render_submit) overlap on the device.
+
+void ensure_host_staging(DeviceState& d, size_t rows) {
+    if (!d.h_counters) d.h_counters = static_cast<unsigned long long*>(host_pinned_alloc(kNumCounters * sizeof(unsigned long long)));
+    if (rows > d.h_row_cost_n) {
+        host_pinned_free(d.h_row_cost);
+        d.h_row_cost = nullptr;
+        d.h_row_cost_n = 0;
+        d.h_row_cost = static_cast<uint64_t*>(host_pinned_alloc(rows * sizeof(uint64_t)));
+        d.h_row_cost_n = rows;
+    }
+}
+
+void submit_view(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, uint64_t ticket) {
+    follow_parent(ctx);
+    if (ctx->pending.active) fail(C5_E_STATE, "render: this context still has a view in flight (c5_render_wait it first)");
+    if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
+    if (!out) fail(C5_E_INVALID, "render: out is NULL");
+    const ViewPlan p = plan_view(v);
+    DeviceState& d = *ctx->dev[0];
+    use_device(d);
+    const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
+    const size_t band_off = static_cast<size_t>(p.row_begin) * v->res_x;
+    // A PAGE-LOCKED host buffer is device-addressable: the walk then stores its pixels straight into it
+    // (posted 128-byte writes over PCIe, spread over the kernel's run time) and the separate
+    // device-to-host copy of the image disappears. Pixels are stored as one 128-bit word, so the
+    // buffer must be 16-byte aligned; pageable or misaligned buffers take the copy.
+    double* host_direct = nullptr;
+    if (!kHostSim && !d.opt_no_zero_copy && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            host_direct = static_cast<double*>(attr.devicePointer) + 2 * band_off;
+        } else {
+            cudaGetLastError(); // pageable memory reports an error on some drivers: not ours
+        }
+    }
+    ensure_host_staging(d, static_cast<size_t>(v->res_y));
+    enqueue_view(d, v, p, steps != nullptr, host_direct);
+    record(d, 5);
+    if (!host_direct) d2h(out + 2 * band_off, d.out.p, 2 * n_pix_band * sizeof(double), d.stream);
+    record(d, 6);
+    const bool solids = v->use_solids && (d.solid_follow.n + d.solid_static.n) > 0;
+    if (steps) d2h(steps + band_off, d.steps.p, n_pix_band * sizeof(uint32_t), d.stream);
+    if (solid_mask) {
+        if (solids) d2h(solid_mask + band_off, d.mask.p + band_off, n_pix_band, d.stream);
+        else std::memset(solid_mask + band_off, 0, n_pix_band);
+    }
+    d2h(d.h_counters, d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);
+    d2h(d.h_row_cost, d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(uint64_t), d.stream);
+    if (!kHostSim) C5_CUDA(cudaEventRecord(d.ev_done, d.stream));
+    ctx->pending.active = true;
+    ctx->pending.ticket = ticket;
+    ctx->pending.view = *v;
+    ctx->pending.plan = p;
+    ctx->pending.d2h_copy = host_direct == nullptr;
+}
+
+// Waits for the view `lane` has in flight; row costs and errors are reported through `owner`
+// (the context the caller holds: lane itself, or the context whose lane it is).
+void finish_view(c5_ctx* owner, c5_ctx* lane, c5_stats* st) {
+    if (!lane->pending.active) fail(C5_E_STATE, "render_wait: no view in flight");
+    DeviceState& d = *lane->dev[0];
+    use_device(d);
+    lane->pending.active = false; // whatever happens below, the lane is free again
+    if (!kHostSim) C5_CUDA(cudaEventSynchronize(d.ev_done));
+    const c5_view& v = lane->pending.view;
+    const ViewPlan& p = lane->pending.plan;
+    owner->last_row_cost.assign(d.h_row_cost, d.h_row_cost + v.res_y);
+    const unsigned long long* c = d.h_counters;
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->pixels = static_cast<uint64_t>(p.row_end - p.row_begin) * static_cast<uint64_t>(v.res_x);
+        st->tet_steps = c[kSteps];
+        st->hit_pixels = c[kHitPixels];
+        st->solid_pixels = c[kSolidPixels];
+        st->walk_errors = c[kWalkErrors];
+        st->grazing_rays = static_cast<int32_t>(c[kDeferred]);
+        st->ms_rotate = elapsed(d, 0, 1);
+        st->ms_bvh = elapsed(d, 1, 2);
+        st->ms_mask = elapsed(d, 2, 3);
+        st->ms_walk = elapsed(d, 3, 4);
+        if (!kHostSim) C5_CUDA(cudaEventElapsedTime(&st->ms_graze, d.ev_walk, d.ev[4]));
+        st->ms_d2h = elapsed(d, 5, 6);
+        st->ms_total = elapsed(d, 0, 6);
+        st->n_devices = 1;
+    }
+    if (c[kWalkErrors]) {
+        fail(C5_E_WALK, "render: " + std::to_string(c[kWalkErrors]) + " ray(s) exceeded the step cap");
+    }
+}
+
+// The lanes of c5_render_submit: lane 0 is the context itself, the others are sibling contexts the
+// library makes (and owns) on first use.
+c5_ctx* lane_of(c5_ctx* ctx, unsigned k) {
+    return k == 0 ? ctx : ctx->lanes[k - 1];
+}
+
+void ensure_lanes(c5_ctx* ctx) {
+    while (static_cast<int>(ctx->lanes.size()) + 1 < ctx->views_in_flight) {
+        c5_ctx* lane = nullptr;
+        const int rc = c5_create_sibling(ctx, &lane);
+        if (rc != C5_OK) fail(rc, "render_submit: cannot create a lane: " + ctx->err);
+        ctx->lanes.push_back(lane);
     }
 }
 
@@ -632,6 +741,14 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
     if (!out) return C5_E_INVALID;
     *out = nullptr;
     c5_ctx* ctx = nullptr;
+    auto failed = [&](int code, const std::string& text) {
+        {
+            std::lock_guard<std::mutex> lock(g_create_err_mu);
+            g_create_err = text;
+        }
+        c5_destroy(ctx); // the same teardown as a finished context: streams, events, NCCL, device memory
+        return code;
+    };
     try {
         if (n_dev < 1 || !devices) fail(C5_E_INVALID, "c5_create: need at least one device");
         ctx = new c5_ctx();
@@ -647,22 +764,16 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
             }
         }
         for (int k = 0; k < n_dev; k++) {
-            auto d = std::make_unique<DeviceState>();
+            ctx->dev.push_back(std::make_unique<DeviceState>());
+            DeviceState* d = ctx->dev.back().get(); // in the context before anything is created: a failure below is torn down
             d->device = devices[k];
             if (!kHostSim) {
                 C5_CUDA(cudaSetDevice(d->device));
                 C5_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
                 for (auto& e : d->ev) C5_CUDA(cudaEventCreate(&e));
-                int prio_lo = 0, prio_hi = 0;
-                C5_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-                C5_CUDA(cudaStreamCreateWithPriority(&d->graze_stream, cudaStreamNonBlocking, prio_lo));
-                C5_CUDA(cudaEventCreateWithFlags(&d->graze_fork, cudaEventDisableTiming));
-                C5_CUDA(cudaEventCreateWithFlags(&d->graze_join, cudaEventDisableTiming));
+                C5_CUDA(cudaEventCreate(&d->ev_walk));
+                C5_CUDA(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
             }
-            ctx->dev.push_back(std::move(d));
-        }
-        if (n_dev > 1) { // NCCL kernels share these devices: no kernel of ours may wait for another (c5gpu.h)
-            for (auto& d : ctx->dev) d->graze_beside = false;
         }
         if (n_dev > 1 && !kHostSim) {
             ctx->nccl = nccl_open(std::vector<int>(devices, devices + n_dev));
@@ -671,17 +782,9 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
         *out = ctx;
         return C5_OK;
     } catch (const Error& e) {
-        std::lock_guard<std::mutex> lock(g_create_err_mu);
-        g_create_err = e.text;
-        if (ctx) nccl_close(ctx->nccl);
-        delete ctx;
-        return e.code;
+        return failed(e.code, e.text);
     } catch (const std::exception& e) {
-        std::lock_guard<std::mutex> lock(g_create_err_mu);
-        g_create_err = e.what();
-        if (ctx) nccl_close(ctx->nccl);
-        delete ctx;
-        return C5_E_NOMEM;
+        return failed(C5_E_NOMEM, e.what());
     }
 }
 
@@ -698,29 +801,37 @@ int c5_create_sibling(c5_ctx* parent, c5_ctx** out) {
     if (rc != C5_OK) return rc;
     ctx->parent = parent;
     parent->siblings.push_back(ctx);
+    DeviceState& from = *parent->dev[0];
+    DeviceState& to = *ctx->dev[0];
+    to.opt_graze_list = from.opt_graze_list;
+    to.opt_query_budget = from.opt_query_budget;
+    to.opt_serial_list = from.opt_serial_list;
+    to.opt_no_zero_copy = from.opt_no_zero_copy;
     *out = ctx;
     return C5_OK;
 }
 
 void c5_destroy(c5_ctx* ctx) {
     if (!ctx) return;
+    for (c5_ctx* lane : ctx->lanes) c5_destroy(lane); // our own lanes go first (each leaves ctx->siblings)
+    ctx->lanes.clear();
     if (ctx->parent) { // a sibling leaves its parent's list
         auto& sib = ctx->parent->siblings;
         sib.erase(std::remove(sib.begin(), sib.end(), ctx), sib.end());
     }
     for (c5_ctx* s : ctx->siblings) { // a parent going first takes the shared mesh with it
-        if (!kHostSim) {
+        if (!kHostSim && !s->dev.empty()) {
             cudaSetDevice(s->dev[0]->device);
             cudaDeviceSynchronize();
         }
         s->parent = nullptr;
         s->has_mesh = false;
-        s->dev[0]->origin = nullptr;
+        if (!s->dev.empty()) s->dev[0]->origin = nullptr;
     }
     ctx->siblings.clear();
     nccl_close(ctx->nccl);
     ctx->nccl = nullptr;
-    if (!kHostSim) {
+    if (!kHostSim && !ctx->dev.empty() && ctx->dev[0]->stream) {
         cudaSetDevice(ctx->dev[0]->device);
         cudaStreamSynchronize(ctx->dev[0]->stream);
     }
@@ -735,8 +846,9 @@ void c5_destroy(c5_ctx* ctx) {
         DeviceState& d = *dp;
         if (!kHostSim) {
             cudaSetDevice(d.device);
-            cudaStreamSynchronize(d.stream);
+            if (d.stream) cudaStreamSynchronize(d.stream);
         }
+#ifdef C5_EXPERIMENTS
         if (!kHostSim && d.trace_launches > 0) {
             if (const char* path = std::getenv("C5_TRACE_FILE")) {
                 cudaDeviceSynchronize();
@@ -754,11 +866,13 @@ void c5_destroy(c5_ctx* ctx) {
                 }
             }
         }
+#endif
+        host_pinned_free(d.h_counters);
+        host_pinned_free(d.h_row_cost);
         if (!kHostSim) {
-            if (d.graze_stream) cudaStreamSynchronize(d.graze_stream);
-            if (d.graze_fork) cudaEventDestroy(d.graze_fork);
-            if (d.graze_join) cudaEventDestroy(d.graze_join);
-            if (d.graze_stream) cudaStreamDestroy(d.graze_stream);
+            for (cudaEvent_t e : d.tl_events) cudaEventDestroy(e);
+            if (d.ev_walk) cudaEventDestroy(d.ev_walk);
+            if (d.ev_done) cudaEventDestroy(d.ev_done);
             for (auto& e : d.ev) {
                 if (e) cudaEventDestroy(e);
             }
@@ -840,14 +954,79 @@ int c5_mesh_info_get(const c5_ctx* ctx, c5_mesh_info* out) {
 }
 
 int c5_render(c5_ctx* ctx, const c5_view* view, double* out, c5_stats* stats) {
-    if (!ctx) return C5_E_INVALID;
-    return guarded(ctx, [&] { render_host(ctx, view, out, nullptr, nullptr, stats); });
+    return c5_render_raw(ctx, view, out, nullptr, nullptr, stats);
 }
 
 int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps, uint8_t* solid_mask,
                   c5_stats* stats) {
     if (!ctx) return C5_E_INVALID;
-    return guarded(ctx, [&] { render_host(ctx, view, out, steps, solid_mask, stats); });
+    return guarded(ctx, [&] {
+        if (ctx->dev.size() > 1) {
+            render_multi_device(ctx, view, out, steps, solid_mask, stats);
+            return;
+        }
+        submit_view(ctx, view, out, steps, solid_mask, 0);
+        finish_view(ctx, ctx, stats);
+    });
+}
+
+int c5_set_views_in_flight(c5_ctx* ctx, int32_t n) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        if (n < 1 || n > C5_MAX_IN_FLIGHT) fail(C5_E_INVALID, "set_views_in_flight: 1 .. C5_MAX_IN_FLIGHT");
+        if (ctx->parent || ctx->dev.size() != 1) fail(C5_E_INVALID, "set_views_in_flight: single-device contexts that are not siblings");
+        for (unsigned k = 0; k <= ctx->lanes.size(); k++) {
+            if (lane_of(ctx, k)->pending.active) fail(C5_E_STATE, "set_views_in_flight: views are in flight");
+        }
+        while (static_cast<int>(ctx->lanes.size()) + 1 > n) { // lanes that are no longer wanted
+            c5_destroy(ctx->lanes.back());
+            ctx->lanes.pop_back();
+        }
+        ctx->views_in_flight = n;
+        ctx->next_lane = 0;
+    });
+}
+
+int c5_render_submit(c5_ctx* ctx, const c5_view* view, double* out, uint64_t* ticket) {
+    if (!ctx || !ticket) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        if (ctx->parent || ctx->dev.size() != 1) fail(C5_E_INVALID, "render_submit: single-device contexts that are not siblings");
+        ensure_lanes(ctx);
+        // the next lane in turn, or any free one
+        const unsigned n = static_cast<unsigned>(ctx->lanes.size()) + 1;
+        c5_ctx* lane = nullptr;
+        for (unsigned k = 0; k < n && !lane; k++) {
+            c5_ctx* cand = lane_of(ctx, (ctx->next_lane + k) % n);
+            if (!cand->pending.active) {
+                lane = cand;
+                ctx->next_lane = (ctx->next_lane + k + 1) % n;
+            }
+        }
+        if (!lane) fail(C5_E_STATE, "render_submit: " + std::to_string(n) + " views are in flight already (c5_render_wait one first)");
+        const uint64_t t = ctx->next_ticket++;
+        try {
+            g_launch_counter = &lane->dev[0]->launches;
+            submit_view(lane, view, out, nullptr, nullptr, t);
+        } catch (const Error& e) {
+            if (lane != ctx) ctx->err = e.text; // (guarded() reports through ctx)
+            throw;
+        }
+        *ticket = t;
+    });
+}
+
+int c5_render_wait(c5_ctx* ctx, uint64_t ticket, c5_stats* stats) {
+    if (!ctx) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        for (unsigned k = 0; k <= ctx->lanes.size(); k++) {
+            c5_ctx* lane = lane_of(ctx, k);
+            if (lane->pending.active && lane->pending.ticket == ticket && ticket != 0) {
+                finish_view(ctx, lane, stats);
+                return;
+            }
+        }
+        fail(C5_E_INVALID, "render_wait: no view with this ticket is in flight");
+    });
 }
 
 int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream, c5_stats* stats) {
@@ -856,7 +1035,9 @@ int c5_render_device(c5_ctx* ctx, const c5_view* view, void* d_out, void* stream
         follow_parent(ctx);
         if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
         if (!d_out) fail(C5_E_INVALID, "render_device: d_out is NULL");
+        if (reinterpret_cast<uintptr_t>(d_out) & 15u) fail(C5_E_INVALID, "render_device: d_out must be 16-byte aligned");
         if (ctx->dev.size() != 1) fail(C5_E_INVALID, "render_device: single-device contexts only");
+        if (ctx->pending.active) fail(C5_E_STATE, "render_device: this context has a submitted view in flight");
         const ViewPlan p = plan_view(view);
         DeviceState& d = *ctx->dev[0];
         // run on the CALLER's stream (NULL = the legacy default stream, which is what torch's
@@ -881,12 +1062,6 @@ int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows) {
     for (int32_t j = 0; j < n_rows; j++) {
         rows[j] = static_cast<size_t>(j) < ctx->last_row_cost.size() ? ctx->last_row_cost[static_cast<size_t>(j)] : 0;
     }
-    return C5_OK;
-}
-
-int c5_set_concurrent_grazing(c5_ctx* ctx, int32_t on) {
-    if (!ctx) return C5_E_INVALID;
-    for (auto& d : ctx->dev) d->graze_beside = on != 0;
     return C5_OK;
 }
 
@@ -988,8 +1163,66 @@ uint64_t c5_kernel_launches(const c5_ctx* ctx) {
     uint64_t n = 0;
     if (ctx) {
         for (const auto& d : ctx->dev) n += d->launches;
+        for (const c5_ctx* lane : ctx->lanes) n += c5_kernel_launches(lane);
     }
     return n;
+}
+
+int c5_debug_set(c5_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        const std::string k = key;
+        std::vector<c5_ctx*> all{ctx};
+        all.insert(all.end(), ctx->siblings.begin(), ctx->siblings.end()); // the caller's siblings and our lanes
+        for (c5_ctx* c : all) {
+            for (auto& dp : c->dev) {
+                DeviceState& d = *dp;
+                if (k == "graze_list") d.opt_graze_list = static_cast<int>(value);
+                else if (k == "query_budget") d.opt_query_budget = static_cast<int>(value);
+                else if (k == "serial_list") d.opt_serial_list = static_cast<int>(value);
+                else if (k == "no_zero_copy") d.opt_no_zero_copy = value != 0;
+                else if (k == "timeline") {
+                    if (value < 0 || value > 4096) fail(C5_E_INVALID, "debug_set: timeline 0 .. 4096 views");
+                    if (kHostSim) continue;
+                    use_device(d);
+                    C5_CUDA(cudaStreamSynchronize(d.stream));
+                    for (cudaEvent_t e : d.tl_events) cudaEventDestroy(e);
+                    d.tl_events.clear();
+                    d.tl_views = 0;
+                    for (int64_t i = 0; i < value * kTimelinePhases; i++) {
+                        cudaEvent_t e = nullptr;
+                        C5_CUDA(cudaEventCreate(&e));
+                        d.tl_events.push_back(e);
+                    }
+                } else {
+                    fail(C5_E_INVALID, "debug_set: unknown key '" + k + "'");
+                }
+            }
+        }
+    });
+}
+
+int c5_timeline_read(c5_ctx* ctx, void* origin, float* ms_out, int32_t max_views, int32_t* n_views) {
+    if (!ctx || !ms_out || !n_views || max_views < 0) return C5_E_INVALID;
+    return guarded(ctx, [&] {
+        *n_views = 0;
+        if (kHostSim) return;
+        if (!origin) fail(C5_E_INVALID, "timeline_read: origin event is NULL");
+        DeviceState& d = *ctx->dev[0];
+        use_device(d);
+        const uint64_t cap = d.tl_events.size() / kTimelinePhases;
+        if (cap == 0) return;
+        const uint64_t have = std::min<uint64_t>({d.tl_views, cap, static_cast<uint64_t>(max_views)});
+        for (uint64_t i = 0; i < have; i++) {
+            const uint64_t view = d.tl_views - have + i;
+            for (int ph = 0; ph < kTimelinePhases; ph++) {
+                cudaEvent_t e = d.tl_events[(view % cap) * kTimelinePhases + static_cast<size_t>(ph)];
+                C5_CUDA(cudaEventSynchronize(e));
+                C5_CUDA(cudaEventElapsedTime(ms_out + i * kTimelinePhases + ph, static_cast<cudaEvent_t>(origin), e));
+            }
+        }
+        *n_views = static_cast<int32_t>(have);
+    });
 }
 
 } // extern "C"

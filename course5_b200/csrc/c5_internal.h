@@ -12,12 +12,12 @@
 namespace c5 {
 
 constexpr int kMaxRot = C5_MAX_ROT;
+constexpr int kTimelinePhases = 6; // start, rotated, refitted, masked, pixel kernel done, grazing-ray kernel done
 
 // Counters the walk kernel accumulates (one 64-bit atomic per warp).
 // kDeferred = rays the pixel kernel handed to the grazing-ray kernel, kTicket = how many of those
 // the grazing-ray kernel's warps have drawn.
-// kBlocksDone = blocks of the pixel kernel that have finished (the grazing-ray kernel's exit condition).
-enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kDeferred = 4, kTicket = 5, kBlocksDone = 6,
+enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kDeferred = 4, kTicket = 5,
                kNumCounters = 8 };
 
 struct SolidSet {
@@ -45,9 +45,16 @@ struct DeviceState {
     DeviceState* origin = nullptr;   // sibling context: the device state that owns the mesh (and these two flags)
     uint64_t mesh_version = 0;       // bumped by every upload; a sibling re-aliases when it falls behind
     bool mesh_shared = false;        // some sibling aliases this state's arrays
+#ifdef C5_EXPERIMENTS
     DevBuf<StepRec> recs;            // experimental "rec" walk variant: 4 step records per tet, built on first use
     double recs_limit = 0.0;
     bool recs_valid = false;
+    // C5_TRACE_FILE: start / end time and SM of every block of the first pixel-kernel launches,
+    // written to that file when the context is destroyed (scripts/trace_blocks.py reads it)
+    DevBuf<unsigned long long> trace;
+    int trace_launches = 0;
+    unsigned trace_grid[64] = {};
+#endif
     DevBuf<BFace> bfaces;            // Morton-sorted boundary faces (BVH leaves)
     DevBuf<BvhNode> nodes;           // n_bfaces - 1 internal nodes, BFS order (root = 0)
     DevBuf<int32_t> node_parent;     // per internal node: (parent << 1) | which child, -1 for the root
@@ -68,23 +75,41 @@ struct DeviceState {
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned long long> row_cost;
     DevBuf<DeferredRay> queue;       // grazing rays of the current view (capacity: pixels of the band)
-    uint32_t queue_generation = 0;   // tag of the last view's records (0: the queue is all zeros)
-    cudaStream_t graze_stream = nullptr; // the grazing-ray kernel runs beside the pixel kernel ...
-    bool graze_beside = true;            // ... unless the caller shares the device with other kernels (c5_set_concurrent_grazing)
-    cudaEvent_t graze_fork = nullptr, graze_join = nullptr;
     int sm_count = 0;
-    bool prep_done = false;          // C5_SKIP_PREP experiment switch
-    // C5_TRACE_FILE: start / end time and SM of every block of the first pixel-kernel launches,
-    // written to that file when the context is destroyed (scripts/trace_blocks.py reads it)
-    DevBuf<unsigned long long> trace;
-    int trace_launches = 0;
-    unsigned trace_grid[64] = {};
+    cudaEvent_t ev_walk = nullptr;   // between the pixel kernel and the grazing-ray kernel (phase times)
+    cudaEvent_t ev_done = nullptr;   // after the view's last copy: what c5_render_wait waits for
+    // results of the view in flight, copied by the stream into pinned host memory
+    unsigned long long* h_counters = nullptr;   // [kNumCounters]
+    uint64_t* h_row_cost = nullptr;             // [h_row_cost_n]
+    size_t h_row_cost_n = 0;
+    // c5_debug_set (tests, diagnostics); 0 = default
+    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0;
+    bool opt_no_zero_copy = false;
+    // c5_debug_set("timeline", n): phase events of the last n views, read by c5_timeline_read
+    std::vector<cudaEvent_t> tl_events;         // [n][kTimelinePhases]
+    uint64_t tl_views = 0;                      // views recorded since the timeline was enabled
 
     uint64_t launches = 0;
 };
 
 struct MeshHost;
 
+} // namespace c5
+
+namespace c5 {
+struct ViewPlan {      // a validated c5_view: trig evaluated, band and pixel steps resolved
+    Rot rot[kMaxRot];
+    int n_rot;
+    int row_begin, row_end;
+    double x_min, y_min, step_x, step_y;
+};
+struct PendingView {   // the view a context has in flight between c5_render_submit and c5_render_wait
+    bool active = false;
+    uint64_t ticket = 0;
+    c5_view view{};
+    ViewPlan plan{};
+    bool d2h_copy = false; // the image went through the device band buffer and a copy (not stored in place)
+};
 } // namespace c5
 
 struct c5_ctx {
@@ -95,7 +120,12 @@ struct c5_ctx {
     std::vector<uint64_t> last_row_cost;
     void* nccl = nullptr; // NcclGroup*, multi-device contexts only
     c5_ctx* parent = nullptr;        // sibling context (c5_create_sibling): shares parent's mesh and solids
-    std::vector<c5_ctx*> siblings;   // contexts created from this one
+    std::vector<c5_ctx*> siblings;   // contexts created from this one (the caller's, and our own lanes)
+    std::vector<c5_ctx*> lanes;      // lanes of c5_render_submit beyond this context itself (owned; also in siblings)
+    int views_in_flight = 3;
+    uint64_t next_ticket = 1;
+    unsigned next_lane = 0;
+    c5::PendingView pending;         // this context's own view in flight
     std::vector<std::pair<void*, bool>> images;   // c5_image_create (true) / c5_image_open (false) pointers
     std::vector<std::pair<void*, void*>> image_offsets; // imported images: (pointer handed out, mapping base)
     std::vector<void*> registered;                // c5_host_register pointers
@@ -128,6 +158,8 @@ struct WalkLaunch {
     int write_steps;
     int precision;
     double* out; // {tau, I} per pixel of the band, x fastest
+    cudaEvent_t mark_walk_done;    // recorded between the pixel kernel and the grazing-ray kernel (may be null)
+    cudaEvent_t mark_walk_done_tl; // the same moment for the timeline ring (may be null)
 };
 void launch_walk(DeviceState& d, const WalkLaunch& w);
 

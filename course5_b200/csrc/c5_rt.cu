@@ -106,6 +106,23 @@ void d2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     }
 }
 
+void* host_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (kHostSim) {
+        p = std::malloc(bytes ? bytes : 1);
+        if (!p) fail(-3, "host allocation failed");
+    } else {
+        C5_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable));
+    }
+    return p;
+}
+
+void host_pinned_free(void* p) {
+    if (!p) return;
+    if (kHostSim) std::free(p);
+    else cudaFreeHost(p);
+}
+
 void stream_sync(cudaStream_t s) {
     if (!kHostSim) C5_CUDA(cudaStreamSynchronize(s));
 }

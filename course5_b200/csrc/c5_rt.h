@@ -51,6 +51,8 @@ void h2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
 void d2h(void* dst, const void* src, size_t bytes, cudaStream_t s);
 void d2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
 void stream_sync(cudaStream_t s);
+void* host_pinned_alloc(size_t bytes); // page-locked host memory (results the stream copies back while the host runs on)
+void host_pinned_free(void* p);
 size_t dev_bytes_in_use();
 
 template <class T>

@@ -483,8 +483,10 @@ void build_mesh(DeviceState& d, const double* pts, int64_t n_pts, const int32_t*
     d.n_tets = n_tets;
     d.n_bfaces = static_cast<int64_t>(n_b);
     d.cells_limit_valid = false;
+#ifdef C5_EXPERIMENTS
     d.recs.release();
     d.recs_valid = false;
+#endif
 }
 
 } // namespace c5

@@ -59,22 +59,17 @@ struct alignas(64) BvhNode {
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
 // A ray the pixel kernel could not finish cheaply (its re-entry list came back full: it grazes a
-// bumpy boundary and has many short crossings). The grazing-ray kernel continues it from here.
-// The queue is filled while the grazing-ray kernel is already draining it (the two run side by
-// side), so a slot carries a tag: the view's generation number in the top bits of the word that
-// holds the step count, written LAST. A consumer that holds ticket t polls slot t until the tag is
-// this view's.
-constexpr int kTagShift = 21;                       // steps < 2^21 (the step cap is 2^20)
-constexpr uint32_t kTagGenerations = (1u << (32 - kTagShift)) - 1; // generations 1 .. 2047, then the queue is cleared
+// bumpy boundary and has many short crossings — or a BVH search ran out of budget). The
+// grazing-ray kernel, launched after the pixel kernel on the same stream, continues it from here.
 struct alignas(32) DeferredRay {
     double tau, inten; // accumulated so far
     double z_after;    // the ray has left the mesh at this depth
     uint32_t pixel;    // j * res_x + i
-    uint32_t tag;      // generation << kTagShift | steps
+    uint32_t steps;    // tets crossed so far
 };
 static_assert(sizeof(DeferredRay) == 32, "DeferredRay must be 32 bytes");
 
-// ---- step records (experimental walk variant "rec") -------------------------------
+// ---- step records (experimental walk variant "rec", libc5gpu_exp.so only) ----------
 // The walk is bound by L1 data-pipe wavefronts: one per lane and load instruction, and the 64-byte
 // Cell costs two. A StepRec is everything a step needs in ONE 256-bit load: there is one per
 // (tet t, entry face e), index 4 t + e, holding for each of the three faces the ray can leave

@@ -38,7 +38,7 @@ namespace c5 {
 
 namespace {
 
-constexpr int kStack = 64;        // LBVH traversal stack (depth is checked at upload)
+constexpr int kStack = 64;        // private LBVH traversal stack; a search that would overflow it is an incomplete search
 constexpr int kBlock = 128;       // 4 warps: 2 x 2 warp tiles of 8 x 4 pixels
 constexpr int kTileX = 16, kTileY = 8;
 
@@ -55,23 +55,27 @@ struct WalkParams {
     unsigned long long* counters;
     unsigned long long* row_cost; // [res_y]
     DeferredRay* queue;   // rays handed to the grazing-ray kernel; counters[kDeferred] of them
-    unsigned long long queue_capacity;
-    uint32_t generation;  // tag of this view's queue records
-    uint32_t n_pixel_blocks; // grid of the pixel kernel: counters[kBlocksDone] reaches it when the queue is final
-    int fence_stores;     // debugging aid (C5_STORE_FENCE): a system-scope fence after every pixel store
-    unsigned long long* trace; // debugging aid (C5_TRACE_FILE): per block {start ns, end ns, sm | launch << 32, block}
     int res_x, res_y, row_begin, row_end;
     int i0, i1, j0, j1;   // pixel rectangle [i0,i1) x [j0,j1) of the band that can see the mesh: the tiles cover it
     int n_tiles_x, n_tiles_y, n_macro_x;
-    int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
     int graze_cap;        // entries one cooperative collection may hold (<= kGrazeList)
     int serial_cap;       // same for the serial (host loop) form (<= kSerialList)
     int query_budget;     // BVH nodes one thread of the pixel kernel may visit per search before deferring the ray
     int max_steps;
     int round_float;
     double alpha_limit;
-    const StepRec* recs;  // experimental "rec" variant only, else null (last: the other kernels' parameter offsets stay put)
+#ifdef C5_EXPERIMENTS     // libc5gpu_exp.so only (scripts/): block timeline, shared-memory BVH top, step records
+    unsigned long long* trace; // per block {start ns, end ns, sm, block}
+    int top_nodes;        // BVH nodes [0, top_nodes) are staged in shared memory
+    const StepRec* recs;
+#endif
 };
+
+#ifdef C5_EXPERIMENTS
+C5_HD int staged_nodes(const WalkParams& P) { return P.top_nodes; }
+#else
+C5_HD int staged_nodes(const WalkParams&) { return 0; }
+#endif
 
 // ---- loads through the read-only path ----------------------------------------------------------
 struct CellData {
@@ -133,6 +137,7 @@ C5_HD void load_vtx(const Vtx* vrot, int id, double& x, double& y, double& z) {
 #endif
 }
 
+#ifdef C5_EXPERIMENTS
 C5_HD StepRec load_rec(const StepRec* recs, uint32_t face) {
     StepRec r;
 #ifdef __CUDA_ARCH__
@@ -144,6 +149,7 @@ C5_HD StepRec load_rec(const StepRec* recs, uint32_t face) {
 #endif
     return r;
 }
+#endif
 
 // Next step's cell and vertex are known as soon as the exit face is (Cell::nbr / Cell::apex), long
 // before this step's divide and exp have retired: asking L1 for them now overlaps their L2/DRAM
@@ -254,7 +260,7 @@ C5_HD bool bvh_collect_entries(const WalkParams& P, const BvhNode* top, double p
             complete = false;
             break;
         }
-        const BvhNode* n = (top && node < P.top_nodes) ? (top + node) : (P.nodes + node);
+        const BvhNode* n = (top && node < staged_nodes(P)) ? (top + node) : (P.nodes + node);
 #ifdef __CUDA_ARCH__
         const float4 bx = *reinterpret_cast<const float4*>(n->xlo); // xlo0 xlo1 xhi0 xhi1
         const float4 by = *reinterpret_cast<const float4*>(n->ylo);
@@ -284,7 +290,11 @@ C5_HD bool bvh_collect_entries(const WalkParams& P, const BvhNode* top, double p
         }
         if (h0 && h1) {
             const bool first0 = bz.x <= bz.y; // descend into the lower subtree first
-            if (sp < kStack) stack[sp++] = first0 ? ch.y : ch.x;
+            if (sp == kStack) { // a tree deeper than the private stack: never drop a subtree, hand the ray on
+                complete = false;
+                break;
+            }
+            stack[sp++] = first0 ? ch.y : ch.x;
             node = first0 ? ch.x : ch.y;
         } else if (h0) {
             node = ch.x;
@@ -399,7 +409,9 @@ C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, d
     return z_cur;
 }
 
-// Experimental variant "rec" (C5_WALK_VARIANT=rec): the same crossing on step records
+#ifdef C5_EXPERIMENTS
+// Experimental variant "rec" (C5_WALK_VARIANT=rec, libc5gpu_exp.so only; measured: 3 % faster on the C3
+// README view, 6 % slower on an oblique one, profiles/r02_exp_rec_vs_cells.jsonl — not adopted): the same crossing on step records
 // (c5_types.h) — one 256-bit load for the tet instead of two, so two L1 data-pipe wavefronts per
 // lane and step instead of three. The exit slot is the rank of the dropped vertex's id among the
 // three entry-face ids. alpha and s arrive cut to 48 bits (7e-12 relative).
@@ -481,6 +493,7 @@ C5_HD double crossing_rec_f64(const WalkParams& P, double px, double py, int lea
     }
     return z_cur;
 }
+#endif
 
 // ---- FP32 variant -----------------------------------------------------------------------------------
 // Same crossing with the per-step geometry in single precision: FP32 orientation tests (still exactly
@@ -605,11 +618,14 @@ C5_HD double crossing_f32(const WalkParams& P, double px, double py, int leaf, d
 template <bool kF32, bool kWide, int kPipe, bool kAffine, bool kRec = false>
 C5_HD double crossing(const WalkParams& P, double px, double py, int leaf, double z_in, double& tau, double& inten,
                       double& gain, uint32_t& steps, uint32_t& error) {
+#ifdef C5_EXPERIMENTS
     if (kRec) return crossing_rec_f64(P, px, py, leaf, z_in, tau, inten, steps, error);
+#endif
     return kF32 ? crossing_f32<kWide, kPipe, kAffine>(P, px, py, leaf, z_in, tau, inten, gain, steps, error)
                 : crossing_f64<kWide, kPipe, kAffine>(P, px, py, leaf, z_in, tau, inten, gain, steps, error);
 }
 
+#ifdef C5_EXPERIMENTS
 // Step record of (tet, entry face) f = 4 t + e: the three faces the ray can leave through, ordered by
 // the global id of the entry-face vertex each one drops.
 C5_HD StepRec make_step_record(const Cell* cells, int64_t f) {
@@ -639,6 +655,7 @@ C5_HD StepRec make_step_record(const Cell* cells, int64_t f) {
     }
     return pack_rec(next_face, next_apex, c.alpha, c.s);
 }
+#endif
 
 // ---- one ray (pixel kernel) ------------------------------------------------------------------------
 
@@ -715,17 +732,13 @@ C5_HD RayResult trace_ray(const WalkParams& P, const BvhNode* top, double px, do
 #else
         const unsigned long long slot = P.counters[kDeferred]++;
 #endif
+        // read by the grazing-ray kernel, which is launched after this one on the same stream
         DeferredRay& q = P.queue[slot];
         q.tau = r.tau;
         q.inten = r.inten;
         q.z_after = z_after;
         q.pixel = pixel;
-#ifdef __CUDA_ARCH__
-        __threadfence(); // the record before its tag: a grazing warp may already be polling this slot
-        *reinterpret_cast<volatile uint32_t*>(&q.tag) = (P.generation << kTagShift) | r.steps;
-#else
-        q.tag = (P.generation << kTagShift) | r.steps;
-#endif
+        q.steps = r.steps;
         r.deferred = 1;
     }
     return r;
@@ -763,12 +776,12 @@ C5_HD RayAcc graze_ray_serial(const WalkParams& P, const DeferredRay& q, double 
     a.tau = q.tau;
     a.inten = q.inten;
     a.z_after = q.z_after;
-    a.steps = q.tag & ((1u << kTagShift) - 1u);
+    a.steps = q.steps;
     a.error = 0;
     EntryList<kSerialList> L;
     int crossings = 0;
     while (!a.error) {
-        bvh_collect_entries(P, nullptr, px, py, a.z_after, L, P.serial_cap, 0x7FFFFFFF);
+        if (!bvh_collect_entries(P, nullptr, px, py, a.z_after, L, P.serial_cap, 0x7FFFFFFF)) a.error = 1; // stack overflow
         for (int e = 0; e < L.n; e++) {
             if (!(L.z[e] > a.z_after)) continue;
             double tau_k = 0.0, inten_k = 0.0, gain_k = 1.0;
@@ -806,9 +819,6 @@ C5_HD void store_pixel(const WalkParams& P, int i, int j, double tau, double int
     P.out[2 * o + 1] = inten;
 #endif
     if (P.steps) P.steps[o] = steps;
-#ifdef __CUDA_ARCH__
-    if (P.fence_stores) __threadfence_system();
-#endif
 }
 
 // Pixels of the band outside the rectangle the walk covers: background (or solid).
@@ -937,43 +947,25 @@ __device__ __forceinline__ void graze_block(const WalkParams& P) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     GrazeSmem& S = smem[threadIdx.x >> 5];
-    // This kernel runs BESIDE the pixel kernel (its own low-priority stream), so that grazing rays
-    // are finished in the gaps and the tail of that kernel instead of after it. A warp draws ticket
-    // t and waits until slot t carries this view's tag — or until every block of the pixel kernel
-    // has finished without filling it.
-    const volatile unsigned long long* blocks_done = &P.counters[kBlocksDone];
+    // Launched after the pixel kernel on the same stream, so the queue and its length are final.
+    // The length lives on the device: a fixed grid of persistent warps draws tickets until they run
+    // out (an empty queue costs one short launch).
+    const unsigned long long n_rays = P.counters[kDeferred];
     while (true) {
-        uint32_t tag = 0;
         unsigned long long ticket = 0;
-        if (lane == 0) {
-            ticket = atomicAdd(&P.counters[kTicket], 1ull);
-            if (ticket < P.queue_capacity) {
-                const volatile uint32_t* slot_tag = &P.queue[ticket].tag;
-                while (true) {
-                    tag = *slot_tag;
-                    if ((tag >> kTagShift) == P.generation) break;
-                    if (*blocks_done >= P.n_pixel_blocks) { // every push is complete: look once more
-                        tag = *slot_tag;
-                        break;
-                    }
-                    __nanosleep(1000);
-                }
-            }
-            if ((tag >> kTagShift) == P.generation) __threadfence(); else tag = 0;
-        }
-        tag = __shfl_sync(full, tag, 0);
+        if (lane == 0) ticket = atomicAdd(&P.counters[kTicket], 1ull);
         ticket = __shfl_sync(full, ticket, 0);
-        if (tag == 0) break;
+        if (ticket >= n_rays) break;
         const DeferredRay* qp = P.queue + ticket;
-        const uint32_t q_steps = tag & ((1u << kTagShift) - 1u);
-        const uint32_t q_pixel = __ldcg(&qp->pixel);
+        const uint32_t q_steps = qp->steps;
+        const uint32_t q_pixel = qp->pixel;
         const int i = static_cast<int>(q_pixel % static_cast<uint32_t>(P.res_x));
         const int j = static_cast<int>(q_pixel / static_cast<uint32_t>(P.res_x));
         const double px = P.xs[i], py = P.ys[j];
         RayAcc a;
-        a.tau = __ldcg(&qp->tau);
-        a.inten = __ldcg(&qp->inten);
-        a.z_after = __ldcg(&qp->z_after);
+        a.tau = qp->tau;
+        a.inten = qp->inten;
+        a.z_after = qp->z_after;
         a.steps = q_steps;
         a.error = 0;
         int crossings = 0;
@@ -1024,9 +1016,16 @@ __device__ __forceinline__ int compact3(int v) {
 
 template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2, bool kRec = false>
 __device__ __forceinline__ void walk_block_body(const WalkParams& P) {
-    constexpr int kTx = 8 * kWarpsX, kTy = 4 * kWarpsY, kThreads = 32 * kWarpsX * kWarpsY;
+    constexpr int kTx = 8 * kWarpsX, kTy = 4 * kWarpsY;
+    [[maybe_unused]] constexpr int kThreads = 32 * kWarpsX * kWarpsY;
+#ifdef C5_EXPERIMENTS
     extern __shared__ __align__(64) unsigned char smem_raw[];
     BvhNode* top = reinterpret_cast<BvhNode*>(smem_raw);
+#else
+    // (staging the top BVH levels in shared memory was measured slower than letting L1 serve them:
+    // C3 6.38 ms with 0 nodes, 6.54 with 63, 6.88 with 255; profiles/r01_exp_c3_variants_b.jsonl)
+    const BvhNode* top = nullptr;
+#endif
 
     // screen-space order: macro tiles of 8 x 8 block tiles in row-major order, Morton inside, so that
     // concurrently resident blocks cover a compact patch of the image and share tets in L2
@@ -1048,12 +1047,14 @@ __device__ __forceinline__ void walk_block_body(const WalkParams& P) {
         const bool s1 = x1 >= root->xlo[1] && x0 <= root->xhi[1] && y1 >= root->ylo[1] && y0 <= root->yhi[1];
         tile_sees_mesh = s0 || s1;
     }
+#ifdef C5_EXPERIMENTS
     if (tile_sees_mesh && P.top_nodes > 0) {
         const int4* src = reinterpret_cast<const int4*>(P.nodes);
         int4* dst = reinterpret_cast<int4*>(top);
         for (int k = threadIdx.x; k < P.top_nodes * 4; k += kThreads) dst[k] = src[k];
         __syncthreads();
     }
+#endif
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = P.i0 + tile_x * kTx + (warp % kWarpsX) * 8 + (lane & 7);
@@ -1105,16 +1106,21 @@ __device__ __forceinline__ void walk_block_body(const WalkParams& P) {
     }
 }
 
+#ifdef C5_EXPERIMENTS
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 
 template <bool kF32, bool kWide, int kPipe, int kWarpsX = 2, int kWarpsY = 2, bool kRec = false>
 __device__ __forceinline__ void walk_block(const WalkParams& P) {
+#ifdef C5_EXPERIMENTS   // block timeline (C5_TRACE_FILE)
     if (P.trace && threadIdx.x == 0) P.trace[4ull * blockIdx.x] = global_ns(); // stored at once: nothing stays live
+#endif
     walk_block_body<kF32, kWide, kPipe, kWarpsX, kWarpsY, kRec>(P);
+#ifdef C5_EXPERIMENTS
     if (P.trace) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1126,33 +1132,35 @@ __device__ __forceinline__ void walk_block(const WalkParams& P) {
             rec[3] = blockIdx.x;
         }
     }
-    // tells the grazing-ray kernel (running beside this one) when no more rays can be deferred
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(&P.counters[kBlocksDone], 1ull);
-    }
+#endif
 }
 
 } // namespace
 
-// The product kernel, and register-capped variants kept for occupancy experiments
-// (C5_WALK_VARIANT=r64|r96 selects one at run time; ncu shows which is better where).
-// 7 blocks of 128 threads per SM = 72 registers: one more resident block than the 80 the compiler picks
-// on its own, measured faster (5.41 vs 5.64 ms on C3) despite a few spilled words outside the step loop
+// The product kernels. 7 blocks of 128 threads per SM = 72 registers: one more resident block than the
+// 80 the compiler picks on its own, measured faster (5.41 vs 5.64 ms on C3) despite a few spilled words
+// outside the step loop.
 __global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64(const WalkParams P) { walk_block<false, true, 0>(P); }
 // optional single-precision step geometry (north-star item (d)); entry search and accumulators stay FP64
 __global__ void __launch_bounds__(kBlock, 8) tet_walk_fp32(const WalkParams P) { walk_block<true, true, 0>(P); }
-// experiment variants (C5_WALK_VARIANT): 128-bit loads, L1 prefetch of the next step, register caps
+
+#ifdef C5_EXPERIMENTS
+// Variants measured and NOT adopted (C5_WALK_VARIANT selects one in libc5gpu_exp.so; results under
+// profiles/): 128-bit loads, L1 prefetch of the next step, 64-thread blocks, other register caps,
+// step records.
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_l128(const WalkParams P) { walk_block<false, false, 0>(P); }
 __global__ void __launch_bounds__(kBlock) tet_walk_fp64_pf(const WalkParams P) { walk_block<false, true, 1>(P); }
-// software-pipelined (measured slower: 5.85 vs 5.40 ms, 96 registers): next step's loads issued right after the exit decision
-// 64-thread blocks (one 8 x 8 pixel tile): finer-grained block scheduling for short bands
 __global__ void __launch_bounds__(64) tet_walk_fp64_b64(const WalkParams P) { walk_block<false, true, 0, 1, 2>(P); }
-__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_r72(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 6) tet_walk_fp64_r80(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, 0>(P); }
+__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_rec(const WalkParams P) { walk_block<false, true, 0, 2, 2, true>(P); }
+// Builds the four step records of every tet from its Cell (after prepare_cells: s depends on --alpha_limit).
+__global__ void __launch_bounds__(256) build_step_records(int64_t n_faces, const Cell* __restrict__ cells, StepRec* __restrict__ recs) {
+    const int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (f < n_faces) recs[f] = make_step_record(cells, f);
+}
+#endif
 
 // The walk's grid only covers the pixel rectangle that can see the mesh (a one-wave row band whose
 // grid is 60 % empty tiles fills the SMs unevenly: measured 1.60 M busy cycles on the fullest SM
@@ -1170,15 +1178,6 @@ __global__ void __launch_bounds__(256) fill_background(const WalkParams P) {
     if ((threadIdx.x & 31) == 0 && solids) atomicAdd(&P.counters[kSolidPixels], static_cast<unsigned long long>(solids));
 }
 
-// experiment: step records, one 256-bit load per tet-step (C5_WALK_VARIANT=rec)
-__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_rec(const WalkParams P) { walk_block<false, true, 0, 2, 2, true>(P); }
-
-// Builds the four step records of every tet from its Cell (after prepare_cells: s depends on --alpha_limit).
-__global__ void __launch_bounds__(256) build_step_records(int64_t n_faces, const Cell* __restrict__ cells, StepRec* __restrict__ recs) {
-    const int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (f < n_faces) recs[f] = make_step_record(cells, f);
-}
-
 // Grazing rays (deferred by the pixel kernel): persistent warps, one ray per warp at a time.
 __global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp64(const WalkParams P) { graze_block<false>(P); }
 __global__ void __launch_bounds__(32 * kGrazeWarps) grazing_rays_fp32(const WalkParams P) { graze_block<true>(P); }
@@ -1193,10 +1192,9 @@ void graze_on_host(const WalkParams& P, bool f32) {
         const int j = static_cast<int>(q.pixel / static_cast<uint32_t>(P.res_x));
         const RayAcc a = f32 ? graze_ray_serial<true>(P, q, P.xs[i], P.ys[j]) : graze_ray_serial<false>(P, q, P.xs[i], P.ys[j]);
         store_pixel(P, i, j, a.tau, a.inten, a.steps);
-        const uint32_t q_steps = q.tag & ((1u << kTagShift) - 1u);
-        P.counters[kSteps] += a.steps - q_steps;
-        P.row_cost[j] += a.steps - q_steps;
-        if (q_steps == 0 && a.steps > 0) P.counters[kHitPixels]++;
+        P.counters[kSteps] += a.steps - q.steps;
+        P.row_cost[j] += a.steps - q.steps;
+        if (q.steps == 0 && a.steps > 0) P.counters[kHitPixels]++;
         if (a.error) P.counters[kWalkErrors]++;
     }
     P.counters[kTicket] = n_rays;
@@ -1220,9 +1218,13 @@ void walk_on_host(const WalkParams& P, bool f32) {
                 continue;
             }
             const uint32_t pixel = static_cast<uint32_t>(j) * static_cast<uint32_t>(P.res_x) + static_cast<uint32_t>(i);
-            const RayResult r = f32      ? trace_ray<true, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0)
-                                : P.recs ? trace_ray<false, false, 0, true>(P, nullptr, P.xs[i], P.ys[j], pixel, 0)
-                                         : trace_ray<false, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0);
+            RayResult r;
+#ifdef C5_EXPERIMENTS
+            if (!f32 && P.recs) r = trace_ray<false, false, 0, true>(P, nullptr, P.xs[i], P.ys[j], pixel, 0);
+            else
+#endif
+            r = f32 ? trace_ray<true, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0)
+                    : trace_ray<false, false, 0>(P, nullptr, P.xs[i], P.ys[j], pixel, 0);
             if (!r.deferred) store_pixel(P, i, j, r.tau, r.inten, r.steps);
             P.counters[kSteps] += r.steps;
             P.row_cost[j] += r.steps;
@@ -1234,8 +1236,9 @@ void walk_on_host(const WalkParams& P, bool f32) {
 
 } // namespace
 
+#ifdef C5_EXPERIMENTS
 // The step records of the mesh `d` renders (its own, or its parent's for a sibling context), (re)built when
-// --alpha_limit changed. Experimental variant only: the default path never allocates them.
+// --alpha_limit changed.
 const StepRec* step_records(DeviceState& dd, double alpha_limit) {
     DeviceState& d = dd.origin ? *dd.origin : dd;
     if (d.recs_valid && d.recs_limit == alpha_limit && d.recs.n == static_cast<size_t>(4 * d.n_tets)) return d.recs.p;
@@ -1258,7 +1261,13 @@ const StepRec* step_records(DeviceState& dd, double alpha_limit) {
     d.recs_valid = true;
     return d.recs.p;
 }
+#endif
 
+// One view's rays on d.stream: background fill, the pixel kernel, then the grazing-ray kernel for the
+// rays it deferred — three launches in stream order, no kernel ever waits for another one. (Round 1
+// ran the grazing-ray kernel BESIDE the pixel kernel, spinning on the queue; CUDA promises no forward
+// progress between kernels, and with three or four views in flight the ordered form is also the faster
+// one: profiles/r02_exp_lanes_graze_after.jsonl against r02_exp_lanes_graze_beside.jsonl.)
 void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (w.precision != 64 && w.precision != 32) fail(C5_E_INVALID, "render: precision must be 64 or 32");
     const bool f32 = w.precision == 32;
@@ -1275,23 +1284,18 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.counters = d.counters.p;
     P.row_cost = d.row_cost.p;
     P.queue = d.queue.p;
-    P.queue_capacity = d.queue.n;
-    // a fresh tag per view; when the tags run out the queue is wiped (once every 2047 views)
-    if (d.queue_generation >= kTagGenerations) {
-        dev_zero(d.queue.p, d.queue.bytes(), d.stream);
-        d.queue_generation = 0;
-    }
-    P.generation = ++d.queue_generation;
     P.res_x = w.res_x;
     P.res_y = w.res_y;
     P.row_begin = w.row_begin;
     P.row_end = w.row_end;
+    int tile_x = kTileX, tile_y = kTileY;
+#ifdef C5_EXPERIMENTS
     const char* variant = std::getenv("C5_WALK_VARIANT");
     const std::string var = variant ? variant : "";
     const bool small_blocks = !f32 && var == "b64"; // 8 x 8 pixel tiles, 64 threads
-    P.recs = nullptr;
-    if (!f32 && var == "rec") P.recs = step_records(d, w.alpha_limit);
-    const int tile_x = small_blocks ? 8 : kTileX, tile_y = small_blocks ? 8 : kTileY;
+    if (small_blocks) tile_x = tile_y = 8;
+    P.recs = (!f32 && var == "rec") ? step_records(d, w.alpha_limit) : nullptr;
+#endif
     // the walk covers [i0,i1) x [j0,j1): the caller's estimate of where the mesh can be, cut to the band
     P.i0 = w.i_begin < 0 ? 0 : w.i_begin;
     P.i1 = w.i_end > w.res_x ? w.res_x : w.i_end;
@@ -1304,31 +1308,10 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     P.n_tiles_y = (P.j1 - P.j0 + tile_y - 1) / tile_y;
     P.n_macro_x = (P.n_tiles_x + 7) / 8;
     const int n_macro_y = (P.n_tiles_y + 7) / 8;
-    const int64_t n_nodes = d.n_bfaces - 1;
-    // Staging the top BVH levels in shared memory was measured SLOWER than letting L1 serve them
-    // (C3: 6.38 ms with 0 nodes, 6.54 with 63, 6.88 with 255; profiles/r01_exp_c3_variants_b.jsonl),
-    // so it is off by default; C5_TOP_NODES=n turns it on for experiments.
-    int top = 0;
-    if (const char* e = std::getenv("C5_TOP_NODES")) top = std::atoi(e);
-    if (top < 0) top = 0;
-    if (top > 1023) top = 1023;
-    P.top_nodes = kHostSim ? 0 : static_cast<int>(n_nodes < top ? n_nodes : top);
-    P.graze_cap = kGrazeList;
-    if (const char* e = std::getenv("C5_GRAZE_LIST")) { // tests shrink it to reach the overflow path on small meshes
-        const int c = std::atoi(e);
-        if (c >= 128 && c <= kGrazeList) P.graze_cap = c & ~1;
-    }
-    P.fence_stores = std::getenv("C5_STORE_FENCE") != nullptr;
-    P.query_budget = 64;
-    if (const char* e = std::getenv("C5_QUERY_BUDGET")) {
-        const int b = std::atoi(e);
-        if (b >= 1) P.query_budget = b;
-    }
-    P.serial_cap = kSerialList;
-    if (const char* e = std::getenv("C5_GRAZE_SERIAL_LIST")) {
-        const int c = std::atoi(e);
-        if (c >= 2 && c <= kSerialList) P.serial_cap = c;
-    }
+    // c5_debug_set (tests shrink these to reach the overflow paths on small meshes); defaults otherwise
+    P.graze_cap = d.opt_graze_list >= 128 && d.opt_graze_list <= kGrazeList ? (d.opt_graze_list & ~1) : kGrazeList;
+    P.query_budget = d.opt_query_budget >= 1 ? d.opt_query_budget : 64;
+    P.serial_cap = d.opt_serial_list >= 2 && d.opt_serial_list <= kSerialList ? d.opt_serial_list : kSerialList;
     P.max_steps = static_cast<int>(d.n_tets < (1 << 20) ? d.n_tets : (1 << 20));
     P.round_float = w.round_through_float;
     P.alpha_limit = w.alpha_limit;
@@ -1352,7 +1335,14 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         return;
     }
     const unsigned grid = static_cast<unsigned>(P.n_macro_x) * static_cast<unsigned>(n_macro_y) * 64u;
-    P.n_pixel_blocks = grid;
+    size_t smem = 0;
+#ifdef C5_EXPERIMENTS
+    const int64_t n_nodes = d.n_bfaces - 1;
+    int top = 0;
+    if (const char* e = std::getenv("C5_TOP_NODES")) top = std::atoi(e);
+    top = top < 0 ? 0 : top > 1023 ? 1023 : top;
+    P.top_nodes = static_cast<int>(n_nodes < top ? n_nodes : top);
+    smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
     P.trace = nullptr;
     if (std::getenv("C5_TRACE_FILE") && d.trace_launches < kTraceLaunches) { // block timeline of the first launches
         if (d.trace.n == 0) {
@@ -1365,9 +1355,6 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
             d.trace_launches++;
         }
     }
-    // fork: the grazing-ray kernel may start as soon as the counters are zero, i.e. beside the pixel kernel
-    C5_CUDA(cudaEventRecord(d.graze_fork, d.stream));
-    const size_t smem = static_cast<size_t>(P.top_nodes) * sizeof(BvhNode);
     if (f32) {
         tet_walk_fp32<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (small_blocks) {
@@ -1380,8 +1367,6 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp64_pf<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r80") {
         tet_walk_fp64_r80<<<grid, kBlock, smem, d.stream>>>(P);
-    } else if (var == "r72") {
-        tet_walk_fp64_r72<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r64") {
         tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r96") {
@@ -1389,28 +1374,27 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     } else {
         tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
     }
+#else
+    if (f32) {
+        tet_walk_fp32<<<grid, kBlock, smem, d.stream>>>(P);
+    } else {
+        tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
+    }
+#endif
     C5_CUDA(cudaGetLastError());
+    if (w.mark_walk_done) C5_CUDA(cudaEventRecord(w.mark_walk_done, d.stream));
+    if (w.mark_walk_done_tl) C5_CUDA(cudaEventRecord(w.mark_walk_done_tl, d.stream));
 
-    // Rays the pixel kernel deferred. The queue length lives on the device, so the launch is a fixed
-    // grid of persistent warps that draw tickets; with an empty queue it costs one short launch.
+    // Rays the pixel kernel deferred: a fixed grid of persistent warps that draw tickets.
     if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
     const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * 4u;
     count_launch();
-    // beside the pixel kernel, or (c5_set_concurrent_grazing(ctx, 0) / C5_GRAZE_SERIAL) after it on the same stream
-    const bool beside = d.graze_beside && std::getenv("C5_GRAZE_SERIAL") == nullptr;
-    cudaStream_t gs = beside ? d.graze_stream : d.stream;
-    if (beside) C5_CUDA(cudaStreamWaitEvent(gs, d.graze_fork, 0));
     if (f32) {
-        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, gs>>>(P);
+        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
     } else {
-        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, gs>>>(P);
+        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
     }
     C5_CUDA(cudaGetLastError());
-    if (beside) {
-        // join: whatever follows on the caller's stream (the next view rewrites the vertices) waits for it
-        C5_CUDA(cudaEventRecord(d.graze_join, gs));
-        C5_CUDA(cudaStreamWaitEvent(d.stream, d.graze_join, 0));
-    }
 }
 
 } // namespace c5

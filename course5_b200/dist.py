@@ -156,12 +156,16 @@ class BandRenderer:
             self._lanes = [(self.ctx, torch.cuda.Stream(self.device) if cuda else None)]
             for _ in range(self.n_lanes - 1):
                 self._lanes.append((self.ctx.sibling(), torch.cuda.Stream(self.device) if cuda else None))
-            if self.world > 1:
-                # NCCL kernels (high-priority stream) share the device: a kernel of ours that spins until
-                # another of ours has finished could hold what they need while that other one queues behind them
-                for c, _ in self._lanes:
-                    c.set_concurrent_grazing(False)
         return self._lanes[k % len(self._lanes)]
+
+    def enable_timeline(self, n_views: int):
+        """Keeps the phase moments of the last n_views views of every lane (c5_debug_set "timeline")."""
+        self._lane(0)
+        self.ctx.debug_set("timeline", n_views)      # reaches the siblings (the other lanes) too
+
+    def timeline(self, origin_event: int) -> list[np.ndarray]:
+        """Per lane: (n, 6) ms since origin_event — start, rotated, refitted, mask, pixel kernel, grazing-ray kernel."""
+        return [c.timeline(origin_event) for c, _ in self._lanes]
 
     def kernel_launches(self) -> int:
         """Kernels launched so far by every context this renderer drives."""

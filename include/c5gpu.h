@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-#define C5_ABI_VERSION 1
+#define C5_ABI_VERSION 2
+#define C5_MAX_IN_FLIGHT 8
 #define C5_MAX_ROT 8
 
 typedef struct c5_ctx c5_ctx;
@@ -90,6 +91,8 @@ typedef struct c5_stats {
     float ms_total;         /* whole call on the device timeline */
     int32_t n_devices;
     int32_t grazing_rays;   /* rays with so many crossings that the grazing-ray kernel finished them */
+    float ms_graze;         /* the grazing-ray kernel's share of ms_walk */
+    int32_t reserved;
 } c5_stats;
 
 typedef struct c5_mesh_info {
@@ -125,8 +128,24 @@ int c5_mesh_info_get(const c5_ctx* ctx, c5_mesh_info* out);
  * rotations main.cpp:104-107 does beforehand. out: caller-owned HOST buffer of
  * res_y * res_x * 2 doubles, x fastest, {tau, I} per pixel — the vtkImageData layout of
  * object2d.cpp:17-21 (with a row band: only rows [row_begin,row_end) are written, at their
- * final position). stats may be NULL. */
+ * final position). stats may be NULL. If `out` is page-locked (cudaHostAlloc, cudaHostRegister or
+ * c5_host_register) and 16-byte aligned the walk kernel stores its pixels straight into it over
+ * PCIe; any other buffer gets a device-to-host copy. Equivalent to c5_render_submit + c5_render_wait. */
 int c5_render(c5_ctx* ctx, const c5_view* view, double* out, c5_stats* stats);
+
+/* The same pass, asynchronous: c5_render_submit enqueues the view and returns a ticket at once;
+ * c5_render_wait blocks until that view's image is complete in `out` and fills stats (may be NULL).
+ * Up to c5_set_views_in_flight() views (default 3, at most C5_MAX_IN_FLIGHT) may be submitted before
+ * the first is waited for; each is rendered by a lane of its own — per-view device state plus a
+ * stream; the mesh is shared — so that consecutive views overlap on the device: the tail of one
+ * view's walk and its grazing-ray kernel run beside the next view's rays. `out` (page-locked for
+ * any overlap: a copy to pageable memory blocks the submitting thread) must stay valid and untouched
+ * until the wait returns; *view is copied. One more submit than lanes returns C5_E_STATE. Tickets may
+ * be waited for in any order, once each. A sweep is: submit k+1, k+2; wait k; write frame k; ...
+ * Single-device contexts that are not siblings. */
+int c5_render_submit(c5_ctx* ctx, const c5_view* view, double* out, uint64_t* ticket);
+int c5_render_wait(c5_ctx* ctx, uint64_t ticket, c5_stats* stats);
+int c5_set_views_in_flight(c5_ctx* ctx, int32_t n);
 
 /* Test/diagnostic variant: same pass, but also returns per-pixel tets crossed and the solid
  * mask (each res_y * res_x, x fastest; either may be NULL). With view->round_through_float = 0
@@ -137,7 +156,8 @@ int c5_render_raw(c5_ctx* ctx, const c5_view* view, double* out, uint32_t* steps
 /* Device-resident variant for callers that own device memory (e.g. a torch tensor that an NCCL
  * gather will read): d_out is a DEVICE pointer on the context's first device to
  * (row_end - row_begin) * res_x * 2 doubles — the band only. Work is enqueued on `stream`
- * (a cudaStream_t; NULL = the legacy default stream). With stats != NULL the call returns
+ * (a cudaStream_t; NULL = the legacy default stream). d_out must be 16-byte aligned (pixels are
+ * stored as one 128-bit word; C5_E_INVALID otherwise). With stats != NULL the call returns
  * after the stream has been synchronised, so stats (and c5_last_row_cost) are final. With
  * stats == NULL nothing is read back and the call returns as soon as the work is enqueued: the
  * caller orders later work on the same stream (successive views and an NCCL gather then pipeline
@@ -155,16 +175,6 @@ int c5_last_row_cost(c5_ctx* ctx, uint64_t* rows, int32_t n_rows);
  * throughput is then set by the work, not by the last rays of every view. Uploads go through the
  * parent (a sibling picks them up at its next render); destroy siblings before the parent. */
 int c5_create_sibling(c5_ctx* parent, c5_ctx** out);
-
-/* The grazing-ray kernel normally runs BESIDE the pixel kernel (side stream, spinning on a queue
- * the pixel kernel fills) and ends when that kernel has finished. CUDA gives no forward-progress
- * guarantee between kernels: if something of higher stream priority needs the resources the
- * spinning blocks hold — an NCCL kernel, say — while the pixel kernel's remaining blocks queue
- * behind it, nothing moves. on = 0 runs the grazing-ray kernel AFTER the pixel kernel on the same
- * stream (no kernel waits for another; about 0.3 ms more per 2400 x 1800 view when views are
- * rendered one at a time, nothing when two are in flight). Use 0 whenever other kernels share the
- * device; course5_b200/dist.py does for every multi-process run. Default 1. */
-int c5_set_concurrent_grazing(c5_ctx* ctx, int32_t on);
 
 /* ---- one image, several processes (one process per GPU) -----------------------------------------
  * Row bands are independent (plane.cpp:161-169 has no cross-pixel state), so N processes can
@@ -188,8 +198,25 @@ int c5_image_close(c5_ctx* ctx, void* d_ptr); /* frees (owner) or unmaps (import
 int c5_host_register(c5_ctx* ctx, void* ptr, uint64_t bytes);
 int c5_host_unregister(c5_ctx* ctx, void* ptr);
 
-/* Number of kernels this library has launched on behalf of ctx since creation. */
+/* Number of kernels this library has launched on behalf of ctx (and the lanes c5_render_submit
+ * made for it) since creation. */
 uint64_t c5_kernel_launches(const c5_ctx* ctx);
+
+/* ---- diagnostics (tests, profiling scripts; no effect on results) ----------------------------------
+ * c5_debug_set(ctx, key, value) — applies to ctx, its lanes and its siblings:
+ *   "graze_list"    entries one cooperative collection of the grazing-ray kernel holds (128..256, 0 = default):
+ *                   tests shrink it to reach the overflow path on small meshes
+ *   "query_budget"  BVH nodes a thread of the pixel kernel may visit per search before it hands the
+ *                   ray to the grazing-ray kernel (>= 1, 0 = default 64)
+ *   "no_zero_copy"  1: page-locked output buffers get a device-to-host copy like pageable ones
+ *   "timeline"      n > 0: keep the phase events of the last n views of every lane (0 = off)
+ * Unknown keys return C5_E_INVALID.
+ * c5_timeline_read: for the last views rendered by ctx itself (not its lanes; oldest first, at most
+ * max_views), six times in milliseconds since `origin` (a cudaEvent_t the caller recorded earlier
+ * on the same device): view start, vertices rotated, BVH refitted, solid mask done, pixel kernel
+ * done, grazing-ray kernel done. Synchronises with the last of them. */
+int c5_debug_set(c5_ctx* ctx, const char* key, int64_t value);
+int c5_timeline_read(c5_ctx* ctx, void* origin, float* ms_out, int32_t max_views, int32_t* n_views);
 
 #ifdef __cplusplus
 }

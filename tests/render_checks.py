@@ -10,8 +10,12 @@ from course5_b200 import api, synth
 from parity import ABS_FLOOR_FP32, REL_TOL_FP32, assert_image_parity, assert_same_hits
 
 
-def render_raw(lib, mesh, res_x, res_y, *, solids=None, raw=True, **flags):
+def render_raw(lib, mesh, res_x, res_y, *, solids=None, raw=True, debug=None, **flags):
+    """debug: {key: value} for c5_debug_set (tests shrink list sizes / search budgets to reach the
+    overflow paths on small meshes)."""
     with api.Context(devices=(0,), lib=lib) as ctx:
+        for key, value in (debug or {}).items():
+            ctx.debug_set(key, value)
         ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
         if solids is not None:
             ctx.upload_solids(solids[0], True)
@@ -38,8 +42,8 @@ def check_golden(lib, name):
     assert img.stats["hit_pixels"] == int((gold["steps"] > 0).sum())
 
 
-def check_against_port(lib, port, mesh, res_x, res_y, flags, *, solids=None, steps_exact=True):
-    img = render_raw(lib, mesh, res_x, res_y, solids=solids, **flags)
+def check_against_port(lib, port, mesh, res_x, res_y, flags, *, solids=None, steps_exact=True, debug=None):
+    img = render_raw(lib, mesh, res_x, res_y, solids=solids, debug=debug, **flags)
     want = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=res_x, res_y=res_y,
                        solid_rot=None if solids is None else solids[0],
                        solid_static=None if solids is None else solids[1], **flags)
@@ -217,25 +221,16 @@ def check_solid_mask_high_resolution(lib, port, res=(1200, 900), views=((0.4, 0.
         assert np.array_equal(np.isnan(got.tau), want.solid.astype(bool))
 
 
-def check_grazing_rays(lib, port, *, n=12, res=(240, 180), env_name="C5_GRAZE_SERIAL_LIST", env_value="5"):
+def check_grazing_rays(lib, port, *, n=12, res=(240, 180), debug_key="serial_list", debug_value=5):
     """Views that look along a lattice axis see the jittered side walls edge-on: rays there leave
     and re-enter the mesh once per cell. The pixel kernel hands them to the grazing-ray kernel
     (c5_stats.grazing_rays); the result must still match the oracle, and must not depend on how many
     entry faces one collection can hold (the overflow path keeps the lowest part and asks again)."""
-    import os
     mesh = synth.kuhn_cube(n, seed=48)
     for flags in (dict(X=0.5, Y=0.0), dict(X=0.0, Y=0.5)):
         img, _ = check_against_port(lib, port, mesh, res[0], res[1], flags)
         assert img.stats["grazing_rays"] > 0
-        old = os.environ.get(env_name)
-        os.environ[env_name] = env_value
-        try:
-            small = render_raw(lib, mesh, res[0], res[1], **flags)
-        finally:
-            if old is None:
-                del os.environ[env_name]
-            else:
-                os.environ[env_name] = old
+        small = render_raw(lib, mesh, res[0], res[1], debug={debug_key: debug_value}, **flags)
         assert small.stats["grazing_rays"] == img.stats["grazing_rays"]
         assert np.array_equal(small.image, img.image)
         assert np.array_equal(small.steps, img.steps)
@@ -278,50 +273,125 @@ def check_search_budget(lib, port, *, n=10, res=(200, 150)):
     """A BVH search that exceeds its node budget hands the ray to the grazing-ray kernel (also before
     its first step). With a budget of a few nodes nearly every ray goes that way; the image must
     still match the oracle, hit counts and step counts included."""
-    import os
     mesh = synth.kuhn_cube(n, seed=55, scalars="sphere", carve_sphere=True)   # a cavity: rays re-enter
     flags = dict(X=0.3, Y=0.4)
     base = render_raw(lib, mesh, res[0], res[1], **flags)
-    old = os.environ.get("C5_QUERY_BUDGET")
-    try:
-        for budget in ("3", "12"):
-            os.environ["C5_QUERY_BUDGET"] = budget
-            img, want = check_against_port(lib, port, mesh, res[0], res[1], flags)
-            assert img.stats["grazing_rays"] > base.stats["grazing_rays"]
-            assert img.stats["hit_pixels"] == base.stats["hit_pixels"] == int(want.hit.sum())
-    finally:
-        if old is None:
-            del os.environ["C5_QUERY_BUDGET"]
-        else:
-            os.environ["C5_QUERY_BUDGET"] = old
+    for budget in (3, 12):
+        img, want = check_against_port(lib, port, mesh, res[0], res[1], flags, debug={"query_budget": budget})
+        assert img.stats["grazing_rays"] > base.stats["grazing_rays"]
+        assert img.stats["hit_pixels"] == base.stats["hit_pixels"] == int(want.hit.sum())
 
 
-def check_step_record_variant(lib, port, *, n=10, res=(200, 150)):
-    """Experimental walk variant C5_WALK_VARIANT=rec (one 32-byte step record per tet and entry face,
-    alpha and s cut to 48 bits): same hit sets and step counts, values inside the parity gate; and the
-    packing itself round-trips."""
+def check_submit_wait(lib, pinned=None):
+    """c5_render_submit / c5_render_wait: several views in flight on lanes that share the mesh give the
+    images one-at-a-time c5_render gives, tickets can be waited for in any order, one submit too many
+    is C5_E_STATE, and stats / row costs belong to the ticket waited for. `pinned(shape)` makes a
+    page-locked array on a GPU box (the walk then stores in place); pageable arrays otherwise."""
+    alloc = pinned or (lambda shape: np.zeros(shape))
+    mesh = synth.kuhn_cube(9, seed=64)
+    solid = synth.kuhn_cube(2, seed=3, side=0.2, centre=(1.0, 0.1, 0.0)).tet_points()
+    views_flags = [dict(X=0.5, Y=0.0), dict(X=0.4, Y=0.3), dict(X=0.0, Y=0.5, alpha_limit=1.1), dict(X=0.45, Y=1.2),
+                   dict(X=0.3, Y=1.7)]
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        ctx.upload_solids(solid, True)
+        views = [api.make_view(160, 120, lib=lib, **f) for f in views_flags]
+        want = [ctx.render(v) for v in views]
+        ctx.set_views_in_flight(3)
+        outs = [alloc((120, 160, 2)) for _ in views]
+        for o in outs:
+            o[:] = -7.0
+        t = [ctx.render_submit(views[k], outs[k]) for k in range(3)]
+        with pytest.raises(api.C5Error) as e:
+            ctx.render_submit(views[3], outs[3])                       # three lanes, three views in flight
+        assert e.value.code == api.E_STATE
+        with pytest.raises(api.C5Error) as e:
+            ctx.render_device(views[0], 16, 0)                         # lane 0 is busy
+        assert e.value.code == api.E_STATE
+        st1 = ctx.render_wait(t[1])                                    # any order
+        assert st1["tet_steps"] == want[1][1]["tet_steps"] and st1["solid_pixels"] == want[1][1]["solid_pixels"]
+        assert int(ctx.last_row_cost(120).sum()) == st1["tet_steps"]
+        t.append(ctx.render_submit(views[3], outs[3]))                 # the freed lane
+        st0 = ctx.render_wait(t[0])
+        t.append(ctx.render_submit(views[4], outs[4]))
+        stats = {0: st0, 1: st1}
+        for k in (2, 3, 4):
+            stats[k] = ctx.render_wait(t[k])
+        with pytest.raises(api.C5Error):
+            ctx.render_wait(t[2])                                      # once each
+        for k in range(5):
+            assert np.array_equal(outs[k], want[k][0], equal_nan=True), f"view {k}"
+            assert stats[k]["tet_steps"] == want[k][1]["tet_steps"]
+        assert len({*t}) == 5 and all(x > 0 for x in t)
+        assert ctx.kernel_launches() > 0
+        # a sweep: two views ahead, bands too
+        ctx.set_views_in_flight(2)
+        band = [api.make_view(160, 120, lib=lib, row_begin=30, row_end=90, **f) for f in views_flags]
+        out = [alloc((120, 160, 2)) for _ in range(2)]
+        tick = [ctx.render_submit(band[0], out[0])]
+        for k in range(1, 5):
+            tick.append(ctx.render_submit(band[k], out[k % 2]))
+            ctx.render_wait(tick[k - 1])
+            assert np.array_equal(out[(k - 1) % 2][30:90], want[k - 1][0][30:90], equal_nan=True)
+        ctx.render_wait(tick[4])
+        assert np.array_equal(out[0][30:90], want[4][0][30:90], equal_nan=True)
+        with pytest.raises(api.C5Error):
+            ctx.set_views_in_flight(api.MAX_IN_FLIGHT + 1)
+        # a sibling has no lanes of its own
+        sib = ctx.sibling()
+        try:
+            with pytest.raises(api.C5Error) as e:
+                sib.render_submit(views[0], outs[0])
+            assert e.value.code == api.E_INVALID
+        finally:
+            sib.close()
+
+
+def check_output_alignment(lib, device_buffer=None):
+    """Pixels are stored as one 128-bit word: a device buffer that is not 16-byte aligned is refused
+    (C5_E_INVALID, not a misaligned-address fault), a host buffer that is not takes the copy path."""
+    mesh = synth.kuhn_cube(5, seed=65)
+    with api.Context(devices=(0,), lib=lib) as ctx:
+        ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+        v = api.make_view(64, 48, X=0.4, Y=0.2, lib=lib)
+        want, _ = ctx.render(v)
+        backing = np.zeros(64 * 48 * 2 + 1)
+        odd = backing[1:] if backing.ctypes.data % 16 == 0 else backing[:-1]     # 8-byte aligned only
+        assert odd.ctypes.data % 16 == 8
+        got, _ = ctx.render(v, out=odd.reshape(48, 64, 2))
+        assert np.array_equal(got, want)
+        if device_buffer is not None:
+            ptr = device_buffer(64 * 48 * 16 + 16)
+            with pytest.raises(api.C5Error) as e:
+                ctx.render_device(v, ptr + 8, 0)
+            assert e.value.code == api.E_INVALID
+            ctx.render_device(v, ptr, 0)
+
+
+# ---- the UNMODIFIED reference at the benchmarked sizes -------------------------------------------
+
+def reference_process(name, overrides, out_path, timeout=1500):
+    """oracle/_ref on configuration `name` (one view per dict of flag overrides) in a process of its
+    own (tests/ref_runner.py: the reference reports a degenerate ray by std::terminate). Returns the
+    saved arrays."""
+    import json
     import os
-    old = os.environ.get("C5_WALK_VARIANT")
-    os.environ["C5_WALK_VARIANT"] = "rec"
-    try:
-        for mesh, flags in ((synth.kuhn_cube(n, seed=56), dict(X=0.0, Y=0.0)),
-                            (synth.kuhn_cube(n, seed=57, grade_beta=1.5), dict(X=0.45, Y=1.2, alpha_limit=0.9)),
-                            (synth.kuhn_cube(n, seed=58, scalars="sphere", carve_sphere=True), dict(X=0.3, Y=0.4))):
-            img, want = check_against_port(lib, port, mesh, res[0], res[1], flags)
-            assert img.stats["tet_steps"] > 0
-        # a second alpha_limit on the same context rebuilds the records (s depends on it)
-        mesh = synth.kuhn_cube(n, seed=56)
-        with api.Context(devices=(0,), lib=lib) as ctx:
-            ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
-            for limit in (2.5, 0.6, 2.5):
-                v = api.make_view(res[0], res[1], X=0.4, Y=0.2, alpha_limit=limit, lib=lib, round_through_float=0)
-                got = ctx.render_raw(v)
-                ref = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=res[0], res_y=res[1], X=0.4, Y=0.2,
-                                  alpha_limit=limit)
-                assert_same_hits(got.steps, ref.steps)
-                assert_image_parity(got.tau, got.inten, ref.tau, ref.inten)
-    finally:
-        if old is None:
-            del os.environ["C5_WALK_VARIANT"]
-        else:
-            os.environ["C5_WALK_VARIANT"] = old
+    import subprocess
+    import sys
+    runner = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_runner.py")
+    p = subprocess.run([sys.executable, runner, name, str(out_path), json.dumps(overrides)],
+                       capture_output=True, text=True, timeout=timeout)
+    assert p.returncode == 0, f"the reference did not finish on {name} {overrides}: rc {p.returncode}\n{p.stderr[-2000:]}"
+    return np.load(str(out_path))
+
+
+def assert_matches_reference(img, r, k, what=""):
+    """The whole parity gate against view k of a reference_process() result: solid masks and hit sets
+    identical, per-pixel tets crossed identical, tau and I within 1e-9 relative (+1e-13) of the
+    reference's pre-cast doubles."""
+    assert np.array_equal(img.solid, r[f"solid{k}"]), f"{what}solid (NaN) masks differ"
+    assert_same_hits(img.steps, r[f"steps{k}"], what=what)
+    assert np.array_equal(img.steps, r[f"steps{k}"]), f"{what}per-pixel tets crossed differ"
+    assert img.stats["tet_steps"] == int(r[f"total_steps{k}"])
+    assert img.stats["walk_errors"] == 0
+    assert_image_parity(img.tau, img.inten, r[f"tau{k}"], r[f"inten{k}"], what=what)

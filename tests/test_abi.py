@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(gpu_lib):
     for name in names:
         assert hasattr(gpu_lib, name), f"{name} is declared in c5gpu.h but not exported"
     assert sorted(api.SYMBOLS) == names, "course5_b200.api.SYMBOLS is out of sync with include/c5gpu.h"
-    assert gpu_lib.c5_abi_version() == 1
+    assert gpu_lib.c5_abi_version() == 2
 
 
 def test_ctypes_structs_match_the_c_layout(tmp_path):
@@ -39,6 +39,7 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
         'printf("%zu %zu %zu %zu %zu\\n", sizeof(c5_view), sizeof(c5_stats), sizeof(c5_mesh_info), '
         "sizeof(c5_rotation), offsetof(c5_view, alpha_limit));\n"
         'printf("%zu %zu %zu\\n", offsetof(c5_view, rot), offsetof(c5_view, row_begin), offsetof(c5_stats, ms_rotate));\n'
+        'printf("%zu\\n", offsetof(c5_stats, ms_graze));\n'
         "return 0;}\n")
     exe = tmp_path / "layout"
     subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
@@ -47,7 +48,7 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
     got = [int(x) for x in out]
     want = [C.sizeof(api.View), C.sizeof(api.Stats), C.sizeof(api.MeshInfo), C.sizeof(api.Rotation),
             api.View.alpha_limit.offset, api.View.rot.offset, api.View.row_begin.offset,
-            api.Stats.ms_rotate.offset]
+            api.Stats.ms_rotate.offset, api.Stats.ms_graze.offset]
     assert got == want
 
 

@@ -36,8 +36,12 @@ def test_search_budget(hostsim_lib, port):
     rc.check_search_budget(hostsim_lib, port)
 
 
-def test_step_record_variant(hostsim_lib, port):
-    rc.check_step_record_variant(hostsim_lib, port)
+def test_submit_wait_lanes(hostsim_lib):
+    rc.check_submit_wait(hostsim_lib)
+
+
+def test_misaligned_output_is_rejected_or_copied(hostsim_lib):
+    rc.check_output_alignment(hostsim_lib)
 
 
 def test_graded_mesh(hostsim_lib, port):

@@ -3,23 +3,27 @@
 ray pass at 2400 x 1800 (BASELINE.json `metric`, configs[2]: synthetic 8M-tet grid, 2400 x 1800,
 --alpha_limit 3.0 -X 0.5, plus the Roche lobe and sphere the reference always renders).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py [--gpus N] [--steps K] [--warmup W]                    # this repo's CUDA path
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # the reference's OpenMP path
 
-A "step" is one view: rotate -> BVH refit -> solid mask -> entry + tet walk (-> band gather at N > 1).
-  value   tet-steps/s with everything resident in HBM, output left on the device (CUDA events on the
-          launching stream, max over ranks).
-  e2e     the same metric through the C-ABI call a user makes (c5_render) with a pinned HOST output
-          buffer: view parameters go host->device, the image device->host, inside the timed region.
-  roofline  the walk kernel: algorithmic bytes (72 B per tet-step + 16 B per pixel, SURVEY.md §8d /
-          DESIGN.md) / its CUDA-event time, against the measured HBM copy peak.
+A "step" is one view: rotate -> BVH refit -> solid mask -> entry + tet walk -> grazing rays (at N > 1
+each rank renders a row band and the walk kernels store their pixels into rank 0's image over NVLink).
+  value     tet-steps/s with everything resident in HBM, output left on the device (CUDA events on
+            the launching stream, max over ranks).
+  e2e       the same metric through the C-ABI calls a user makes (c5_render_submit / c5_render_wait)
+            with page-locked HOST images: view parameters go host->device, the image device->host,
+            inside the timed region; every image is complete in host memory when its wait returns.
+  roofline  the walk kernels: algorithmic bytes (72 B per tet-step + 16 B per pixel, SURVEY.md §8d /
+            DESIGN.md) / their CUDA-event time, against the measured HBM copy peak.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, built from /root/reference in the build
-          container) timed on this box's host cores on the same workload (N = 1, rank 0 only).
+            container) on this box's host cores on the SAME workload at the SAME resolution
+            (N = 1, rank 0 only), and `parity`: this run's image held against the reference's.
 The oracle is only ever the thing compared against or the baseline — never the thing measured as ours.
 """
 from __future__ import annotations
 
 import argparse
+import collections
 import json
 import os
 import sys
@@ -33,9 +37,9 @@ sys.path.insert(0, ROOT)
 
 from course5_b200 import api, synth  # noqa: E402
 
-WORKLOAD = "C3"
 BYTES_PER_STEP = 72      # 16 B connectivity + 16 B neighbours + 24 B one new vertex + 16 B (alpha, Q)
 BYTES_PER_PIXEL = 16     # {tau, I} doubles written
+REL_TOL, ABS_FLOOR = 1e-9, 1e-13   # the parity gate (tests/parity.py, BASELINE.json north_star)
 
 
 def measured_hbm_peak():
@@ -55,11 +59,6 @@ def ncu_capture():
             return json.load(f)
     except Exception:
         return {}
-
-
-def ncu_traffic_per_launch():
-    """dram bytes per walk launch from the committed ncu capture, if one exists."""
-    return ncu_capture().get("dram_bytes_per_launch")
 
 
 class ClockSampler(threading.Thread):
@@ -113,8 +112,8 @@ class ClockSampler(threading.Thread):
 
 class Watchdog(threading.Thread):
     """Ends the process if the run stops making progress. A multi-GPU run that deadlocks (a collective
-    some rank never joins, a kernel that spins for ever) would otherwise sit on its GPUs until an
-    outer limit kills it; this way it fails fast, says in which phase, and frees the devices."""
+    some rank never joins) would otherwise sit on its GPUs until an outer limit kills it; this way it
+    fails fast, says in which phase, and frees the devices."""
 
     def __init__(self, rank: int, limit_s: float):
         super().__init__(daemon=True)
@@ -140,11 +139,6 @@ class Watchdog(threading.Thread):
                 os._exit(3)
 
 
-def workload():
-    mesh, view = synth.make_config(WORKLOAD)
-    return mesh, view
-
-
 def reference_solids(D):
     """The reference's Roche lobe + sphere from the host-side generator (bit-identical to the
     reference's own, tests/test_host.py)."""
@@ -152,88 +146,114 @@ def reference_solids(D):
     return hostlib.make_solids(D)
 
 
+def config_dict(name, mesh, view):
+    """The workload, in the same words for both arms (what ran it goes under `execution`)."""
+    return {
+        "workload": (f"{name}: synthetic Kuhn-split grid, {mesh.n_tets} tets / {mesh.n_points} points, "
+                     f"{view['res_x']}x{view['res_y']}, -X {view['X']} -Y {view['Y']} --alpha_limit "
+                     f"{view['alpha_limit']}, reference Roche lobe + sphere as solids"),
+        "res_x": view["res_x"], "res_y": view["res_y"], "n_tets": mesh.n_tets, "n_points": mesh.n_points,
+        "flags": {k: view[k] for k in ("X", "Y", "D", "I", "alpha_limit")},
+        "l2": "inputs larger than L2 (cell records alone are 64 B x n_tets >> 126 MB); no explicit flush",
+    }
+
+
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU implementation of the path on this box's host cores
+# the reference's own CPU implementation of the path on this box's host cores
 # ------------------------------------------------------------------------------------------------
 
-def reference_sample(view):
-    """Bounded sample of the workload for the CPU arms: same mesh, same flags, same solids, at half
-    the linear resolution (1/4 of the pixels) so that a step is seconds, not half a minute."""
-    return dict(view, res_x=view["res_x"] // 2, res_y=view["res_y"] // 2)
-
-
-def time_reference(mesh, view, *, steps, warmup):
+def time_reference(mesh, view, *, steps, warmup, raw=False, keep_image=False, tick=None):
+    """oracle/_ref (the unmodified reference) — or, where it was never built, the C restatement — on
+    the workload at its own resolution. raw=False is the reference's timed flow (plane ctor +
+    find_intersections + trace_rays, main.cpp:126-130); raw=True drives the same per-pixel loop
+    (plane.cpp:161-169) from the harness so the pre-cast doubles survive for the parity gate."""
     from oracle import refbind
     cores = os.cpu_count() or 1
     threads = min(32, cores)           # MAX_NUMBER_OF_THREADS = 32 (config.hpp:39)
     tet_pts = mesh.tet_points()
     kind = "reference" if os.path.exists(refbind.REF_SO) else "port"
     flags = dict(X=view["X"], Y=view["Y"], D=view["D"], I=view["I"], alpha_limit=view["alpha_limit"])
-    times, total_steps = [], 0
+    times, img = [], None
     if kind == "reference":
         ref = refbind.Ref()
         for k in range(warmup + steps):
+            if tick:
+                tick(f"reference step {k - warmup}" if k >= warmup else f"reference warm-up {k}")
             img = ref.render(tet_pts, mesh.alpha, mesh.q, res_x=view["res_x"], res_y=view["res_y"],
-                             threads=threads, solids=1, raw=False, **flags)
-            # the reference's own timed region: plane ctor + find_intersections + trace_rays (main.cpp:126-130)
-            t = img.timings["ctor"] + img.timings["find"] + img.timings["trace"]
+                             threads=threads, solids=1, raw=raw, **flags)
             if k >= warmup:
-                times.append(t)
-            total_steps = img.total_steps
+                times.append(img.timings["ctor"] + img.timings["find"] + img.timings["trace"])
     else:
         port = refbind.Port()
         threads = cores
+        roche, sphere = reference_solids(view["D"])
         for k in range(warmup + steps):
-            img = port.render(tet_pts, mesh.alpha, mesh.q, res_x=view["res_x"], res_y=view["res_y"],
-                              threads=threads, X=flags["X"], Y=flags["Y"], I=flags["I"],
-                              alpha_limit=flags["alpha_limit"])
+            if tick:
+                tick(f"port step {k - warmup}" if k >= warmup else f"port warm-up {k}")
+            img = port.render(tet_pts, mesh.alpha, mesh.q, res_x=view["res_x"], res_y=view["res_y"], threads=threads,
+                              X=flags["X"], Y=flags["Y"], I=flags["I"], alpha_limit=flags["alpha_limit"],
+                              solid_rot=roche, solid_static=sphere)
             if k >= warmup:
                 times.append(img.timings["trace"])
-            total_steps = img.total_steps
     t_step = float(np.mean(times))
-    return dict(value=total_steps / t_step, seconds_per_step=t_step, tet_steps=total_steps, kind=kind,
-                cores=threads, pixels=view["res_x"] * view["res_y"])
+    return dict(value=img.total_steps / t_step, seconds_per_step=t_step, tet_steps=img.total_steps, kind=kind,
+                cores=threads, pixels=view["res_x"] * view["res_y"], image=img if keep_image else None)
+
+
+def parity_record(ours, want, *, against):
+    """This run's image (api.RawImage, pre-cast doubles) against the oracle's (refbind.OracleImage):
+    the gate of tests/parity.py, as numbers. `ok` is the conjunction the tests assert."""
+    got = ours.image
+    solid_equal = bool(np.array_equal(ours.solid.astype(bool), want.solid.astype(bool)))
+    hits_equal = bool(np.array_equal(ours.steps > 0, want.steps > 0))
+    steps_equal = bool(np.array_equal(ours.steps, want.steps))
+    worst_rel, worst_abs, bad = 0.0, 0.0, 0
+    for comp, ref in ((got[..., 0], want.tau), (got[..., 1], want.inten)):
+        nan = np.isnan(ref)
+        err = np.abs(np.where(nan, 0.0, comp - ref))
+        mag = np.abs(np.where(nan, 0.0, ref))
+        bad += int((err > REL_TOL * mag + ABS_FLOOR).sum()) + int((np.isnan(comp) != nan).sum())
+        worst_abs = max(worst_abs, float(err.max()))
+        # relative error where the value is not itself at the rounding floor of a silhouette-grazing pixel
+        worst_rel = max(worst_rel, float(np.where(mag >= 1e-3, err / np.maximum(mag, 1e-3), 0.0).max()))
+    rec = {"against": against, "gate": f"|got - want| <= {REL_TOL:g} |want| + {ABS_FLOOR:g} per pixel on pre-cast doubles; "
+                                       "identical hit/miss sets, solid masks and per-pixel tets crossed",
+           "pixels": int(want.steps.size), "hit_pixels": int((want.steps > 0).sum()),
+           "solid_pixels": int(want.solid.astype(bool).sum()),
+           "hit_sets_equal": hits_equal, "solid_masks_equal": solid_equal, "per_pixel_steps_equal": steps_equal,
+           "tet_steps": [int(ours.stats["tet_steps"]), int(want.total_steps)],
+           "pixels_out_of_tolerance": bad, "max_abs_err": worst_abs, "max_rel_err_where_value_ge_1e-3": worst_rel}
+    rec["ok"] = bool(hits_equal and solid_equal and steps_equal and bad == 0 and
+                     int(ours.stats["tet_steps"]) == int(want.total_steps))
+    return rec
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mesh, view = workload()
-    sample = reference_sample(view)
-    r = time_reference(mesh, sample, steps=args.steps, warmup=args.warmup)
-    sample_txt = (f"{WORKLOAD} mesh ({mesh.n_tets} tets) + reference solids, same flags, "
-                  f"{sample['res_x']}x{sample['res_y']} (1/4 of the pixels), {r['tet_steps']} tet-steps per step")
+    dog = Watchdog(0, limit_s=1800.0)
+    dog.start()
+    mesh, view = synth.make_config(args.workload)
+    r = time_reference(mesh, view, steps=args.steps, warmup=args.warmup, tick=dog.tick)
+    sample_txt = (f"{args.workload} mesh ({mesh.n_tets} tets) + reference solids at {view['res_x']}x{view['res_y']}, the whole "
+                  f"workload: {r['tet_steps']} tet-steps per step; timed region = plane ctor + find_intersections + "
+                  "trace_rays (main.cpp:126-130)")
     line = {
         "impl": "reference", "metric": "tet_steps_per_sec", "value": r["value"], "unit": "tet-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "pixels_per_sec": r["pixels"] / r["seconds_per_step"],
-        "config": config_dict(mesh, view, args.gpus),
+        "tet_steps_per_view": r["tet_steps"],
+        "config": config_dict(args.workload, mesh, view),
+        "execution": {"where": f"host CPU, OpenMP, {r['cores']} threads", "gpus_used": 0},
         "cpu_baseline": {"value": r["value"], "unit": "tet-steps/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": sample_txt},
         "e2e": {"value": r["value"], "unit": "tet-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def config_dict(mesh, view, n_gpus, gather="p2p", lanes=1, name=WORKLOAD):
-    return {
-        "workload": (f"{name}: synthetic Kuhn-split grid, {mesh.n_tets} tets / {mesh.n_points} points, "
-                     f"{view['res_x']}x{view['res_y']}, -X {view['X']} -Y {view['Y']} --alpha_limit "
-                     f"{view['alpha_limit']}, reference Roche lobe + sphere as solids"),
-        "res_x": view["res_x"], "res_y": view["res_y"], "n_tets": mesh.n_tets,
-        "views_in_flight": lanes,
-        "grazing_kernel": ("after the pixel kernel (NCCL shares the device)" if n_gpus > 1 else
-                           "after the pixel kernel" if os.environ.get("C5_GRAZE_SERIAL") else "beside the pixel kernel (side stream)"),
-        "parallelism": "single GPU" if n_gpus == 1 else
-                       f"{n_gpus} row bands (time-balanced), mesh replicated, " +
-                       ("bands stored into rank 0's image over NVLink peer mappings by the walk kernel, one barrier per view"
-                        if gather != "sendrecv" else "one grouped ncclSend/ncclRecv gather-v to rank 0 per view"),
-        "l2": "inputs larger than L2 (cell records alone are 64 B x n_tets >> 126 MB); no explicit flush",
-    }
 
 
 # ------------------------------------------------------------------------------------------------
@@ -243,52 +263,36 @@ def config_dict(mesh, view, n_gpus, gather="p2p", lanes=1, name=WORKLOAD):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from course5_b200.dist import BandRenderer
+    from course5_b200.dist import BandRenderer, SharedHostImage
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
-    dry = args.dry_run_hostsim   # CPU rehearsal of this function's control flow (tests/test_bench.py); not a measurement
-    if not dry and not torch.cuda.is_available():
+    if world != args.gpus and world == 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path "
                          "(use --impl reference for the CPU baseline)")
-    if dry:
-        device = torch.device("cpu")
-        lib = api.load_library(os.path.join(ROOT, "tests", "hostsim", "libc5hostsim.so"))
-    else:
-        torch.cuda.set_device(local_rank)
-        device = torch.device("cuda", local_rank)
-        lib = None
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     dog = Watchdog(rank, limit_s=float(os.environ.get("C5_BENCH_STALL_LIMIT", "150" if world == 1 else "90")))
     dog.start()
     dog.tick("init process group" if world > 1 else "single process")
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
-        if dry:
-            dist.init_process_group("gloo")
-        else:
-            dist.init_process_group("nccl", device_id=device)
+        dist.init_process_group("nccl", device_id=device)
 
     dog.tick("synthetic mesh + solids on the host")
-    if dry:
-        mesh = synth.kuhn_cube(8, seed=3)
-        view = dict(res_x=160, res_y=120, X=0.5, Y=0.0, I=0.0, D=0.0, alpha_limit=3.0)
-        solids = None
-    else:
-        mesh, view = workload()
-        solids = reference_solids(view["D"])
+    mesh, view = synth.make_config(args.workload)
+    solids = reference_solids(view["D"])
 
     dog.tick("upload (topology, BVH)")
-    ctx = api.Context(devices=(0 if dry else local_rank,), lib=lib)
+    ctx = api.Context(devices=(local_rank,))
     t0 = time.perf_counter()
     info = ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
-    if solids is not None:
-        ctx.upload_solids(solids[0], True)
-        ctx.upload_solids(solids[1], False)
+    ctx.upload_solids(solids[0], True)
+    ctx.upload_solids(solids[1], False)
     upload_s = time.perf_counter() - t0
     v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
                       alpha_limit=view["alpha_limit"], lib=ctx.lib)
@@ -297,110 +301,142 @@ def run_ours(args):
     def barrier():
         if world > 1:
             dist.barrier()
-        if not dry:
-            torch.cuda.synchronize(device)
+        torch.cuda.synchronize(device)
 
-    class HostClock:   # dry run only: stands in for a CUDA event
-        def record(self):
-            self.t = time.perf_counter()
-
-        def elapsed_time(self, other):
-            return 1e3 * (other.t - self.t)
-
-    # ---- value: everything resident, output stays on the device -------------------------------
-    # warm-up views also settle the band cuts: tet-steps of the previous view, weighted by the time
-    # each band took (a few iterations; a sweep does the same from frame to frame)
-    n_warm = max(args.warmup, 3) if world == 1 else max(args.warmup, 6)
+    # ---- warm-up: also settles the band cuts -----------------------------------------------------
+    # tet-steps of the previous view, weighted by the time each band took (a few iterations; a sweep
+    # does the same from frame to frame)
+    n_warm = max(args.warmup, 3)
     for k in range(n_warm):
         dog.tick(f"warm-up view {k}")
-        _, _, bands = br.render(v, rebalance="time")
+        br.render(v, rebalance="steps")
+    if world > 1:
+        # bands cut so that every rank sustains the same pipelined time per view (a sweep does the same
+        # from frame to frame): rounds of a few views each, no exchange, re-cut after each
+        dog.tick("band calibration")
+        br.calibrate(v, rounds=args.calibrate, views=8)
+        n_warm += args.calibrate * 9
+    bands = br.bands(view["res_y"])
     dog.tick(f"bands {bands}")
     barrier()
-    sampler = ClockSampler(local_rank)
-    if not dry:
-        sampler.start()
-    launches0 = br.kernel_launches()
-    ev0, ev1 = (HostClock(), HostClock()) if dry else (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    walk_ms, steps_total, stats_last = [], 0, None
-    ev0.record()
+
+    # ---- N > 1: the assembled image against one rank's own render of the whole view ---------------
+    parity, parity_failed = None, False
+    if world > 1:
+        dog.tick("parity of the assembled image")
+        img_dev, _, _ = br.render(v, rebalance=False)
+        torch.cuda.synchronize(device)
+        barrier()
+        if rank == 0:
+            whole, _ = ctx.render(v)
+            got = img_dev.cpu().numpy()
+            same = bool(np.array_equal(got, whole, equal_nan=True))
+            rows = np.where(~np.all((got == whole) | (np.isnan(got) & np.isnan(whole)), axis=(1, 2)))[0]
+            parity = {"against": f"rank 0's own render of the whole view (bit for bit); one rank against oracle/_ref: "
+                                 "the N = 1 line and tests/test_gpu_parity.py",
+                      "assembled_image_equals_single_rank_render": same, "rows_that_differ": int(rows.size),
+                      "n_ranks": world, "gather": br.gather_mode, "ok": same}
+        barrier()
+
+    # ---- value: everything resident, output stays on the device -----------------------------------
     # The views are only enqueued (no host readback between them; statistics come from a second
-    # pass): consecutive views alternate between two lanes — the context and a sibling that shares
-    # its mesh, each on its own stream — so the tail of one view's walk overlaps the start of the
-    # next. N > 1, gather=p2p: the walk stores straight into rank 0's image over NVLink and the
-    # barrier of view k is left in flight (three images); gather=sendrecv: the same with one grouped
-    # ncclSend/ncclRecv per view.
+    # pass): consecutive views rotate over the lanes — the context and siblings that share its mesh,
+    # each on its own stream — so the tail of one view's walk and its grazing-ray kernel overlap the
+    # next views. N > 1, gather=p2p: the walk stores straight into rank 0's image over NVLink and the
+    # barrier of view k is left in flight (lanes + 1 images); gather=sendrecv: the same with one
+    # grouped ncclSend/ncclRecv per view.
+    if args.timeline:
+        br.enable_timeline(args.steps)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = br.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dog.tick(f"timed region: {args.steps} views, {br.n_lanes} in flight, gather={br.gather_mode}")
+    host_t = []
+    ev0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        _, _, bands = br.render(v, rebalance=False, stats=False, pipeline=True)
+        br.render(v, rebalance=False, stats=False, pipeline=True)
+        host_t.append(time.perf_counter() - t_host0)
     br.finish()
     ev1.record()
     barrier()
-    dog.tick("statistics pass")
-    clocks = sampler.stop() if not dry else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    clocks = sampler.stop()
     launches = br.kernel_launches() - launches0
     elapsed_ms = max(ev0.elapsed_time(ev1), 1e-6)
+    host_enqueue_ms = 1e3 * host_t[-1] / args.steps
+    timeline = None
+    if args.timeline:
+        lanes_tl = br.timeline(ev0.cuda_event)
+        timeline = {"rank": rank, "band": list(bands[rank]), "host_enqueue_done_ms": [1e3 * t for t in host_t],
+                    "phases": ["start", "rotated", "refitted", "mask", "pixel_kernel", "grazing_kernel"],
+                    "lanes": [tl.tolist() for tl in lanes_tl], "elapsed_ms": elapsed_ms}
+        br.enable_timeline(0)
+
+    dog.tick("statistics pass")
+    walk_ms, stats_last = [], None
     for _ in range(3):
-        _, st, bands = br.render(v, rebalance=False)
+        _, st, _ = br.render(v, rebalance=False)
         walk_ms.append(st["ms_walk"])
         stats_last = st
     barrier()
     band_steps = stats_last["tet_steps"]
 
-    # ---- e2e: the public C-ABI call with a pinned HOST output buffer ---------------------------
-    # N = 1: c5_render into a pinned buffer. N > 1: the image is ONE pinned shared-memory segment;
-    # every rank's c5_render writes its band in place over its own PCIe link, then one barrier.
-    # Wall clock around the calls a user makes; the image is complete in host memory at the end
-    # of every step.
-    dog.tick("e2e: host image")
-    from course5_b200.dist import SharedHostImage
-    if os.environ.get("C5_BENCH_FAKE_HANG") == "1" and args.lanes > 1:   # tests/test_bench.py: the fallback path
-        time.sleep(10_000)
-    old_style = world > 1 and args.e2e == "gather"
-    if world == 1 or old_style:
-        host_out = torch.empty((view["res_y"], view["res_x"], 2), dtype=torch.float64)
-        if not dry:
-            host_out = host_out.pin_memory()
-        host_np = host_out.numpy()
-        shared = None
-    else:
-        shared = SharedHostImage(ctx, view["res_x"], view["res_y"], rank=rank, world=world)
-        host_np = shared.array
+    # ---- e2e: the public C-ABI calls with page-locked HOST images ----------------------------------
+    # c5_render_submit / c5_render_wait with `lanes` views in flight. N = 1: the images are pinned
+    # buffers. N > 1: ONE shared-memory segment every rank pins; each rank's walk writes its band in
+    # place over its own PCIe link and publishes "band of view k done" in the segment; rank 0 takes the
+    # image when all bands are in. Wall clock around the calls a user makes; every step's image is
+    # complete in host memory (and its stats read) inside the timed region.
+    dog.tick("e2e: host images")
+    L = br.n_lanes
+    ctx.set_views_in_flight(L)
+    if args.e2e_mode == "copy":
+        ctx.debug_set("no_zero_copy", 1)
     lo, hi = bands[rank]
-    ve = api.View.from_buffer_copy(v)
-    ve.row_begin, ve.row_end = lo, hi
-    def e2e_step():
-        if old_style:      # band gather on the devices, then ONE device-to-host copy of the image on rank 0
-            img, _, _ = br.render(v, rebalance=False, stats=False)
-            if rank == 0:
-                host_out.copy_(img, non_blocking=False)
-        else:
-            ctx.render(ve, out=host_np)
-            if world > 1:
-                shared.barrier()
+    shared = SharedHostImage(ctx, view["res_x"], view["res_y"], rank=rank, world=world, sets=L + 1)
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(n_views, base):
+        """Views base .. base + n_views - 1 (the flags in the segment count views since its creation)."""
+        tickets = collections.deque()
+        steps_seen = 0
+        for k in range(n_views + L):
+            if k >= L:
+                kk = base + k - L
+                steps_seen += shared.complete_band(tickets.popleft(), kk)["tet_steps"]
+                if rank == 0:
+                    image = shared.wait_image(kk)      # complete in host memory here
+                    assert image.shape[0] == view["res_y"]
+                    shared.release(kk)
+            if k < n_views:
+                tickets.append(shared.submit_band(v, (lo, hi), base + k))
+        return steps_seen
+
+    e2e_run(2 * L, 0)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_steps = e2e_run(args.steps, 2 * L)
     barrier()
     e2e_s = time.perf_counter() - t0
-    if shared is not None:
-        shared.close()
+    e2e_image_ok = True
+    if rank == 0:   # the last host image is the view (spot check: same NaN mask and finite elsewhere)
+        last = shared.arrays[(2 * L + args.steps - 1) % (L + 1)]
+        e2e_image_ok = bool(np.isnan(last).any() and np.isfinite(last[~np.isnan(last)]).all() and (last != 0).any())
+    shared.close()
+    assert e2e_steps == band_steps * args.steps, (e2e_steps, band_steps)
 
     dog.tick("reduce over ranks")
-    # ---- reduce over ranks ----------------------------------------------------------------------
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, float(np.mean(walk_ms))], dtype=torch.float64, device=device)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, float(np.mean(walk_ms)), host_enqueue_ms], dtype=torch.float64, device=device)
     s = torch.tensor([band_steps, launches], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, walk_ms_max = (float(x) for x in t.cpu())
+    elapsed_ms, e2e_ms, walk_ms_max, host_enqueue_ms = (float(x) for x in t.cpu())
     total_steps, total_launches = (int(x) for x in s.cpu())
     # the roofline line describes the walk of the band with the most tet-steps (rank 0's may be empty)
-    mine = torch.tensor([float(band_steps), float((bands[rank][1] - bands[rank][0]) * view["res_x"]),
-                         float(np.mean(walk_ms))], dtype=torch.float64, device=device)
+    mine = torch.tensor([float(band_steps), float((hi - lo) * view["res_x"]), float(np.mean(walk_ms)),
+                         float(stats_last["ms_graze"]), float(stats_last["ms_mask"]), float(stats_last["ms_total"])],
+                        dtype=torch.float64, device=device)
     per_rank = [torch.zeros_like(mine) for _ in range(world)]
     if world > 1:
         dist.all_gather(per_rank, mine)
@@ -408,6 +444,15 @@ def run_ours(args):
         per_rank = [mine]
     per_rank = [p.cpu().tolist() for p in per_rank]
     busiest = max(range(world), key=lambda r: per_rank[r][0])
+    if timeline is not None:
+        gathered = [None] * world
+        if world > 1:
+            dist.all_gather_object(gathered, timeline)
+        else:
+            gathered = [timeline]
+        if rank == 0:
+            with open(args.timeline, "w") as f:
+                json.dump({"n_gpus": world, "steps": args.steps, "lanes": L, "gather": br.gather_mode, "ranks": gathered}, f)
 
     if rank == 0:
         pixels = view["res_x"] * view["res_y"]
@@ -415,55 +460,83 @@ def run_ours(args):
         value = total_steps / (ms_per_step * 1e-3)
         e2e_value = total_steps / (e2e_ms * 1e-3 / args.steps)
         peak, peak_src = measured_hbm_peak()
-        # dominant kernel (tet_walk_fp64 + its grazing-ray kernel) on the busiest band; at N = 1 the whole image
-        k_steps, k_pixels, k_ms = per_rank[busiest]
-        k_ms = max(k_ms, 1e-9)      # (only the dry run has zero device times)
-        achieved = (k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL) / (k_ms * 1e-3) / 1e9
+        cap = ncu_capture()
+        # dominant kernels (tet_walk_fp64 + grazing_rays_fp64) on the busiest band; at N = 1 the whole image
+        k_steps, k_pixels, k_ms = per_rank[busiest][:3]
+        k_ms = max(k_ms, 1e-9)
+        alg_bytes = k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = cap.get("dram_bytes_per_launch") if world == 1 else None
         line = {
             "metric": "tet_steps_per_sec", "value": value, "unit": "tet-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "pixels_per_sec": pixels / (ms_per_step * 1e-3),
             "tet_steps_per_view": total_steps,
-            "config": config_dict(mesh, view, world, br.gather_mode, br.n_lanes, "dry-run cube (no solids)" if dry else WORKLOAD),
+            "config": config_dict(args.workload, mesh, view),
+            "execution": {
+                "views_in_flight": br.n_lanes,
+                "walk": "pixel kernel, then the grazing-ray kernel on the same stream (no kernel waits for another)",
+                "parallelism": "single GPU" if world == 1 else
+                               f"{world} row bands (time-balanced), mesh replicated, " +
+                               ("bands stored into rank 0's image over NVLink peer mappings by the walk kernels, one 4-byte all-reduce per view as the barrier"
+                                if br.gather_mode == "p2p" else "one grouped ncclSend/ncclRecv gather-v to rank 0 per view"),
+                "host_enqueue_ms_per_view": host_enqueue_ms},
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(api.C.sizeof(api.View)), "d2h_bytes_per_step": pixels * 16,
-                    "api": "c5_render (pinned host buffer)" if world == 1 else
-                    "BandRenderer.render + one device-to-host copy on rank 0" if old_style else
-                    "c5_render (row band) into one pinned shared-memory host image, one barrier per view"},
+                    "h2d_bytes_per_step": int(api.C.sizeof(api.View)) * world, "d2h_bytes_per_step": pixels * 16 + world * (64 + 8 * view["res_y"]),
+                    "views_in_flight": L, "image_spot_check": e2e_image_ok, "mode": args.e2e_mode,
+                    "api": "c5_render_submit / c5_render_wait into page-locked host images written in place by the walk kernels" +
+                           ("" if world == 1 else " (one shared-memory image per view, every rank its band over its own PCIe link; completion flags in the segment)")},
             "gpu_launches": total_launches,
-            "roofline": {"kernel": "tet_walk_fp64", "rank": busiest, "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "frac_of_8000_GBps_nominal": achieved / 8000.0,
-                         "traffic": ncu_traffic_per_launch(),
+            "roofline": {"kernel": "tet_walk_fp64 + grazing_rays_fp64", "rank": busiest, "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_8000_GBps_nominal": achieved / 8000.0, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": k_ms,
-                         "ncu": {k: ncu_capture().get(k) for k in ("l1_hit_rate_pct", "l2_hit_rate_pct",
-                                                                   "l1_data_pipe_wavefronts_pct_of_peak", "source")},
-                         "algorithmic_bytes_per_launch": int(k_steps * BYTES_PER_STEP + k_pixels * BYTES_PER_PIXEL)},
+                         "kernel_ms_note": "CUDA events around the two kernels of ONE view rendered alone (statistics pass); ms_per_step is "
+                                           "the pipelined rate with several views in flight, which hides each view's tail, so it can be lower",
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "limiter": "L1 data-pipe wavefronts and load latency, not DRAM: `achieved` is a normalised throughput "
+                                    "(algorithmic bytes / time); rays share tets in L1/L2, so real DRAM traffic is `traffic`",
+                         "dram_frac_of_peak": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "ncu": {k: cap.get(k) for k in ("l1_hit_rate_pct", "l2_hit_rate_pct",
+                                                         "l1_data_pipe_wavefronts_pct_of_peak", "source")}},
             "bands": [list(b) for b in bands],
-            "phases_ms": {k: stats_last[k] for k in ("ms_rotate", "ms_bvh", "ms_mask", "ms_walk", "ms_total")},
+            "per_rank": [{"tet_steps": int(p[0]), "walk_ms": p[2], "graze_ms": p[3], "mask_ms": p[4], "view_ms_alone": p[5]} for p in per_rank],
+            "phases_ms": {k: stats_last[k] for k in ("ms_rotate", "ms_bvh", "ms_mask", "ms_walk", "ms_graze", "ms_total")},
             "one_off": {"upload_and_topology_s": upload_s, "device_bytes": int(info.device_bytes),
                         "boundary_faces": int(info.n_boundary_faces)},
             "clocks": clocks,
         }
+        if parity is not None:
+            line["parity"] = parity
         if os.environ.get("C5_BENCH_ATTEMPTS"):
             line["attempts"] = json.loads(os.environ["C5_BENCH_ATTEMPTS"])   # configurations left before this one
-        if dry:
-            line["data"] = "DRY RUN on the host-loop test build: control flow only, not a measurement"
-        if world == 1 and not args.no_cpu_baseline and not dry:
-            dog.tick("cpu_baseline: the reference on the host cores", limit_s=1800.0)
-            sample = reference_sample(view)
-            r = time_reference(mesh, sample, steps=1, warmup=0)
+        if world == 1 and not args.no_cpu_baseline:
+            dog.tick("cpu_baseline + parity: the reference on the host cores, same workload, same resolution", limit_s=1800.0)
+            vraw = api.View.from_buffer_copy(v)
+            vraw.round_through_float = 0
+            ours = ctx.render_raw(vraw)
+            r = time_reference(mesh, view, steps=1, warmup=0, raw=True, keep_image=True)
             line["cpu_baseline"] = {
                 "value": r["value"], "unit": "tet-steps/s", "cores": r["cores"], "kind": r["kind"],
                 "seconds": r["seconds_per_step"],
-                "sample": (f"{WORKLOAD} mesh + reference solids, same flags, {sample['res_x']}x{sample['res_y']} "
-                           f"(1/4 of the pixels), {r['tet_steps']} tet-steps, 1 run")}
+                "sample": (f"the whole workload once: {args.workload} mesh + reference solids at {view['res_x']}x{view['res_y']}, "
+                           f"{r['tet_steps']} tet-steps; plane ctor + find_intersections + the per-pixel loop of "
+                           "plane.cpp:161-169 driven by the harness without the float cast (the pre-cast doubles feed `parity`)")}
+            line["parity"] = parity_record(ours, r["image"], against=(
+                "oracle/_ref (the unmodified reference) on this box, same mesh, flags, solids and resolution"
+                if r["kind"] == "reference" else "oracle/c5_oracle.c (C restatement; oracle/_ref was not built)"))
         print(json.dumps(line), flush=True)
+        if line.get("parity") and not line["parity"]["ok"]:
+            print("[bench] PARITY FAILED: " + json.dumps(line["parity"]), file=sys.stderr, flush=True)
+            parity_failed = True
     dog.tick("teardown", limit_s=120.0)
     br.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity_failed:
+        raise SystemExit(4)
 
 
 def main():
@@ -472,18 +545,20 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2, 3, 4],
+    ap.add_argument("--workload", default="C3", choices=sorted(synth.CONFIGS),
+                    help="named configuration (course5_b200.synth.CONFIGS); C3 is BASELINE.json's metric configuration")
+    ap.add_argument("--lanes", type=int, default=4, choices=range(1, api.MAX_IN_FLIGHT + 1),
                     help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each)")
-    ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="sendrecv",
-                    help="N > 1: how bands reach rank 0's image. sendrecv = one grouped ncclSend/ncclRecv per view "
-                         "(default: the transport of this round's 8-GPU scaling run); p2p = stored by the walk kernel straight into rank "
-                         "0's image over NVLink peer mappings (validated at 2 GPUs, same speed there)")
-    ap.add_argument("--dry-run-hostsim", action="store_true",
-                    help="rehearse the control flow on CPU with tests/hostsim (gloo, tiny mesh); prints a line marked as a dry run")
-    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--e2e", choices=["shared-host", "gather"], default="shared-host",
-                    help="N > 1: e2e through one pinned shared-memory host image written by every rank (default), or "
-                         "through the band gather plus one device-to-host copy on rank 0")
+    ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="p2p",
+                    help="N > 1: how bands reach rank 0's image. p2p = stored by the walk kernels straight into rank 0's image "
+                         "over NVLink peer mappings (CUDA IPC); sendrecv = one grouped ncclSend/ncclRecv per view (the baseline)")
+    ap.add_argument("--calibrate", type=int, default=5, help="N > 1: rounds of band calibration before the timed region")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline + parity leg (profiling runs)")
+    ap.add_argument("--e2e-mode", choices=["inplace", "copy"], default="inplace",
+                    help="e2e: the walk kernels store into the page-locked host image in place (default), or render into "
+                         "device memory and let the copy engine bring the image to the host (c5_debug_set no_zero_copy)")
+    ap.add_argument("--timeline", default=None, metavar="FILE",
+                    help="write per-rank, per-view phase times of the timed region (CUDA events) and host enqueue times as JSON")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -505,9 +580,9 @@ def _die_with_parent():
 
 
 def run_with_fallback(args):
-    """N > 1: every rank runs the measurement in a CHILD process and falls back to a more conservative
-    configuration if the first one does not finish. A multi-process GPU run that deadlocks cannot be
-    rescued from inside (the collective never returns); the child's own watchdog ends it, every rank
+    """N > 1: every rank runs the measurement in a CHILD process and falls back to the baseline
+    transport if the first configuration does not finish. A multi-process GPU run that deadlocks cannot
+    be rescued from inside (the collective never returns); the child's own watchdog ends it, every rank
     sees a non-zero exit code at about the same time, and all of them start the next attempt — on a
     fresh rendezvous port, since the first attempt's store is dead. The parent touches neither CUDA
     nor NCCL, so a killed child leaves the devices free. What was attempted and why it was left is
@@ -515,9 +590,8 @@ def run_with_fallback(args):
     import subprocess
     rank = int(os.environ.get("RANK", "0"))
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
-    attempts = [dict(gather=args.gather, lanes=args.lanes, e2e=args.e2e)]
-    # the fallback is the shape of this round's first 8-GPU run: one view in flight, NCCL gather, one copy to the host
-    safe = dict(gather="sendrecv", lanes=1, e2e="gather")
+    attempts = [dict(gather=args.gather, lanes=args.lanes)]
+    safe = dict(gather="sendrecv", lanes=2)     # round 1's measured configuration
     if attempts[0] != safe:
         attempts.append(safe)
     log = []
@@ -528,11 +602,12 @@ def run_with_fallback(args):
         env = dict(os.environ, C5_BENCH_CHILD="1", MASTER_PORT=str(port), TORCHELASTIC_USE_AGENT_STORE="False",
                    C5_BENCH_ATTEMPTS=json.dumps(log))
         cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--e2e", a["e2e"]]
-        if args.dry_run_hostsim:
-            cmd.append("--dry-run-hostsim")
+               "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--workload", args.workload,
+               "--e2e-mode", args.e2e_mode, "--calibrate", str(args.calibrate)]
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
+        if args.timeline:
+            cmd += ["--timeline", args.timeline]
         try:   # stderr passes through; the hard limit is a second line of defence behind the child's watchdog
             p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True, preexec_fn=_die_with_parent,
                                timeout=float(os.environ.get("C5_BENCH_ATTEMPT_LIMIT", "600")))

@@ -509,7 +509,8 @@ void ensure_host_staging(DeviceState& d, size_t rows) {
     }
 }
 
-void submit_view(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, uint64_t ticket) {
+void submit_view(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, uint8_t* solid_mask, uint64_t ticket,
+                 bool in_place_allowed = true) {
     follow_parent(ctx);
     if (ctx->pending.active) fail(C5_E_STATE, "render: this context still has a view in flight (c5_render_wait it first)");
     if (!ctx->has_mesh) fail(C5_E_STATE, "render: no mesh uploaded");
@@ -519,12 +520,17 @@ void submit_view(c5_ctx* ctx, const c5_view* v, double* out, uint32_t* steps, ui
     use_device(d);
     const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
     const size_t band_off = static_cast<size_t>(p.row_begin) * v->res_x;
-    // A PAGE-LOCKED host buffer is device-addressable: the walk then stores its pixels straight into it
+    // A PAGE-LOCKED host buffer is device-addressable: the walk can store its pixels straight into it
     // (posted 128-byte writes over PCIe, spread over the kernel's run time) and the separate
-    // device-to-host copy of the image disappears. Pixels are stored as one 128-bit word, so the
-    // buffer must be 16-byte aligned; pageable or misaligned buffers take the copy.
+    // device-to-host copy of the image disappears. That is the shorter path for ONE view at a time
+    // (c5_render). With several views in flight the copy engine is the better one: it moves view k's
+    // image while the SMs walk view k+1, and the walk kernels are not held up by PCIe write
+    // back-pressure (C3, 4 views in flight: 4.76 ms per view against 5.53 in place and 4.59 with no host
+    // image at all; profiles/r02_bench_c3_n1_e2e_*.json) — so c5_render_submit passes
+    // in_place_allowed = false. Pixels are stored as one 128-bit word, so an in-place buffer must be
+    // 16-byte aligned; pageable or misaligned buffers take the copy.
     double* host_direct = nullptr;
-    if (!kHostSim && !d.opt_no_zero_copy && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    if (!kHostSim && in_place_allowed && !d.opt_no_zero_copy && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
         cudaPointerAttributes attr{};
         if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
             host_direct = static_cast<double*>(attr.devicePointer) + 2 * band_off;
@@ -806,6 +812,7 @@ int c5_create_sibling(c5_ctx* parent, c5_ctx** out) {
     to.opt_graze_list = from.opt_graze_list;
     to.opt_query_budget = from.opt_query_budget;
     to.opt_serial_list = from.opt_serial_list;
+    to.opt_graze_blocks = from.opt_graze_blocks;
     to.opt_no_zero_copy = from.opt_no_zero_copy;
     *out = ctx;
     return C5_OK;
@@ -1006,7 +1013,7 @@ int c5_render_submit(c5_ctx* ctx, const c5_view* view, double* out, uint64_t* ti
         const uint64_t t = ctx->next_ticket++;
         try {
             g_launch_counter = &lane->dev[0]->launches;
-            submit_view(lane, view, out, nullptr, nullptr, t);
+            submit_view(lane, view, out, nullptr, nullptr, t, /*in_place_allowed=*/ctx->views_in_flight == 1);
         } catch (const Error& e) {
             if (lane != ctx) ctx->err = e.text; // (guarded() reports through ctx)
             throw;
@@ -1180,6 +1187,7 @@ int c5_debug_set(c5_ctx* ctx, const char* key, int64_t value) {
                 if (k == "graze_list") d.opt_graze_list = static_cast<int>(value);
                 else if (k == "query_budget") d.opt_query_budget = static_cast<int>(value);
                 else if (k == "serial_list") d.opt_serial_list = static_cast<int>(value);
+                else if (k == "graze_blocks") d.opt_graze_blocks = static_cast<int>(value);
                 else if (k == "no_zero_copy") d.opt_no_zero_copy = value != 0;
                 else if (k == "timeline") {
                     if (value < 0 || value > 4096) fail(C5_E_INVALID, "debug_set: timeline 0 .. 4096 views");

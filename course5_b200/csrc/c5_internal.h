@@ -83,7 +83,7 @@ struct DeviceState {
     uint64_t* h_row_cost = nullptr;             // [h_row_cost_n]
     size_t h_row_cost_n = 0;
     // c5_debug_set (tests, diagnostics); 0 = default
-    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0;
+    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0;
     bool opt_no_zero_copy = false;
     // c5_debug_set("timeline", n): phase events of the last n views, read by c5_timeline_read
     std::vector<cudaEvent_t> tl_events;         // [n][kTimelinePhases]

@@ -830,7 +830,10 @@ C5_HD bool background_pixel(const WalkParams& P, int i, int j) {
 }
 
 // ---- warp-cooperative form ---------------------------------------------------------------------------
-constexpr int kGrazeWarps = 2;    // warps (= rays in flight) per block: small blocks fit into the gaps the pixel kernel leaves
+constexpr int kGrazeWarps = 2;    // warps (= rays in flight) per block: small blocks fit into the gaps the pixel kernels leave
+constexpr int kGrazeBlocksPerSm = 12; // grid of the grazing-ray kernel (persistent warps drawing tickets). The kernel is
+                                      // latency-bound: C3 whole view alone 0.80 ms with 4 blocks per SM, 0.57 with 8, 0.50 with 12,
+                                      // 0.51 with 16 (profiles/r02_exp_graze_blocks.jsonl); blocks that find the queue empty leave at once
 constexpr int kGrazeList = 256;   // entries per collection; more are fetched by another round
 constexpr int kGrazeStack = 512;  // shared traversal stack per warp ...
 constexpr int kGrazeSlack = 128;  // ... plus room for one wide round and a depth-first tail
@@ -1387,7 +1390,7 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
 
     // Rays the pixel kernel deferred: a fixed grid of persistent warps that draw tickets.
     if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
-    const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * 4u;
+    const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * static_cast<unsigned>(d.opt_graze_blocks > 0 ? d.opt_graze_blocks : kGrazeBlocksPerSm);
     count_launch();
     if (f32) {
         grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);

@@ -71,6 +71,7 @@ class BandRenderer:
         self._bands = None                 # cached cut, valid until the row costs change
         self._cost_has_base = False        # row_cost is measured time (the per-row constant is in it)
         self._flag = None
+        self._time_cost = None             # calibrate(): last per-row time estimate (milliseconds)
         self._lanes = []                   # [(context, side stream)] on CUDA, created on first use
 
     # -- band cuts --------------------------------------------------------------------------------
@@ -181,6 +182,51 @@ class BandRenderer:
         for _, s in self._lanes:
             cur.wait_stream(s)
 
+    # -- band cuts from measured throughput -------------------------------------------------------
+    def calibrate(self, view: api.View, *, rounds: int = 4, views: int = 8) -> list[tuple[int, int]]:
+        """Cuts the bands so that every rank SUSTAINS the same time per view.
+
+        What an N-rank sweep runs at is the slowest rank's pipelined rate — several views in flight,
+        tails and grazing-ray kernels overlapped — not the time one view takes alone, and a band's
+        rate per tet-step depends on what is in it (short silhouette rays, the solid mask, rows of
+        grazing rays). So each round renders `views` pipelined views of this rank's band without
+        any exchange, times them with CUDA events, spreads the time over the band's rows in
+        proportion to their tet-steps (time_weighted_row_cost) and re-cuts; damped, because a band's
+        rate changes with its cut. Collective: every rank must call it with the same arguments."""
+        cuda = self.device.type == "cuda"
+        for _ in range(rounds):
+            _, _, bands = self.render(view, gather=False, rebalance="steps")      # per-row tet-steps, all-reduced
+            steps = self.row_cost.copy()
+            lo, hi = bands[self.rank]
+            if cuda:
+                torch.cuda.synchronize(self.device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            else:
+                import time
+                t0 = time.perf_counter()
+            for _ in range(views):
+                self.render(view, gather=False, stats=False, pipeline=True)
+            self.finish()
+            if cuda:
+                e1.record()
+                torch.cuda.synchronize(self.device)
+                ms = e0.elapsed_time(e1) / views
+            else:
+                ms = 1e3 * (time.perf_counter() - t0) / views
+            mine = torch.from_numpy(api.time_weighted_row_cost(steps, (lo, hi), ms, base_cost=self.base_cost))
+            if self.world > 1:
+                mine = mine.to(self.device)
+                dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+                mine = mine.cpu()
+            new_cost = mine.numpy().astype(np.float64)
+            if self._time_cost is not None and self._time_cost.shape == new_cost.shape:
+                new_cost = 0.5 * (new_cost + self._time_cost)
+            self._time_cost = new_cost
+            self.row_cost, self._cost_has_base = new_cost, True
+            self._bands = None
+        return self.bands(view.res_y)
+
     # -- one view ---------------------------------------------------------------------------------
     def render(self, view: api.View, *, gather: bool = True, rebalance: bool | str = True, stats: bool = True,
                pipeline: bool = False):
@@ -284,22 +330,34 @@ def _tensor_from_pointer(ptr: int, n_doubles: int, device: torch.device) -> torc
 
 
 class SharedHostImage:
-    """One (res_y, res_x, 2) float64 HOST image shared by all ranks of the node.
+    """`sets` (res_y, res_x, 2) float64 HOST images shared by all ranks of the node.
 
     Rank 0 creates a POSIX shared-memory segment, the others attach; every rank pins it with its
-    own context (``c5_host_register``), after which ``Context.render(view_with_row_band, out=image)``
-    makes the walk kernel store the band straight into the shared image over that GPU's PCIe link.
-    ``barrier()`` then tells rank 0 that all bands of the view are in. The image is single-buffered:
-    a consumer on rank 0 calls ``barrier()`` once more when it is done with the image, before any
-    rank renders the next view into it. In the CPU tests (hostsim build) the same calls degrade to
-    a plain memcpy into the shared segment."""
+    own context (``c5_host_register``), after which a render of a row band into it makes the walk
+    kernel store the band straight into the shared image over that GPU's own PCIe link.
 
-    def __init__(self, ctx: api.Context, res_x: int, res_y: int, *, rank: int, world: int):
-        self.ctx, self.rank, self.world = ctx, rank, world
-        nbytes = res_y * res_x * 16
+    One view at a time: ``render_band`` (synchronous ``c5_render``) then ``barrier()``; the
+    consumer on rank 0 calls ``barrier()`` once more when it is done with the image.
+
+    Pipelined (``sets`` > 1): view k goes to image k % sets. ``submit_band(view, band, k)`` enqueues
+    this rank's band (``c5_render_submit``; it first waits until rank 0 has released the image's
+    previous view), ``complete_band(ticket, k)`` waits for it and publishes "rank r has finished view
+    k" in the segment; rank 0's ``wait_image(k)`` returns the image once every rank has, and
+    ``release(k)`` hands the set back. The flags are 8-byte words in the same segment (plain stores,
+    polled): no collective on the path. In the CPU tests (hostsim build) the same calls degrade to
+    plain memcpys into the shared segment."""
+
+    _POLL_S = 2e-5
+
+    def __init__(self, ctx: api.Context, res_x: int, res_y: int, *, rank: int, world: int, sets: int = 1):
+        self.ctx, self.rank, self.world, self.sets = ctx, rank, world, max(1, int(sets))
+        image_bytes = res_y * res_x * 16
+        flag_bytes = 8 * (world + 1)
+        nbytes = self.sets * image_bytes + flag_bytes
         names = [None]
         if rank == 0:
             self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            self._shm.buf[self.sets * image_bytes: nbytes] = bytes(flag_bytes)
             names = [self._shm.name]
         if world > 1:
             dist.broadcast_object_list(names, src=0)
@@ -310,8 +368,13 @@ class SharedHostImage:
                 resource_tracker.unregister(self._shm._name, "shared_memory")
             except Exception:
                 pass
-        self.array = np.ndarray((res_y, res_x, 2), dtype=np.float64, buffer=self._shm.buf)
-        ctx.host_register(self.array)
+        self.arrays = [np.ndarray((res_y, res_x, 2), dtype=np.float64, buffer=self._shm.buf, offset=s * image_bytes)
+                       for s in range(self.sets)]
+        self.array = self.arrays[0]
+        # done[r] = views rank r has completed; released = views rank 0 has handed back
+        self._flags = np.ndarray((world + 1,), dtype=np.int64, buffer=self._shm.buf, offset=self.sets * image_bytes)
+        self._pinned = np.ndarray((self.sets * res_y, res_x, 2), dtype=np.float64, buffer=self._shm.buf)
+        ctx.host_register(self._pinned)
         self._registered = True
 
     def render_band(self, view: api.View, band: tuple[int, int]) -> dict:
@@ -320,15 +383,45 @@ class SharedHostImage:
         _, st = self.ctx.render(v, out=self.array)
         return st
 
+    # -- pipelined ----------------------------------------------------------------------------------
+    def _spin(self, cond, what: str, timeout_s: float = 120.0):
+        import time
+        t0 = time.monotonic()
+        while not cond():
+            time.sleep(self._POLL_S)
+            if time.monotonic() - t0 > timeout_s:
+                raise TimeoutError(f"SharedHostImage: rank {self.rank} waited {timeout_s:.0f} s for {what}; flags {self._flags.tolist()}")
+
+    def submit_band(self, view: api.View, band: tuple[int, int], k: int) -> int:
+        """Enqueues this rank's band of view number k (numbered from 0, in order) into image k % sets."""
+        self._spin(lambda: int(self._flags[self.world]) >= k - self.sets + 1, f"the release of view {k - self.sets}")
+        v = api.View.from_buffer_copy(view)
+        v.row_begin, v.row_end = band
+        return self.ctx.render_submit(v, self.arrays[k % self.sets])
+
+    def complete_band(self, ticket: int, k: int) -> dict:
+        st = self.ctx.render_wait(ticket)
+        self._flags[self.rank] = k + 1
+        return st
+
+    def wait_image(self, k: int) -> np.ndarray:
+        """Rank 0: image of view k once every rank's band is in."""
+        self._spin(lambda: int(self._flags[: self.world].min()) >= k + 1, f"the bands of view {k}")
+        return self.arrays[k % self.sets]
+
+    def release(self, k: int):
+        """Rank 0: view k has been consumed; its image may be overwritten by view k + sets."""
+        self._flags[self.world] = k + 1
+
     def barrier(self):
         if self.world > 1:
             dist.barrier()
 
     def close(self):
         if self._registered:
-            self.ctx.host_unregister(self.array)
+            self.ctx.host_unregister(self._pinned)
             self._registered = False
-        self.array = None
+        self.array, self.arrays, self._flags, self._pinned = None, [], None, None
         if self.world > 1:
             dist.barrier()
         self._shm.close()

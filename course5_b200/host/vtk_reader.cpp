@@ -106,6 +106,22 @@ public:
         _p += bytes;
         return s;
     }
+    // n elements of w bytes each (n * w must not wrap before it is compared with what is left)
+    const char* take(std::size_t n, std::size_t w) {
+        if (w != 0 && n > static_cast<std::size_t>(_e - _p) / w) fail("file ends inside a binary section");
+        return take(n * w);
+    }
+    // a count read from the file: non-negative, and no larger than the bytes that are left could hold
+    // (every value takes at least one byte in either format) — before anything is allocated for it
+    void require_values(std::size_t n) const {
+        if (n > static_cast<std::size_t>(_e - _p)) fail("a section declares more values than the file has bytes left");
+    }
+    std::size_t count(long long v, const char* what) {
+        if (v < 0 || static_cast<unsigned long long>(v) > static_cast<unsigned long long>(_e - _p)) {
+            fail(std::string("implausible ") + what + " (" + std::to_string(v) + ")");
+        }
+        return static_cast<std::size_t>(v);
+    }
 
 private:
     const char* _p;
@@ -139,6 +155,7 @@ T load_be(const char* p) {
 // n values of VTK type `type` as doubles
 void read_reals(cursor& c, bool binary, std::string type, std::size_t n, std::vector<double>& out) {
     std::transform(type.begin(), type.end(), type.begin(), [](unsigned char ch) { return std::tolower(ch); });
+    c.require_values(n);
     out.resize(n);
     if (!binary) {
         for (auto& v : out) v = c.real();
@@ -146,7 +163,7 @@ void read_reals(cursor& c, bool binary, std::string type, std::size_t n, std::ve
     }
     const std::size_t w = type_size(type, c);
     c.eat_newline();
-    const char* p = c.take(n * w);
+    const char* p = c.take(n, w);
     for (std::size_t i = 0; i < n; i++, p += w) {
         if (is_float_type(type)) {
             out[i] = (w == 8) ? load_be<double>(p) : static_cast<double>(load_be<float>(p));
@@ -164,6 +181,7 @@ void read_reals(cursor& c, bool binary, std::string type, std::size_t n, std::ve
 
 void read_ints(cursor& c, bool binary, std::string type, std::size_t n, std::vector<long long>& out) {
     std::transform(type.begin(), type.end(), type.begin(), [](unsigned char ch) { return std::tolower(ch); });
+    c.require_values(n);
     out.resize(n);
     if (!binary) {
         for (auto& v : out) v = c.integer();
@@ -171,10 +189,18 @@ void read_ints(cursor& c, bool binary, std::string type, std::size_t n, std::vec
     }
     const std::size_t w = type_size(type, c);
     c.eat_newline();
-    const char* p = c.take(n * w);
+    const char* p = c.take(n, w);
     for (std::size_t i = 0; i < n; i++, p += w) {
-        out[i] = (w == 8) ? load_be<int64_t>(p) : (w == 4) ? load_be<int32_t>(p) : load_be<int16_t>(p);
+        out[i] = (w == 8)   ? load_be<int64_t>(p)
+                 : (w == 4) ? load_be<int32_t>(p)
+                 : (w == 2) ? load_be<int16_t>(p)
+                            : static_cast<long long>(static_cast<signed char>(*p));
     }
+}
+
+int32_t point_id(long long v, const cursor& c) { // before the narrowing cast: a 64-bit id must not alias a valid one
+    if (v < 0 || v > 0x7FFFFFFFll) c.fail("cell references point id " + std::to_string(v) + " out of range");
+    return static_cast<int32_t>(v);
 }
 
 } // namespace
@@ -201,7 +227,7 @@ tet_grid read_legacy_vtk(const std::string& filename) {
             const std::string kind = c.upper_word();
             if (kind != "UNSTRUCTURED_GRID") c.fail("DATASET " + kind + " is not UNSTRUCTURED_GRID");
         } else if (key == "POINTS") {
-            const std::size_t n = static_cast<std::size_t>(c.integer());
+            const std::size_t n = c.count(c.integer(), "POINTS count");
             const std::string type = c.word();
             read_reals(c, binary, type, 3 * n, grid.points);
         } else if (key == "CELLS") {
@@ -217,21 +243,29 @@ tet_grid read_legacy_vtk(const std::string& filename) {
             if (next == "OFFSETS") {
                 c.upper_word();
                 const std::string otype = c.word();
-                read_ints(c, binary, otype, static_cast<std::size_t>(a), offsets);
+                read_ints(c, binary, otype, c.count(a, "OFFSETS count"), offsets);
                 if (c.upper_word() != "CONNECTIVITY") c.fail("expected CONNECTIVITY after OFFSETS");
                 const std::string ctype = c.word();
-                read_ints(c, binary, ctype, static_cast<std::size_t>(b), ints);
+                read_ints(c, binary, ctype, c.count(b, "CONNECTIVITY count"), ints);
                 n_cells = offsets.empty() ? 0 : offsets.size() - 1;
+                // offsets index `ints`: non-negative, non-decreasing, the last one inside the array
+                const long long n_conn = static_cast<long long>(ints.size());
+                for (std::size_t k = 0; k < offsets.size(); k++) {
+                    if (offsets[k] < 0 || offsets[k] > n_conn || (k > 0 && offsets[k] < offsets[k - 1])) {
+                        c.fail("OFFSETS entry " + std::to_string(k) + " (" + std::to_string(offsets[k]) +
+                               ") is negative, decreasing or beyond CONNECTIVITY");
+                    }
+                }
                 grid.tets.resize(4 * n_cells);
                 for (std::size_t k = 0; k < n_cells; k++) {
                     if (offsets[k + 1] - offsets[k] < 4) c.fail("cell " + std::to_string(k) + " has fewer than 4 points");
                     for (int i = 0; i < 4; i++) {
-                        grid.tets[4 * k + i] = static_cast<int32_t>(ints[static_cast<std::size_t>(offsets[k]) + i]);
+                        grid.tets[4 * k + i] = point_id(ints[static_cast<std::size_t>(offsets[k]) + i], c);
                     }
                 }
             } else {
-                n_cells = static_cast<std::size_t>(a);
-                read_ints(c, binary, "int", static_cast<std::size_t>(b), ints);
+                n_cells = c.count(a, "CELLS count");
+                read_ints(c, binary, "int", c.count(b, "CELLS size"), ints);
                 grid.tets.resize(4 * n_cells);
                 std::size_t at = 0;
                 for (std::size_t k = 0; k < n_cells; k++) {
@@ -240,12 +274,12 @@ tet_grid read_legacy_vtk(const std::string& filename) {
                     if (m < 4 || at + 1 + static_cast<std::size_t>(m) > ints.size()) {
                         c.fail("cell " + std::to_string(k) + " has fewer than 4 points or is truncated");
                     }
-                    for (int i = 0; i < 4; i++) grid.tets[4 * k + i] = static_cast<int32_t>(ints[at + 1 + i]);
+                    for (int i = 0; i < 4; i++) grid.tets[4 * k + i] = point_id(ints[at + 1 + i], c);
                     at += 1 + static_cast<std::size_t>(m);
                 }
             }
         } else if (key == "CELL_TYPES") {
-            const std::size_t n = static_cast<std::size_t>(c.integer());
+            const std::size_t n = c.count(c.integer(), "CELL_TYPES count");
             read_ints(c, binary, "int", n, ints);
         } else if (key == "CELL_DATA") {
             c.integer();
@@ -262,6 +296,7 @@ tet_grid read_legacy_vtk(const std::string& filename) {
                 const std::string maybe = probe.upper_word();
                 if (maybe != "LOOKUP_TABLE") comps = c.integer();
             }
+            if (comps < 1 || comps > 4) c.fail("SCALARS " + name + ": 1 to 4 components");
             if (c.upper_word() != "LOOKUP_TABLE") c.fail("SCALARS " + name + ": expected LOOKUP_TABLE");
             c.word();
             std::vector<double> values;
@@ -284,7 +319,9 @@ tet_grid read_legacy_vtk(const std::string& filename) {
                 const long long tuples = c.integer();
                 const std::string type = c.word();
                 std::vector<double> values;
-                read_reals(c, binary, type, static_cast<std::size_t>(comps * tuples), values);
+                const std::size_t n_comp = c.count(comps, "FIELD component count"), n_tup = c.count(tuples, "FIELD tuple count");
+                if (n_comp != 0 && n_tup > (static_cast<std::size_t>(-1) / 8) / n_comp) c.fail("implausible FIELD array size");
+                read_reals(c, binary, type, n_comp * n_tup, values);
                 if (in_cell_data && static_cast<std::size_t>(tuples) == n_cells && comps >= 1) {
                     std::vector<double> first(static_cast<std::size_t>(tuples));
                     for (std::size_t k = 0; k < first.size(); k++) first[k] = values[k * static_cast<std::size_t>(comps)];
@@ -293,11 +330,11 @@ tet_grid read_legacy_vtk(const std::string& filename) {
             }
         } else if (key == "LOOKUP_TABLE") {
             c.word();
-            const std::size_t n = static_cast<std::size_t>(c.integer());
+            const std::size_t n = c.count(c.integer(), "LOOKUP_TABLE size");
             std::vector<double> skip;
             if (binary) {
                 c.eat_newline();
-                c.take(4 * n);
+                c.take(n, 4);
             } else {
                 read_reals(c, false, "float", 4 * n, skip);
             }

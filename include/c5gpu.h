@@ -130,7 +130,7 @@ int c5_mesh_info_get(const c5_ctx* ctx, c5_mesh_info* out);
  * object2d.cpp:17-21 (with a row band: only rows [row_begin,row_end) are written, at their
  * final position). stats may be NULL. If `out` is page-locked (cudaHostAlloc, cudaHostRegister or
  * c5_host_register) and 16-byte aligned the walk kernel stores its pixels straight into it over
- * PCIe; any other buffer gets a device-to-host copy. Equivalent to c5_render_submit + c5_render_wait. */
+ * PCIe (the shortest path for one view at a time); any other buffer gets a device-to-host copy. */
 int c5_render(c5_ctx* ctx, const c5_view* view, double* out, c5_stats* stats);
 
 /* The same pass, asynchronous: c5_render_submit enqueues the view and returns a ticket at once;
@@ -138,8 +138,9 @@ int c5_render(c5_ctx* ctx, const c5_view* view, double* out, c5_stats* stats);
  * Up to c5_set_views_in_flight() views (default 3, at most C5_MAX_IN_FLIGHT) may be submitted before
  * the first is waited for; each is rendered by a lane of its own — per-view device state plus a
  * stream; the mesh is shared — so that consecutive views overlap on the device: the tail of one
- * view's walk and its grazing-ray kernel run beside the next view's rays. `out` (page-locked for
- * any overlap: a copy to pageable memory blocks the submitting thread) must stay valid and untouched
+ * view's walk and its grazing-ray kernel run beside the next view's rays, and the copy engine moves
+ * one view's image to the host while the SMs walk the next. `out` (page-locked for any overlap: a
+ * copy to pageable memory blocks the submitting thread) must stay valid and untouched
  * until the wait returns; *view is copied. One more submit than lanes returns C5_E_STATE. Tickets may
  * be waited for in any order, once each. A sweep is: submit k+1, k+2; wait k; write frame k; ...
  * Single-device contexts that are not siblings. */
@@ -208,6 +209,8 @@ uint64_t c5_kernel_launches(const c5_ctx* ctx);
  *                   tests shrink it to reach the overflow path on small meshes
  *   "query_budget"  BVH nodes a thread of the pixel kernel may visit per search before it hands the
  *                   ray to the grazing-ray kernel (>= 1, 0 = default 64)
+ *   "serial_list"   the same for the serial form of the CPU test build (2..64)
+ *   "graze_blocks"  blocks per SM of the grazing-ray kernel's grid (tuning experiments; 0 = default)
  *   "no_zero_copy"  1: page-locked output buffers get a device-to-host copy like pageable ones
  *   "timeline"      n > 0: keep the phase events of the last n views of every lane (0 = off)
  * Unknown keys return C5_E_INVALID.

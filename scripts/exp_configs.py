@@ -2,7 +2,11 @@
 """Experiment driver (not a bench line): renders named configurations on one GPU and prints one
 JSON line per (config, variant) with per-phase device times and the walk kernel's algorithmic GB/s.
 
-    python scripts/exp_configs.py C1 C3 --variants default,r64,r96 --top 255,0
+    python scripts/exp_configs.py C1 C3 --debug graze_blocks=8
+    C5GPU_LIBRARY=build/exp/libc5gpu_exp.so python scripts/exp_configs.py C3 --variants default,r64,rec --top 255,0
+
+--variants / --top select kernel variants that only exist in the experiments build of the library
+(make -C course5_b200/csrc exp); the product library ignores them.
 """
 import argparse
 import json
@@ -22,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="+")
     ap.add_argument("--variants", default="default")
-    ap.add_argument("--top", default="255")
+    ap.add_argument("--top", default="0")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-solids", action="store_true")
     ap.add_argument("--view", default=None, help="X,Y override (units of pi)")
@@ -30,7 +34,10 @@ def main():
     ap.add_argument("--precision", default="64")
     ap.add_argument("--prefetch", default="1", help="comma-separated C5_PREFETCH values (strips of L2 lookahead; 0 = off)")
     ap.add_argument("--rows", default=None, help="semicolon-separated row bands a,b;c,d to render separately")
+    ap.add_argument("--debug", default="", help="c5_debug_set knobs, key=value[,key=value]")
     args = ap.parse_args()
+    if (args.variants != "default" or args.top not in ("0", "255")) and "exp" not in os.environ.get("C5GPU_LIBRARY", ""):
+        raise SystemExit("--variants / --top need the experiments build: C5GPU_LIBRARY=build/exp/libc5gpu_exp.so")
     import torch
     dev = torch.device("cuda", 0)
     for name in args.configs:
@@ -43,6 +50,8 @@ def main():
             view["res_x"], view["res_y"] = (int(x) for x in args.res.split(","))
         solids = None if args.no_solids else hostlib.make_solids(view["D"])
         ctx = api.Context(devices=(0,))
+        for kv in (kv for kv in args.debug.split(",") if kv):
+            ctx.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
         t0 = time.perf_counter()
         info = ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
         t_up = time.perf_counter() - t0
@@ -63,7 +72,7 @@ def main():
                 os.environ["C5_TOP_NODES"] = top
                 for _ in range(2):
                     st = ctx.render_device(v, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-                acc = {k: [] for k in ("ms_rotate", "ms_bvh", "ms_mask", "ms_walk", "ms_total")}
+                acc = {k: [] for k in ("ms_rotate", "ms_bvh", "ms_mask", "ms_walk", "ms_graze", "ms_total")}
                 for _ in range(args.reps):
                     st = ctx.render_device(v, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
                     for k in acc:

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--views", type=int, default=24)
     ap.add_argument("--view", default=None)
     ap.add_argument("--no-solids", action="store_true")
+    ap.add_argument("--debug", default="", help="c5_debug_set knobs, key=value[,key=value]")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
@@ -26,6 +27,9 @@ def main():
     if args.view:
         view["X"], view["Y"] = (float(x) for x in args.view.split(","))
     ctx = api.Context(devices=(0,))
+    debug = dict(kv.split("=") for kv in args.debug.split(",") if kv)
+    for key, value in debug.items():
+        ctx.debug_set(key, int(value))
     ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
     if not args.no_solids:
         solids = hostlib.make_solids(view["D"])
@@ -61,7 +65,8 @@ def main():
             print(json.dumps({"config": args.config, "view": [view["X"], view["Y"]], "rows": [lo, hi], "lanes": n_lanes,
                               "ms_per_view": round(ms, 4), "tet_steps": st["tet_steps"],
                               "Gsteps_per_s": round(st["tet_steps"] / ms / 1e6, 2),
-                              "one_view_ms_total": round(st["ms_total"], 4)}), flush=True)
+                              "one_view_ms_total": round(st["ms_total"], 4), "one_view_ms_graze": round(st["ms_graze"], 4),
+                              "debug": debug}), flush=True)
     for c, _ in lanes[1:]:
         c.close()
     ctx.close()

@@ -45,6 +45,11 @@ def _worker(rank, world, port, out_path):
             results[f"full{k}"] = full
             results[f"bands{k}"] = np.array(bands)
             results[f"steps{k}"] = np.array([int(steps), st["tet_steps"]])
+    # bands cut by measured pipelined time: collective, keeps the cuts a partition of the rows
+    cal = br.calibrate(api.make_view(120, 90, X=0.4, Y=0.9, lib=lib), rounds=2, views=3)
+    assert cal[0][0] == 0 and cal[-1][1] == 90 and all(a[1] == b[0] for a, b in zip(cal, cal[1:]))
+    if rank == 0:
+        results["cal"] = np.array(cal)
     # pipelined mode: views in flight on separate buffer sets, gathers drained at the end
     va = api.make_view(120, 90, X=0.4, Y=0.2, lib=lib)
     vb = api.make_view(120, 90, X=0.4, Y=0.9, lib=lib)
@@ -68,6 +73,27 @@ def _worker(rank, world, port, out_path):
         results["shared_b"] = shared.array.copy()
     assert st["pixels"] == (bands[rank][1] - bands[rank][0]) * 120
     shared.close()
+    # the same, pipelined: c5_render_submit / c5_render_wait into three shared images, completion and
+    # release flags in the segment, no collective per view
+    import collections
+    views = [api.make_view(120, 90, X=0.4, Y=Y, lib=lib) for Y in (0.2, 0.9, 1.3, 0.2, 1.3)]
+    lanes = 2
+    ctx.set_views_in_flight(lanes)
+    shared = SharedHostImage(ctx, 120, 90, rank=rank, world=world, sets=lanes + 1)
+    tickets = collections.deque()
+    for k in range(len(views) + lanes):
+        if k >= lanes:
+            st = shared.complete_band(tickets.popleft(), k - lanes)
+            assert st["pixels"] == (bands[rank][1] - bands[rank][0]) * 120
+            if rank == 0:
+                results[f"pipe_shared{k - lanes}"] = shared.wait_image(k - lanes).copy()
+                shared.release(k - lanes)
+        if k < len(views):
+            tickets.append(shared.submit_band(views[k], bands[rank], k))
+    shared.close()
+    if rank == 0:
+        for k, v in enumerate(views):
+            results[f"pipe_full{k}"] = ctx.render(v)[0]
     if rank == 0:
         np.savez(out_path, **results)
     br.close()
@@ -86,6 +112,8 @@ def test_two_ranks_assemble_the_same_image(built, tmp_path):
         assert b[0][0] == 0 and b[-1][1] == 90 and b[0][1] == b[1][0]
     assert np.array_equal(r["pipe_a"], r["full0"]) and np.array_equal(r["pipe_b"], r["full1"])
     assert np.array_equal(r["shared_b"], r["full1"])
+    for k in range(5):                                   # pipelined host images: five views through three sets
+        assert np.array_equal(r[f"pipe_shared{k}"], r[f"pipe_full{k}"]), f"pipelined shared host image {k}"
     assert r["launches"][0] > r["launches"][1] > 0       # views alternate between the context and its sibling
     # first view: equal heights; second view: cut by the first view's per-row cost
     assert r["bands0"][0][1] == 45

@@ -74,7 +74,8 @@ void c5host_grid_copy(double* points, int32_t* tets, const char* alpha_name, dou
 
 long long c5host_write_vti(const char* filename, const double* image, long long res_x, long long res_y, int compress) {
     return guarded([&]() -> long long {
-        write_vti(filename, image, static_cast<std::size_t>(res_x), static_cast<std::size_t>(res_y), compress != 0);
+        write_vti(filename, image, static_cast<std::size_t>(res_x), static_cast<std::size_t>(res_y),
+                  compress == 2 ? vti_encoding::zlib_base64 : compress == 1 ? vti_encoding::zlib_raw : vti_encoding::raw);
         return 0;
     });
 }

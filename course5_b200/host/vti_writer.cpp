@@ -22,10 +22,77 @@ struct file_closer {
     }
 };
 
+const char kB64[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+
+// One self-contained base64 stream (padded): VTK encodes the block table and the data separately.
+std::string base64(const unsigned char* p, std::size_t n) {
+    std::string out;
+    out.reserve((n + 2) / 3 * 4);
+    std::size_t i = 0;
+    for (; i + 2 < n; i += 3) {
+        const unsigned v = (p[i] << 16) | (p[i + 1] << 8) | p[i + 2];
+        out += kB64[v >> 18];
+        out += kB64[(v >> 12) & 63];
+        out += kB64[(v >> 6) & 63];
+        out += kB64[v & 63];
+    }
+    if (i + 1 == n) {
+        const unsigned v = p[i] << 16;
+        out += kB64[v >> 18];
+        out += kB64[(v >> 12) & 63];
+        out += "==";
+    } else if (i + 2 == n) {
+        const unsigned v = (p[i] << 16) | (p[i + 1] << 8);
+        out += kB64[v >> 18];
+        out += kB64[(v >> 12) & 63];
+        out += kB64[(v >> 6) & 63];
+        out += '=';
+    }
+    return out;
+}
+
+// Decodes ONE padded base64 stream starting at p (stops after its padding or at a non-alphabet byte);
+// returns the bytes and advances p past the stream.
+std::vector<unsigned char> unbase64(const unsigned char*& p, const unsigned char* end, std::size_t want_bytes) {
+    static int lut[256];
+    static bool init = false;
+    if (!init) {
+        for (int& v : lut) v = -1;
+        for (int i = 0; i < 64; i++) lut[static_cast<unsigned char>(kB64[i])] = i;
+        init = true;
+    }
+    std::vector<unsigned char> out;
+    const std::size_t quads = (want_bytes + 2) / 3;
+    out.reserve(quads * 3);
+    for (std::size_t q = 0; q < quads; q++) {
+        int v[4];
+        for (int k = 0; k < 4; k++) {
+            while (p < end && (*p == '\n' || *p == '\r' || *p == ' ')) ++p;
+            if (p >= end) throw std::runtime_error("base64 stream is truncated");
+            v[k] = (*p == '=') ? -2 : lut[*p];
+            if (v[k] == -1) throw std::runtime_error("bad base64 character");
+            ++p;
+        }
+        out.push_back(static_cast<unsigned char>((v[0] << 2) | (v[1] >> 4)));
+        if (v[2] >= 0) out.push_back(static_cast<unsigned char>(((v[1] & 15) << 4) | (v[2] >> 2)));
+        if (v[2] >= 0 && v[3] >= 0) out.push_back(static_cast<unsigned char>(((v[2] & 3) << 6) | v[3]));
+    }
+    if (out.size() < want_bytes) throw std::runtime_error("base64 stream is shorter than its header says");
+    out.resize(want_bytes);
+    return out;
+}
+
 } // namespace
 
 void write_vti(const std::string& filename, const double* image, std::size_t res_x, std::size_t res_y,
                bool compress) {
+    write_vti(filename, image, res_x, res_y, compress ? vti_encoding::zlib_raw : vti_encoding::raw);
+}
+
+void write_vti(const std::string& filename, const double* image, std::size_t res_x, std::size_t res_y,
+               vti_encoding encoding) {
+    const bool compress = encoding != vti_encoding::raw;
+    const bool b64 = encoding == vti_encoding::zlib_base64;
     FILE* fp = std::fopen(filename.c_str(), "wb");
     if (!fp) throw std::runtime_error("cannot write " + filename);
     file_closer closer{fp};
@@ -43,8 +110,8 @@ void write_vti(const std::string& filename, const double* image, std::size_t res
                  "      <CellData/>\n"
                  "    </Piece>\n"
                  "  </ImageData>\n"
-                 "  <AppendedData encoding=\"raw\">\n   _",
-                 compress ? " compressor=\"vtkZLibDataCompressor\"" : "", ex, ey, ex, ey);
+                 "  <AppendedData encoding=\"%s\">\n   _",
+                 compress ? " compressor=\"vtkZLibDataCompressor\"" : "", ex, ey, ex, ey, b64 ? "base64" : "raw");
     if (!compress) {
         std::fwrite(&n_bytes, sizeof(n_bytes), 1, fp);
         if (std::fwrite(image, 1, n_bytes, fp) != n_bytes) throw std::runtime_error("short write to " + filename);
@@ -69,8 +136,19 @@ void write_vti(const std::string& filename, const double* image, std::size_t res
             packed[b].resize(out_size);
             header[3 + b] = out_size;
         }
-        std::fwrite(header.data(), sizeof(std::uint64_t), header.size(), fp);
-        for (const auto& p : packed) std::fwrite(p.data(), 1, p.size(), fp);
+        if (!b64) {
+            std::fwrite(header.data(), sizeof(std::uint64_t), header.size(), fp);
+            for (const auto& p : packed) std::fwrite(p.data(), 1, p.size(), fp);
+        } else {
+            // vtkXMLWriter's default (EncodeAppendedData on): the block table is one base64 stream, the
+            // concatenated compressed blocks another
+            const std::string h = base64(reinterpret_cast<const unsigned char*>(header.data()), header.size() * sizeof(std::uint64_t));
+            std::fwrite(h.data(), 1, h.size(), fp);
+            std::vector<unsigned char> all;
+            for (const auto& p : packed) all.insert(all.end(), p.begin(), p.end());
+            const std::string d = base64(all.data(), all.size());
+            std::fwrite(d.data(), 1, d.size(), fp);
+        }
     }
     std::fprintf(fp, "\n  </AppendedData>\n</VTKFile>\n");
 }
@@ -99,10 +177,39 @@ void read_vti(const std::string& filename, std::size_t& res_x, std::size_t& res_
     res_y = static_cast<std::size_t>(y1 - y0 + 1);
     comps = static_cast<std::size_t>(std::stoul(attr("DataArray", "NumberOfComponents")));
     const bool compressed = !attr("VTKFile", "compressor").empty();
+    const bool b64 = attr("AppendedData", "encoding") == "base64";
     const std::size_t marker = all.find("<AppendedData");
     const std::size_t under = all.find('_', all.find('>', marker));
     const unsigned char* p = reinterpret_cast<const unsigned char*>(all.data()) + under + 1;
+    const unsigned char* file_end = reinterpret_cast<const unsigned char*>(all.data()) + all.size();
     const std::size_t n_values = res_x * res_y * comps;
+    std::vector<unsigned char> decoded; // base64: the appended section turned back into the raw layout
+    if (b64) {
+        if (!compressed) {
+            std::vector<unsigned char> h = unbase64(p, file_end, 8);
+            std::uint64_t n_bytes;
+            std::memcpy(&n_bytes, h.data(), 8);
+            std::vector<unsigned char> d = unbase64(p, file_end, n_bytes);
+            decoded = h;
+            decoded.insert(decoded.end(), d.begin(), d.end());
+        } else {
+            const unsigned char* q = p;
+            std::vector<unsigned char> h3 = unbase64(q, file_end, 24); // how many blocks: then the whole table
+            std::uint64_t n_blocks;
+            std::memcpy(&n_blocks, h3.data(), 8);
+            std::vector<unsigned char> h = unbase64(p, file_end, 24 + 8 * n_blocks);
+            std::uint64_t total = 0;
+            for (std::uint64_t b = 0; b < n_blocks; b++) {
+                std::uint64_t sz;
+                std::memcpy(&sz, h.data() + 24 + 8 * b, 8);
+                total += sz;
+            }
+            std::vector<unsigned char> d = unbase64(p, file_end, total);
+            decoded = h;
+            decoded.insert(decoded.end(), d.begin(), d.end());
+        }
+        p = decoded.data();
+    }
     image_out = new double[n_values];
     if (!compressed) {
         std::uint64_t n_bytes;

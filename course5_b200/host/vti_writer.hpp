@@ -8,12 +8,22 @@
 
 namespace c5host {
 
-// image: res_y * res_x * 2 doubles, x fastest. compress: zlib-compressed appended blocks (what
-// VTK's writer does by default) instead of raw appended data; both are standard VTK XML.
-void write_vti(const std::string& filename, const double* image, std::size_t res_x, std::size_t res_y,
-               bool compress = false);
+// How the appended data section is written; all three are standard VTK XML that vtkXMLImageDataReader
+// (and ParaView, utility/screen.py:5) reads.
+//   raw          header_type UInt64 byte count + the doubles, encoding="raw" (fastest to write)
+//   zlib_raw     vtkZLibDataCompressor blocks (block table of UInt64s + compressed blocks), encoding="raw"
+//   zlib_base64  the same blocks with the table and the data as two base64 streams: what
+//                vtkXMLImageDataWriter — the reference's writer, object2d.cpp:24-27 — writes with its
+//                defaults (appended data mode, EncodeAppendedData on, zlib compressor)
+enum class vti_encoding { raw = 0, zlib_raw = 1, zlib_base64 = 2 };
 
-// Reads back what write_vti (or the oracle's shim writer) wrote: raw-appended or zlib-appended
+// image: res_y * res_x * 2 doubles, x fastest.
+void write_vti(const std::string& filename, const double* image, std::size_t res_x, std::size_t res_y,
+               vti_encoding encoding);
+void write_vti(const std::string& filename, const double* image, std::size_t res_x, std::size_t res_y,
+               bool compress = false); // false: raw, true: zlib_raw
+
+// Reads back what write_vti (or the oracle's shim writer) wrote: raw, zlib or zlib + base64 appended
 // Float64 ImageScalars. Used by tests and by `course --compare`.
 void read_vti(const std::string& filename, std::size_t& res_x, std::size_t& res_y, std::size_t& comps,
               double*& image_out);

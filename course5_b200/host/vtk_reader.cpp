@@ -59,6 +59,7 @@ public:
         skip_space();
         return _p >= _e;
     }
+    bool has_more() const { return _p < _e; }
     std::string line() {
         const char* s = _p;
         while (_p < _e && *_p != '\n') ++_p;
@@ -344,8 +345,11 @@ tet_grid read_legacy_vtk(const std::string& filename) {
             std::vector<double> skip;
             read_reals(c, binary, type, 3 * (in_cell_data ? n_cells : grid.n_points()), skip);
         } else if (key == "METADATA") {
-            // "METADATA" block: skip lines until an empty one
-            while (!c.at_end()) {
+            // "METADATA" block (VTK >= 8 writes one after arrays that carry information keys): the rest of
+            // this line, then lines up to and including the first empty one. (at_end() would skip that
+            // empty line as white space and the block would swallow the next section.)
+            c.line();
+            while (c.has_more()) {
                 if (c.line().empty()) break;
             }
         } else {

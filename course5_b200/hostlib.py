@@ -76,11 +76,14 @@ def read_vtk(path: str, alpha_name="AbsorpCoef", q_name="radEnLooseRate"):
     return pts, tets, alpha, q
 
 
-def write_vti(path: str, image: np.ndarray, compress=False):
+def write_vti(path: str, image: np.ndarray, compress=False, base64=False):
+    """compress: vtkZLibDataCompressor blocks; base64 (with compress): the appended section as base64
+    streams — together what vtkXMLImageDataWriter writes by default."""
     image = np.ascontiguousarray(image, dtype=np.float64)
     res_y, res_x, comps = image.shape
     assert comps == 2
-    if lib().c5host_write_vti(path.encode(), image.ctypes.data_as(_dp), res_x, res_y, 1 if compress else 0) < 0:
+    mode = 2 if (compress and base64) else 1 if compress else 0
+    if lib().c5host_write_vti(path.encode(), image.ctypes.data_as(_dp), res_x, res_y, mode) < 0:
         raise RuntimeError(_err())
 
 

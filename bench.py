@@ -289,6 +289,8 @@ def run_ours(args):
 
     dog.tick("upload (topology, BVH)")
     ctx = api.Context(devices=(local_rank,))
+    for kv in (kv for kv in args.debug.split(",") if kv):
+        ctx.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
     t0 = time.perf_counter()
     info = ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
     ctx.upload_solids(solids[0], True)
@@ -345,6 +347,13 @@ def run_ours(args):
     # next views. N > 1, gather=p2p: the walk stores straight into rank 0's image over NVLink and the
     # barrier of view k is left in flight (lanes + 1 images); gather=sendrecv: the same with one
     # grouped ncclSend/ncclRecv per view.
+    # one untimed pipelined round with the final bands: every lane, every image set and every lazily
+    # created mapping has been used once before the clock starts
+    br.prepare(v)
+    for _ in range(2 * br.n_lanes + 2):
+        br.render(v, rebalance=False, stats=False, pipeline=True)
+    br.finish()
+    barrier()
     if args.timeline:
         br.enable_timeline(args.steps)
     sampler = ClockSampler(local_rank)
@@ -557,6 +566,7 @@ def main():
     ap.add_argument("--e2e-mode", choices=["inplace", "copy"], default="inplace",
                     help="e2e: the walk kernels store into the page-locked host image in place (default), or render into "
                          "device memory and let the copy engine bring the image to the host (c5_debug_set no_zero_copy)")
+    ap.add_argument("--debug", default="", help="c5_debug_set knobs for experiments, key=value[,key=value]")
     ap.add_argument("--timeline", default=None, metavar="FILE",
                     help="write per-rank, per-view phase times of the timed region (CUDA events) and host enqueue times as JSON")
     args = ap.parse_args()
@@ -603,7 +613,7 @@ def run_with_fallback(args):
                    C5_BENCH_ATTEMPTS=json.dumps(log))
         cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--workload", args.workload,
-               "--e2e-mode", args.e2e_mode, "--calibrate", str(args.calibrate)]
+               "--e2e-mode", args.e2e_mode, "--calibrate", str(args.calibrate), "--debug", args.debug]
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
         if args.timeline:

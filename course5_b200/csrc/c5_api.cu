@@ -173,15 +173,32 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     use_device(d);
     g_launch_counter = &d.launches;
     ensure_pixel_tables(d, v, p);
-    const size_t n_pix_band = static_cast<size_t>(p.row_end - p.row_begin) * v->res_x;
+    // Per-view buffers are sized for the WHOLE image, not the band: cost-balanced bands move from view to
+    // view, and a buffer that had to grow in the middle of a sweep would cost a cudaFree (a device-wide
+    // synchronisation) and a cudaMalloc on the spot.
+    const size_t n_pix = static_cast<size_t>(v->res_y) * v->res_x;
     const bool solids = v->use_solids && (d.solid_follow.n + d.solid_static.n) > 0;
-    if (!out_override) d.out.ensure(2 * n_pix_band);
-    if (want_steps) d.steps.ensure(n_pix_band);
+    if (!out_override) d.out.ensure(2 * n_pix);
+    if (want_steps) d.steps.ensure(n_pix);
     d.counters.ensure(kNumCounters);
-    d.queue.ensure(n_pix_band); // every ray of the band may be deferred (reserved, hardly ever touched)
+    d.queue.ensure(n_pix); // every ray may be deferred (reserved, hardly ever touched)
     d.row_cost.ensure(static_cast<size_t>(v->res_y));
-    if (solids) d.mask.ensure(static_cast<size_t>(v->res_x) * v->res_y);
+    if (solids) d.mask.ensure(n_pix);
 
+    // c5_debug_set("prep_priority", 1): rotate / refit / mask go to a high-priority stream of their own, so
+    // that their (small, latency-bound) blocks are dispatched ahead of the queued blocks of other lanes'
+    // pixel kernels instead of behind them; the walk waits for them by event.
+    struct StreamSwap {
+        DeviceState& d;
+        cudaStream_t main;
+        ~StreamSwap() { d.stream = main; }
+    } swap{d, d.stream};
+    const bool prep = !kHostSim && d.opt_prep_priority && d.prep_stream != nullptr;
+    if (prep) {
+        C5_CUDA(cudaEventRecord(d.ev_fork, swap.main)); // after whatever the caller's stream holds (this lane's previous view)
+        C5_CUDA(cudaStreamWaitEvent(d.prep_stream, d.ev_fork, 0));
+        d.stream = d.prep_stream;
+    }
     record(d, 0);
     timeline_mark(d, 0);
     launch_prepare_cells(d, v->alpha_limit); // no-op unless --alpha_limit changed since the last view
@@ -199,6 +216,11 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     }
     record(d, 3);
     timeline_mark(d, 3);
+    if (prep) {
+        C5_CUDA(cudaEventRecord(d.ev_join, d.prep_stream));
+        d.stream = swap.main;
+        C5_CUDA(cudaStreamWaitEvent(d.stream, d.ev_join, 0));
+    }
     dev_zero(d.counters.p, kNumCounters * sizeof(unsigned long long), d.stream);
     dev_zero(d.row_cost.p, static_cast<size_t>(v->res_y) * sizeof(unsigned long long), d.stream);
     WalkLaunch w{};
@@ -779,6 +801,11 @@ int c5_create(const int32_t* devices, int32_t n_dev, c5_ctx** out) {
                 for (auto& e : d->ev) C5_CUDA(cudaEventCreate(&e));
                 C5_CUDA(cudaEventCreate(&d->ev_walk));
                 C5_CUDA(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
+                int prio_lo = 0, prio_hi = 0;
+                C5_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                C5_CUDA(cudaStreamCreateWithPriority(&d->prep_stream, cudaStreamNonBlocking, prio_hi));
+                C5_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+                C5_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
             }
         }
         if (n_dev > 1 && !kHostSim) {
@@ -813,6 +840,8 @@ int c5_create_sibling(c5_ctx* parent, c5_ctx** out) {
     to.opt_query_budget = from.opt_query_budget;
     to.opt_serial_list = from.opt_serial_list;
     to.opt_graze_blocks = from.opt_graze_blocks;
+    to.opt_prep_priority = from.opt_prep_priority;
+    to.opt_mask_lane_shift = from.opt_mask_lane_shift;
     to.opt_no_zero_copy = from.opt_no_zero_copy;
     *out = ctx;
     return C5_OK;
@@ -880,6 +909,12 @@ void c5_destroy(c5_ctx* ctx) {
             for (cudaEvent_t e : d.tl_events) cudaEventDestroy(e);
             if (d.ev_walk) cudaEventDestroy(d.ev_walk);
             if (d.ev_done) cudaEventDestroy(d.ev_done);
+            if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+            if (d.ev_join) cudaEventDestroy(d.ev_join);
+            if (d.prep_stream) {
+                cudaStreamSynchronize(d.prep_stream);
+                cudaStreamDestroy(d.prep_stream);
+            }
             for (auto& e : d.ev) {
                 if (e) cudaEventDestroy(e);
             }
@@ -1188,6 +1223,8 @@ int c5_debug_set(c5_ctx* ctx, const char* key, int64_t value) {
                 else if (k == "query_budget") d.opt_query_budget = static_cast<int>(value);
                 else if (k == "serial_list") d.opt_serial_list = static_cast<int>(value);
                 else if (k == "graze_blocks") d.opt_graze_blocks = static_cast<int>(value);
+                else if (k == "prep_priority") d.opt_prep_priority = value != 0;
+                else if (k == "mask_lane_shift") d.opt_mask_lane_shift = static_cast<int>(value < 0 ? 0 : value > 6 ? 6 : value);
                 else if (k == "no_zero_copy") d.opt_no_zero_copy = value != 0;
                 else if (k == "timeline") {
                     if (value < 0 || value > 4096) fail(C5_E_INVALID, "debug_set: timeline 0 .. 4096 views");

@@ -11,6 +11,7 @@
 //   bvh_refit        per-view boxes of the boundary-face LBVH (no reference counterpart: it
 //                    replaces the full scan conversion plane.cpp:184-192 as the way a ray finds
 //                    the tets it crosses).
+#include <algorithm>
 #include <cstring>
 
 #include "c5_internal.h"
@@ -159,96 +160,219 @@ C5_HD void mark_span(uint8_t* p, uint8_t* e) {
     }
 }
 
-// Inclusive scanline footprint of one projected triangle -> mask bytes (idempotent stores).
-// Rows are independent (the reference's running y equals the accumulated table entry ys[j]), so
-// `n_lanes` threads share one face, lane `lane` taking rows j_lo + lane, j_lo + lane + n_lanes, ...
-C5_HD void mark_face(const MaskGrid& g, const double* a, const double* b, const double* c, int lane, int n_lanes) {
-    const double* p0 = a;
-    const double* p1 = b;
-    const double* p2 = c;
+// Everything the scan conversion of one projected triangle derives from its three points before the
+// row loop (plane.cpp:57-100): y-sorted vertices, the rows of the band the triangle reaches, which
+// side the long edge is on and the three edge functions.
+struct FaceScan {
+    double p1x, p1y; // the middle vertex
+    EdgeFn e_long, e_low, e_up;
+    bool long_edge_is_left;
+    long long j_lo, j_hi; // empty if j_lo > j_hi
+};
+
+// First half of the setup: the vertices in y-descending order and the rows of the band the triangle
+// reaches. Faces outside the band, and tall faces in the listing pass, stop here.
+struct FaceRows {
+    const double *p0, *p1, *p2;
+    long long j_lo, j_hi;
+};
+
+C5_HD FaceRows scan_rows(const MaskGrid& g, const double* a, const double* b, const double* c) {
+    FaceRows R;
+    R.p0 = a;
+    R.p1 = b;
+    R.p2 = c;
     const double* t;
     // y-descending with the tie order of a stable insertion sort (std::sort on 3 items, plane.cpp:61)
-    if (p1[1] > p0[1]) { t = p0; p0 = p1; p1 = t; }
-    if (p2[1] > p0[1]) { t = p2; p2 = p1; p1 = p0; p0 = t; }
-    else if (p2[1] > p1[1]) { t = p1; p1 = p2; p2 = t; }
+    if (R.p1[1] > R.p0[1]) { t = R.p0; R.p0 = R.p1; R.p1 = t; }
+    if (R.p2[1] > R.p0[1]) { t = R.p2; R.p2 = R.p1; R.p1 = R.p0; R.p0 = t; }
+    else if (R.p2[1] > R.p1[1]) { t = R.p1; R.p1 = R.p2; R.p2 = t; }
+    R.j_hi = static_cast<long long>(floor(pixel_of_y(g, R.p0[1])));
+    R.j_lo = static_cast<long long>(ceil(pixel_of_y(g, R.p2[1])));
+    if (R.j_lo < g.row_begin) R.j_lo = g.row_begin;
+    if (R.j_hi > g.row_end - 1) R.j_hi = g.row_end - 1;
+    return R;
+}
 
+// Second half: which side the long edge is on and the three edge functions (a divide each).
+C5_HD FaceScan scan_edges(const FaceRows& R) {
+    const double *p0 = R.p0, *p1 = R.p1, *p2 = R.p2;
     // which side of the long edge p0-p2 the middle vertex lies on (plane.cpp:46-48,66-89)
     const double rel = (p2[1] - p0[1]) * p1[0] + (p0[0] - p2[0]) * p1[1] + (p2[0] * p0[1] - p0[0] * p2[1]);
     const bool asc_above = (p0[0] >= p2[0]) && (rel >= 0);
     const bool des_below = (p0[0] < p2[0]) && (rel > 0);
-    const bool long_edge_is_left = !(asc_above || des_below);
+    FaceScan S;
+    S.long_edge_is_left = !(asc_above || des_below);
+    S.j_lo = R.j_lo;
+    S.j_hi = R.j_hi;
+    S.p1x = p1[0];
+    S.p1y = p1[1];
+    S.e_long = make_edge(p0, p2);
+    S.e_low = make_edge(p2, p1);
+    S.e_up = make_edge(p0, p1);
+    return S;
+}
 
-    long long j_hi = static_cast<long long>(floor(pixel_of_y(g, p0[1])));
-    long long j_lo = static_cast<long long>(ceil(pixel_of_y(g, p2[1])));
-    if (j_lo < g.row_begin) j_lo = g.row_begin;
-    if (j_hi > g.row_end - 1) j_hi = g.row_end - 1;
-    if (j_lo + lane > j_hi) return;
-    const EdgeFn e_long = make_edge(p0, p2), e_low = make_edge(p2, p1), e_up = make_edge(p0, p1);
-    for (long long j = j_lo + lane; j <= j_hi; j += n_lanes) {
-        const double y = g.ys[j]; // == ys[j_lo] + (j - j_lo) additions of step_y (plane.cpp:100,138)
-        const double x_long = edge_x(e_long, y);
-        const double x_short = (y < p1[1]) ? edge_x(e_low, y) : edge_x(e_up, y);
-        const double x_lo = long_edge_is_left ? x_long : x_short;
-        const double x_hi = long_edge_is_left ? x_short : x_long;
-        const long long i_hi = static_cast<long long>(floor(pixel_of_x(g, x_hi)));
-        const long long i_lo = static_cast<long long>(ceil(pixel_of_x(g, x_lo)));
-        uint8_t* row = g.mask + static_cast<size_t>(j) * g.res_x;
-        if (i_lo <= i_hi) mark_span(row + i_lo, row + i_hi + 1);
+// The two ends of the triangle's footprint at height y (plane.cpp:101-137), unrounded.
+C5_HD void scan_ends(const FaceScan& S, double y, double& x_lo, double& x_hi) {
+    const double x_long = edge_x(S.e_long, y);
+    const double x_short = (y < S.p1y) ? edge_x(S.e_low, y) : edge_x(S.e_up, y);
+    x_lo = S.long_edge_is_left ? x_long : x_short;
+    x_hi = S.long_edge_is_left ? x_short : x_long;
+}
+
+C5_HD void scan_row(const MaskGrid& g, const FaceScan& S, long long j) {
+    const double y = g.ys[j]; // == ys[j_lo] + (j - j_lo) additions of step_y (plane.cpp:100,138)
+    double x_lo, x_hi;
+    scan_ends(S, y, x_lo, x_hi);
+    const long long i_hi = static_cast<long long>(floor(pixel_of_x(g, x_hi)));
+    const long long i_lo = static_cast<long long>(ceil(pixel_of_x(g, x_lo)));
+    uint8_t* row = g.mask + static_cast<size_t>(j) * g.res_x;
+    if (i_lo <= i_hi) mark_span(row + i_lo, row + i_hi + 1);
+}
+
+// ---- tall faces ------------------------------------------------------------------------------------
+// The reference's solids are fans of tets around a centre (object3d_base.cpp:156-193): two thirds of
+// their faces run from the centre to a surface edge — slivers a pixel or two wide and a hundred rows
+// tall, almost all of it under pixels the small surface faces have marked already. Marking is
+// idempotent, so a face may skip any stretch of rows whose footprint is PROVEN marked: the mask is cut
+// into tiles of kTileW x kTileH pixels with one flag per tile ("every pixel of the tile that lies in
+// the band is solid"), built after the small faces have been drawn. A tall face walks its rows one
+// tile row at a time; the footprint of a triangle over a range of rows is bounded by its ends at the
+// first and the last of those rows and by the middle vertex, so four edge evaluations decide whether
+// all tiles under it are full — against two per row plus the stores otherwise. What is skipped is
+// only ever marked already, so the mask stays bit-identical to the reference's.
+constexpr int kTileW = 16, kTileH = 8;
+constexpr int kSmallRows = 8; // faces of at most this many rows are drawn at once, by one thread
+
+struct TileGrid {
+    uint8_t* full; // [tiles_y][tiles_x]
+    int tiles_x, tiles_y;
+};
+
+C5_HD void mark_face_by_tile_rows(const MaskGrid& g, const TileGrid& tg, const FaceScan& S, int lane, int n_lanes) {
+    const long long c_lo = S.j_lo / kTileH, c_hi = S.j_hi / kTileH;
+    for (long long c = c_lo + lane; c <= c_hi; c += n_lanes) {
+        const long long ja = c * kTileH > S.j_lo ? c * kTileH : S.j_lo;
+        const long long jb = c * kTileH + kTileH - 1 < S.j_hi ? c * kTileH + kTileH - 1 : S.j_hi;
+        const double ya = g.ys[ja], yb = g.ys[jb];
+        double lo_a, hi_a, lo_b, hi_b;
+        scan_ends(S, ya, lo_a, hi_a);
+        scan_ends(S, yb, lo_b, hi_b);
+        double x_min = fmin(fmin(lo_a, hi_a), fmin(lo_b, hi_b));
+        double x_max = fmax(fmax(lo_a, hi_a), fmax(lo_b, hi_b));
+        if (S.p1y >= ya && S.p1y <= yb) { // the short edge changes inside the range: its corner may stick out
+            x_min = fmin(x_min, S.p1x);
+            x_max = fmax(x_max, S.p1x);
+        }
+        bool covered = x_min == x_min && x_max == x_max; // (never skip on a NaN)
+        if (covered) {
+            // two pixels of margin each way: edge_x is monotone in y only up to its rounding
+            long long i_a = static_cast<long long>(floor(pixel_of_x(g, x_min))) - 2;
+            long long i_b = static_cast<long long>(ceil(pixel_of_x(g, x_max))) + 2;
+            if (i_a < 0) i_a = 0;
+            if (i_b > g.res_x - 1) i_b = g.res_x - 1;
+            const uint8_t* flags = tg.full + c * tg.tiles_x;
+            for (long long t = i_a / kTileW; t <= i_b / kTileW && covered; t++) covered = flags[t] != 0;
+        }
+        if (covered) continue;
+        for (long long j = ja; j <= jb; j++) scan_row(g, S, j);
     }
 }
 
-
 // face f of a solid tet: 0 = (v0,v1,v2), 1 = (v0,v1,v3), 2 = (v0,v2,v3), 3 = (v1,v2,v3) (plane.cpp:30-37)
-C5_HD void solid_face_body(int64_t f, const double* pts, const MaskGrid& g, int lane, int n_lanes) {
+C5_HD void face_corners(int64_t f, const double* pts, const double*& a, const double*& b, const double*& c) {
     const double* p = pts + 12 * (f >> 2);
     const int k = static_cast<int>(f & 3);
-    const double* a = p + (k == 3 ? 3 : 0);
-    const double* b = p + (k >= 2 ? 6 : 3);
-    const double* c = p + (k == 0 ? 6 : 9);
-    mark_face(g, a, b, c, lane, n_lanes);
+    a = p + (k == 3 ? 3 : 0);
+    b = p + (k >= 2 ? 6 : 3);
+    c = p + (k == 0 ? 6 : 9);
 }
 
-// The row range mark_face would visit, and nothing else (same expressions, so the same rows).
-C5_HD bool solid_face_in_band(int64_t f, const double* pts, const MaskGrid& g) {
-    const double* p = pts + 12 * (f >> 2);
-    const int k = static_cast<int>(f & 3);
-    const double ya = p[(k == 3 ? 3 : 0) + 1], yb = p[(k >= 2 ? 6 : 3) + 1], yc = p[(k == 0 ? 6 : 9) + 1];
-    double y_top = ya > yb ? ya : yb, y_bot = ya > yb ? yb : ya;
-    y_top = yc > y_top ? yc : y_top;
-    y_bot = yc < y_bot ? yc : y_bot;
-    long long j_hi = static_cast<long long>(floor(pixel_of_y(g, y_top)));
-    long long j_lo = static_cast<long long>(ceil(pixel_of_y(g, y_bot)));
-    if (j_lo < g.row_begin) j_lo = g.row_begin;
-    if (j_hi > g.row_end - 1) j_hi = g.row_end - 1;
-    return j_lo <= j_hi;
+// pass 1 for one face: draws it if it is small; returns whether it is tall (to be listed)
+C5_HD bool small_face_body(uint32_t f, const double* pts, const MaskGrid& g) {
+    const double *a, *b, *c;
+    face_corners(f, pts, a, b, c);
+    const FaceRows R = scan_rows(g, a, b, c);
+    if (R.j_lo > R.j_hi) return false;
+    if (R.j_hi - R.j_lo >= kSmallRows) return true;
+    const FaceScan S = scan_edges(R);
+    for (long long j = S.j_lo; j <= S.j_hi; j++) scan_row(g, S, j);
+    return false;
+}
+
+// pass 2 for one tile
+C5_HD void tile_flag_body(int ty, int tx, const MaskGrid& g, const TileGrid& tg) {
+    const int j0 = ty * kTileH > g.row_begin ? ty * kTileH : g.row_begin;
+    const int j1 = ty * kTileH + kTileH < g.row_end ? ty * kTileH + kTileH : g.row_end;
+    const int i0 = tx * kTileW, i1 = i0 + kTileW < g.res_x ? i0 + kTileW : g.res_x;
+    bool all = true;
+    for (int j = j0; j < j1 && all; j++) {
+        const uint8_t* row = g.mask + static_cast<size_t>(j) * g.res_x;
+        if (i1 - i0 == kTileW && (reinterpret_cast<uintptr_t>(row + i0) & 7u) == 0) {
+            const unsigned long long* w = reinterpret_cast<const unsigned long long*>(row + i0);
+            all = w[0] == 0x0101010101010101ull && w[1] == 0x0101010101010101ull;
+        } else {
+            for (int i = i0; i < i1; i++) all = all && row[i] != 0;
+        }
+    }
+    tg.full[static_cast<size_t>(ty) * tg.tiles_x + tx] = all ? 1 : 0;
+}
+
+// pass 3 for one tall face
+C5_HD void tall_face_body(uint32_t f, const double* pts, const MaskGrid& g, const TileGrid& tg, int lane, int n_lanes) {
+    const double *a, *b, *c;
+    face_corners(f, pts, a, b, c);
+    const FaceRows R = scan_rows(g, a, b, c);
+    if (R.j_lo > R.j_hi) return;
+    mark_face_by_tile_rows(g, tg, scan_edges(R), lane, n_lanes);
 }
 
 } // namespace
 
-// Phase 1: one face per thread — does any of its rows fall into the band? (Most faces of a row
-// band's view do not: this is all they cost.) Phase 2: the warp's surviving faces are dealt to
-// groups of 2^lane_shift lanes, which share a face's rows round-robin as before.
+// Pass 1, one face per thread: faces that do not reach the band cost their row range and nothing else;
+// small faces are drawn here; tall ones are appended to `tall` (one atomic per warp).
 __global__ void __launch_bounds__(256)
-solid_mask(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g,
-           int lane_shift) {
+solid_mask_small(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g,
+                 uint32_t* __restrict__ tall, unsigned* n_tall) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     uint32_t f = 0;
-    bool live = false;
+    bool is_tall = false;
     if (k < n_faces) {
         f = faces[k];
-        live = solid_face_in_band(f, pts, g);
+        is_tall = small_face_body(f, pts, g);
     }
-    const unsigned m = __ballot_sync(full, live);
-    const int n_live = __popc(m);
-    const int group_lanes = 1 << lane_shift, groups = 32 >> lane_shift;
-    const int group = lane >> lane_shift, group_lane = lane & (group_lanes - 1);
-    for (int base = 0; base < n_live; base += groups) {
-        const int idx = base + group;
-        const int owner = idx < n_live ? static_cast<int>(__fns(m, 0, idx + 1)) : -1;
-        const uint32_t ff = __shfl_sync(full, f, owner < 0 ? 0 : owner);
-        if (owner >= 0) solid_face_body(ff, pts, g, group_lane, group_lanes);
+    const unsigned m = __ballot_sync(full, is_tall);
+    if (m) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(n_tall, static_cast<unsigned>(__popc(m)));
+        base = __shfl_sync(full, base, 0);
+        if (is_tall) tall[base + __popc(m & ((1u << lane) - 1u))] = f;
+    }
+}
+
+// Pass 2: one thread per tile of the band.
+__global__ void __launch_bounds__(256) mask_tile_flags(MaskGrid g, TileGrid tg, int tile_row_begin, int tile_row_end) {
+    const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t n = static_cast<int64_t>(tile_row_end - tile_row_begin) * tg.tiles_x;
+    if (k >= n) return;
+    tile_flag_body(tile_row_begin + static_cast<int>(k / tg.tiles_x), static_cast<int>(k % tg.tiles_x), g, tg);
+}
+
+// Pass 3: the tall faces, 2^lane_shift lanes per face sharing its tile rows round-robin; a fixed grid
+// strides over the list (its length lives on the device).
+__global__ void __launch_bounds__(256)
+solid_mask_tall(const uint32_t* __restrict__ tall, const unsigned* __restrict__ n_tall, const double* __restrict__ pts,
+                MaskGrid g, TileGrid tg, int lane_shift) {
+    const unsigned n = *n_tall;
+    const int group_lanes = 1 << lane_shift;
+    const unsigned groups_per_block = blockDim.x >> lane_shift;
+    const unsigned group = threadIdx.x >> lane_shift;
+    const int group_lane = static_cast<int>(threadIdx.x) & (group_lanes - 1);
+    for (unsigned idx = blockIdx.x * groups_per_block + group; idx < n; idx += gridDim.x * groups_per_block) {
+        tall_face_body(tall[idx], pts, g, tg, group_lane, group_lanes);
     }
 }
 
@@ -475,21 +599,63 @@ void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot) {
 void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
                        double step_y, int row_begin, int row_end) {
     MaskGrid g{res_x, res_y, x_min, y_min, step_x, step_y, 1.0 / step_x, 1.0 / step_y, d.ys.p, d.mask.p, row_begin, row_end};
-    for (SolidSet* ss : {&d.solid_follow, &d.solid_static}) {
-        if (ss->n == 0) continue;
-        const int64_t n_faces = ss->n_faces;
-        count_launch();
-        if (kHostSim) {
-            for (int64_t k = 0; k < n_faces; k++) solid_face_body(ss->faces.p[k], ss->pts_view.p, g, 0, 1);
-            continue;
+    SolidSet* sets[2] = {&d.solid_follow, &d.solid_static};
+    // tall-face lists of the two sets, back to back; their lengths at mask_counts[0..1]
+    const size_t cap = static_cast<size_t>(d.solid_follow.n_faces + d.solid_static.n_faces);
+    d.mask_tall.ensure(cap);
+    d.mask_counts.ensure(2);
+    TileGrid tg{nullptr, (res_x + kTileW - 1) / kTileW, (res_y + kTileH - 1) / kTileH};
+    d.mask_tiles.ensure(static_cast<size_t>(tg.tiles_x) * tg.tiles_y);
+    tg.full = d.mask_tiles.p;
+    dev_zero(d.mask_counts.p, 2 * sizeof(unsigned), d.stream);
+    uint32_t* tall[2] = {d.mask_tall.p, d.mask_tall.p + d.solid_follow.n_faces};
+    const int ty0 = row_begin / kTileH, ty1 = (row_end + kTileH - 1) / kTileH;
+    if (kHostSim) { // the same three passes as host loops
+        for (int k = 0; k < 2; k++) {
+            if (sets[k]->n == 0) continue;
+            count_launch();
+            for (int64_t i = 0; i < sets[k]->n_faces; i++) {
+                const uint32_t f = sets[k]->faces.p[i];
+                if (small_face_body(f, sets[k]->pts_view.p, g)) tall[k][d.mask_counts.p[k]++] = f;
+            }
         }
-        // threads per face ~ rows a face of this object can span / 8 (the sphere's faces are a few
-        // rows tall, the Roche lobe's fan faces hundreds)
-        const double rows = ss->extent / step_y;
+        count_launch();
+        for (int ty = ty0; ty < ty1; ty++) {
+            for (int tx = 0; tx < tg.tiles_x; tx++) tile_flag_body(ty, tx, g, tg);
+        }
+        for (int k = 0; k < 2; k++) {
+            if (sets[k]->n == 0) continue;
+            count_launch();
+            for (unsigned i = 0; i < d.mask_counts.p[k]; i++) tall_face_body(tall[k][i], sets[k]->pts_view.p, g, tg, 0, 1);
+        }
+        return;
+    }
+    // pass 1: small faces are drawn, tall ones listed
+    for (int k = 0; k < 2; k++) {
+        if (sets[k]->n == 0) continue;
+        count_launch();
+        solid_mask_small<<<grid_for(sets[k]->n_faces, 256), 256, 0, d.stream>>>(sets[k]->n_faces, sets[k]->faces.p,
+                                                                                  sets[k]->pts_view.p, g, tall[k], d.mask_counts.p + k);
+        C5_CUDA(cudaGetLastError());
+    }
+    // pass 2: which tiles of the band are solid already
+    count_launch();
+    mask_tile_flags<<<grid_for(static_cast<int64_t>(ty1 - ty0) * tg.tiles_x, 256), 256, 0, d.stream>>>(g, tg, ty0, ty1);
+    C5_CUDA(cudaGetLastError());
+    // pass 3: tall faces, skipping tile rows that are solid already
+    if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
+    for (int k = 0; k < 2; k++) {
+        if (sets[k]->n == 0) continue;
+        // Lanes per face. With most tile rows skipped a tall face is a few hundred instructions, about as
+        // much as its setup (three divides), which every lane of a group repeats: one lane per face unless
+        // faces are hundreds of tile rows tall (c5_debug_set "mask_lane_shift" overrides, for experiments).
+        const double tile_rows = std::min(sets[k]->extent / step_y, static_cast<double>(row_end - row_begin)) / kTileH;
         int lane_shift = 0;
-        while (lane_shift < 5 && (8 << lane_shift) < rows) lane_shift++;
-        solid_mask<<<grid_for(n_faces, 256), 256, 0, d.stream>>>(n_faces, ss->faces.p, ss->pts_view.p, g,
-                                                                                lane_shift);
+        while (lane_shift < 5 && (64 << lane_shift) < tile_rows) lane_shift++;
+        if (d.opt_mask_lane_shift > 0) lane_shift = d.opt_mask_lane_shift - 1;
+        count_launch();
+        solid_mask_tall<<<static_cast<unsigned>(d.sm_count) * 8u, 256, 0, d.stream>>>(tall[k], d.mask_counts.p + k,
+                                                                                      sets[k]->pts_view.p, g, tg, lane_shift);
         C5_CUDA(cudaGetLastError());
     }
 }

@@ -70,6 +70,9 @@ struct DeviceState {
     int xs_res = 0, ys_res = 0;
     double xs_win[2] = {0, 0}, ys_win[2] = {0, 0};
     DevBuf<uint8_t> mask;
+    DevBuf<uint32_t> mask_tall;      // solid mask: faces taller than a few rows, listed by the first pass
+    DevBuf<unsigned> mask_counts;    // their number per solid set
+    DevBuf<uint8_t> mask_tiles;      // "every pixel of this 16 x 8 tile is solid already"
     DevBuf<double> out;              // band output, {tau, I} per pixel
     DevBuf<uint32_t> steps;
     DevBuf<unsigned long long> counters;
@@ -83,8 +86,10 @@ struct DeviceState {
     uint64_t* h_row_cost = nullptr;             // [h_row_cost_n]
     size_t h_row_cost_n = 0;
     // c5_debug_set (tests, diagnostics); 0 = default
-    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0;
-    bool opt_no_zero_copy = false;
+    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0, opt_mask_lane_shift = 0;
+    bool opt_no_zero_copy = false, opt_prep_priority = false;
+    cudaStream_t prep_stream = nullptr;         // high priority: rotate / refit / mask when opt_prep_priority
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // c5_debug_set("timeline", n): phase events of the last n views, read by c5_timeline_read
     std::vector<cudaEvent_t> tl_events;         // [n][kTimelinePhases]
     uint64_t tl_views = 0;                      // views recorded since the timeline was enabled

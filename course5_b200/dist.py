@@ -182,6 +182,18 @@ class BandRenderer:
         for _, s in self._lanes:
             cur.wait_stream(s)
 
+    def prepare(self, view: api.View):
+        """Everything a pipelined run of `view`-sized images creates lazily, created now: the lanes and,
+        for gather="p2p", rank 0's images and their peer mappings (cudaMalloc, CUDA IPC open and a
+        broadcast each — milliseconds that do not belong in the first views of a sweep). Collective."""
+        self._lane(0)
+        if self.gather_mode == "p2p" and self.world > 1:
+            for par in range(self.n_sets):
+                self._peer_image(view, par)
+        else:
+            for par in range(self.n_sets):
+                self._buffers(view, view.res_y, par)
+
     # -- band cuts from measured throughput -------------------------------------------------------
     def calibrate(self, view: api.View, *, rounds: int = 4, views: int = 8) -> list[tuple[int, int]]:
         """Cuts the bands so that every rank SUSTAINS the same time per view.

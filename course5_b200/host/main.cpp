@@ -102,12 +102,23 @@ int main(int argc, char** argv) {
                 stem = stem.substr(0, dot);
             }
             const auto t3 = std::chrono::steady_clock::now();
-            for (int k = 0; k < config.frames; k++) {
+            // Frame 0 is the view just rendered. The others go through the pipelined calls: up to three
+            // views are in flight on the device while this thread writes the previous frame's file.
+            auto rotations_of = [&](int k) {
                 const double y = config.angle_around_y + (config.sweep_y_to - config.angle_around_y) * k / config.frames;
-                base_plane.set_view_rotations({c5_rotation{0, 0, make_perpendicular_to_y_angle, 0.0},
-                                               c5_rotation{1, 0, y * PI, ACC_X0}, c5_rotation{0, 0, last_angle, 0.0}});
-                if (k > 0) result = base_plane.trace_rays(tetra_value::alpha, tetra_value::Q);
-                result.export_to_vti(stem + "_" + std::to_string(k) + ext);
+                return std::vector<c5_rotation>{c5_rotation{0, 0, make_perpendicular_to_y_angle, 0.0},
+                                                c5_rotation{1, 0, y * PI, ACC_X0}, c5_rotation{0, 0, last_angle, 0.0}};
+            };
+            result.export_to_vti(stem + "_0" + ext);
+            const int ahead = base_plane.views_in_flight();
+            for (int k = 1; k < config.frames + ahead; k++) {
+                if (k - ahead >= 1) {
+                    base_plane.collect_rays([&](const image_ref& frame) { frame.export_to_vti(stem + "_" + std::to_string(k - ahead) + ext); });
+                }
+                if (k < config.frames) {
+                    base_plane.set_view_rotations(rotations_of(k));
+                    base_plane.submit_rays();
+                }
             }
             std::cout << "Sweep of " << config.frames << " frames completed in "
                       << ms_between(t3, std::chrono::steady_clock::now()) << " ms. " << std::endl;

@@ -116,6 +116,10 @@ void object2d::export_to_vti(const std::string& filename, bool compress) const {
     write_vti(filename, _image.data(), _x, _y, compress);
 }
 
+void image_ref::export_to_vti(const std::string& filename, bool compress) const {
+    write_vti(filename, data, x, y, compress);
+}
+
 plane::plane(std::size_t res_x, std::size_t res_y, std::vector<object3d_base> objects3d,
              std::vector<double> global_boundaries, render_options options)
     : _objects(std::move(objects3d)), _x(res_x), _y(res_y), _options(std::move(options)) {
@@ -145,7 +149,52 @@ plane::plane(std::size_t res_x, std::size_t res_y, std::vector<object3d_base> ob
 }
 
 plane::~plane() {
+    // views still in flight write into _buffers: wait for them before the memory goes away
+    for (const auto& pv : _pending) c5_render_wait(_ctx, pv.ticket, nullptr);
+    for (auto& b : _buffers) c5_host_unregister(_ctx, b.data());
     c5_destroy(_ctx);
+}
+
+void plane::set_views_in_flight(int n) {
+    if (!_pending.empty()) throw std::runtime_error("set_views_in_flight: views are in flight");
+    check(_ctx, c5_set_views_in_flight(_ctx, n), "c5_set_views_in_flight");
+    _in_flight_max = n;
+}
+
+void plane::submit_rays() {
+    if (!_uploaded) find_intersections();
+    if (static_cast<int>(_pending.size()) >= _in_flight_max) {
+        throw std::runtime_error("submit_rays: collect a view first (" + std::to_string(_in_flight_max) + " are in flight)");
+    }
+    if (_free_buffers.empty()) { // one more page-locked image, kept for the life of the plane
+        _buffers.emplace_back(_x * _y * 2);
+        check(_ctx, c5_host_register(_ctx, _buffers.back().data(), _buffers.back().size() * sizeof(double)), "c5_host_register");
+        _free_buffers.push_back(_buffers.size() - 1);
+    }
+    const std::size_t b = _free_buffers.back();
+    std::uint64_t ticket = 0;
+    check(_ctx, c5_render_submit(_ctx, &_view, _buffers[b].data(), &ticket), "c5_render_submit");
+    _free_buffers.pop_back();
+    _pending.push_back({ticket, b});
+}
+
+void plane::collect_rays(const std::function<void(const image_ref&)>& consume) {
+    if (_pending.empty()) throw std::runtime_error("collect_rays: nothing was submitted");
+    const pending_view pv = _pending.front();
+    _pending.erase(_pending.begin());
+    struct give_back { // also when the wait or the consumer throws
+        std::vector<std::size_t>& pool;
+        std::size_t b;
+        ~give_back() { pool.push_back(b); }
+    } guard{_free_buffers, pv.buffer};
+    check(_ctx, c5_render_wait(_ctx, pv.ticket, &_stats), "c5_render_wait");
+    consume(image_ref{_buffers[pv.buffer].data(), _x, _y});
+}
+
+object2d plane::collect_rays() {
+    std::vector<double> copy;
+    collect_rays([&](const image_ref& im) { copy.assign(im.data, im.data + im.x * im.y * 2); });
+    return object2d{std::move(copy), _x, _y};
 }
 
 void plane::find_intersections() {

@@ -14,6 +14,7 @@
 
 #include <array>
 #include <cstddef>
+#include <cstdint>
 #include <functional>
 #include <memory>
 #include <string>
@@ -89,6 +90,13 @@ private:
     std::size_t _x, _y;
 };
 
+// An image that lives in someone else's buffer (a submitted view's page-locked memory).
+struct image_ref {
+    const double* data; // res_y * res_x * {tau, I}, x fastest
+    std::size_t x, y;
+    void export_to_vti(const std::string& filename, bool compress = false) const;
+};
+
 struct render_options {
     std::vector<int> devices{0};
     double alpha_limit = 2.5; // the reference reads app::instance().config.limit_alpha_value (line.cpp:204)
@@ -109,6 +117,18 @@ public:
     // Sweeps: replace the recorded view rotations (grid and view-following solids) without
     // re-uploading anything; the next trace_rays() renders the new view in milliseconds.
     void set_view_rotations(const std::vector<c5_rotation>& rotations);
+    // Sweeps, pipelined (c5_render_submit / c5_render_wait): submit_rays() enqueues the view with the
+    // current rotations and returns at once; collect_rays() returns the OLDEST submitted view's image.
+    // Up to `views_in_flight` (default 3) may be submitted before the first is collected, so the device
+    // renders frames k+1, k+2 while the caller writes frame k to disk.
+    void set_views_in_flight(int n);
+    int views_in_flight() const { return _in_flight_max; }
+    void submit_rays();
+    // `consume` sees the image in the page-locked buffer the device wrote (no copy); the buffer is
+    // handed back to the pool when it returns.
+    void collect_rays(const std::function<void(const image_ref&)>& consume);
+    object2d collect_rays(); // the same, as a copy
+    std::size_t pending_views() const { return _pending.size(); }
     std::size_t count_all_intersections() const { return static_cast<std::size_t>(_stats.tet_steps); }
     std::size_t get_x() const { return _x; }
     std::size_t get_y() const { return _y; }
@@ -125,6 +145,15 @@ private:
     c5_stats _stats{};
     c5_mesh_info _info{};
     bool _uploaded = false;
+    // page-locked image buffers of the submitted views, oldest first
+    struct pending_view {
+        std::uint64_t ticket;
+        std::size_t buffer;
+    };
+    std::vector<std::vector<double>> _buffers; // registered with the context (c5_host_register)
+    std::vector<std::size_t> _free_buffers;
+    std::vector<pending_view> _pending;
+    int _in_flight_max = 3;
 };
 
 } // namespace c5host

@@ -398,3 +398,48 @@ def test_timeline_of_pipelined_views(gpu_lib):
         assert np.all(np.diff(tl, axis=1) >= 0) and np.all(np.diff(tl[:, 0]) > 0) and tl[0, 0] >= 0
         ctx.debug_set("timeline", 0)
         assert ctx.timeline(origin.cuda_event).shape == (0, 6)
+
+
+def test_config_c4_sweep_every_30th_frame_against_reference(gpu_lib, ref, tmp_path):
+    """configs[3] as specified: the 360-view turn of the 8M-tet grid at 1200 x 900, -X 0.4 -I -0.03
+    -D 0.1 (utility/rotate_traces.py:8-9,18), rendered in one go through the pipelined calls
+    (course5_b200.sweep.render_sweep: three views in flight); every 30th frame is held against
+    oracle/_ref. The .vti values are doubles that went through float (plane.cpp:165-166): equal, or
+    one float ulp apart on at most 1e-4 of the pixels; NaN masks and step totals identical."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from course5_b200 import sweep
+    from parity import float_ulp_distance
+    mesh, c4 = synth.make_config("C4")
+    every = list(range(0, 360, 30))
+    runner = os.path.join(os.path.dirname(rc.__file__), "ref_runner.py")
+    proc = subprocess.Popen([sys.executable, runner, "C4", str(tmp_path / "c4.npz"),
+                             json.dumps([dict(Y=2.0 * k / 360) for k in every])],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    kept, totals = {}, {}
+    with api.Context(devices=(0,), lib=gpu_lib) as ctx:
+        _upload_with_solids(ctx, mesh, c4["D"])
+        views = sweep.sweep_views(c4["res_x"], c4["res_y"], X=c4["X"], I=c4["I"], alpha_limit=c4["alpha_limit"],
+                                  frames=360, lib=gpu_lib)
+
+        def consume(k, image, st):
+            totals[k] = st["tet_steps"]
+            if k in every:
+                kept[k] = image.copy()
+
+        steps, stats = sweep.render_sweep(ctx, views, in_flight=3, consume=consume)
+    assert len(stats) == 360 and steps == sum(totals.values()) and all(s["walk_errors"] == 0 for s in stats)
+    _, err = proc.communicate(timeout=1500)
+    assert proc.returncode == 0, f"the reference did not finish: rc {proc.returncode}\n{err[-2000:]}"
+    r = np.load(str(tmp_path / "c4.npz"))
+    for n, k in enumerate(every):
+        want = np.stack([r[f"tau{n}"], r[f"inten{n}"]], axis=-1).astype(np.float32).astype(np.float64)
+        got = kept[k]
+        assert np.array_equal(np.isnan(got), np.isnan(want)), f"frame {k}: NaN (solid) masks differ"
+        assert totals[k] == int(r[f"total_steps{n}"]), f"frame {k}: tet-steps differ"
+        ok = ~np.isnan(want)
+        ulp = float_ulp_distance(got[ok], want[ok])
+        assert ulp.max() <= 1 and (ulp > 0).mean() <= 1e-4, f"frame {k}: {int((ulp > 0).sum())} pixels differ, max {int(ulp.max())} ulp"
+        assert np.array_equal(got[..., 0] != 0, want[..., 0] != 0), f"frame {k}: hit/miss sets differ"

@@ -842,6 +842,7 @@ int c5_create_sibling(c5_ctx* parent, c5_ctx** out) {
     to.opt_graze_blocks = from.opt_graze_blocks;
     to.opt_prep_priority = from.opt_prep_priority;
     to.opt_mask_lane_shift = from.opt_mask_lane_shift;
+    to.opt_mask_tile = from.opt_mask_tile;
     to.opt_no_zero_copy = from.opt_no_zero_copy;
     *out = ctx;
     return C5_OK;
@@ -1224,6 +1225,7 @@ int c5_debug_set(c5_ctx* ctx, const char* key, int64_t value) {
                 else if (k == "serial_list") d.opt_serial_list = static_cast<int>(value);
                 else if (k == "graze_blocks") d.opt_graze_blocks = static_cast<int>(value);
                 else if (k == "prep_priority") d.opt_prep_priority = value != 0;
+                else if (k == "mask_tile") d.opt_mask_tile = static_cast<int>(value);
                 else if (k == "mask_lane_shift") d.opt_mask_lane_shift = static_cast<int>(value < 0 ? 0 : value > 6 ? 6 : value);
                 else if (k == "no_zero_copy") d.opt_no_zero_copy = value != 0;
                 else if (k == "timeline") {

@@ -242,19 +242,20 @@ C5_HD void scan_row(const MaskGrid& g, const FaceScan& S, long long j) {
 // first and the last of those rows and by the middle vertex, so four edge evaluations decide whether
 // all tiles under it are full — against two per row plus the stores otherwise. What is skipped is
 // only ever marked already, so the mask stays bit-identical to the reference's.
-constexpr int kTileW = 16, kTileH = 8;
+constexpr int kTileW = 16, kTileH = 8; // default tile: 16 x 8 and 16 x 4 measured best, smaller tiles slower (profiles/r02_exp_mask_tile_sizes.jsonl); (c5_debug_set "mask_tile" = 100 w + h overrides, for experiments)
 constexpr int kSmallRows = 8; // faces of at most this many rows are drawn at once, by one thread
 
 struct TileGrid {
     uint8_t* full; // [tiles_y][tiles_x]
     int tiles_x, tiles_y;
+    int w, h;      // tile size in pixels (w a multiple of 8)
 };
 
 C5_HD void mark_face_by_tile_rows(const MaskGrid& g, const TileGrid& tg, const FaceScan& S, int lane, int n_lanes) {
-    const long long c_lo = S.j_lo / kTileH, c_hi = S.j_hi / kTileH;
+    const long long c_lo = S.j_lo / tg.h, c_hi = S.j_hi / tg.h;
     for (long long c = c_lo + lane; c <= c_hi; c += n_lanes) {
-        const long long ja = c * kTileH > S.j_lo ? c * kTileH : S.j_lo;
-        const long long jb = c * kTileH + kTileH - 1 < S.j_hi ? c * kTileH + kTileH - 1 : S.j_hi;
+        const long long ja = c * tg.h > S.j_lo ? c * tg.h : S.j_lo;
+        const long long jb = c * tg.h + tg.h - 1 < S.j_hi ? c * tg.h + tg.h - 1 : S.j_hi;
         const double ya = g.ys[ja], yb = g.ys[jb];
         double lo_a, hi_a, lo_b, hi_b;
         scan_ends(S, ya, lo_a, hi_a);
@@ -273,7 +274,7 @@ C5_HD void mark_face_by_tile_rows(const MaskGrid& g, const TileGrid& tg, const F
             if (i_a < 0) i_a = 0;
             if (i_b > g.res_x - 1) i_b = g.res_x - 1;
             const uint8_t* flags = tg.full + c * tg.tiles_x;
-            for (long long t = i_a / kTileW; t <= i_b / kTileW && covered; t++) covered = flags[t] != 0;
+            for (long long t = i_a / tg.w; t <= i_b / tg.w && covered; t++) covered = flags[t] != 0;
         }
         if (covered) continue;
         for (long long j = ja; j <= jb; j++) scan_row(g, S, j);
@@ -303,15 +304,15 @@ C5_HD bool small_face_body(uint32_t f, const double* pts, const MaskGrid& g) {
 
 // pass 2 for one tile
 C5_HD void tile_flag_body(int ty, int tx, const MaskGrid& g, const TileGrid& tg) {
-    const int j0 = ty * kTileH > g.row_begin ? ty * kTileH : g.row_begin;
-    const int j1 = ty * kTileH + kTileH < g.row_end ? ty * kTileH + kTileH : g.row_end;
-    const int i0 = tx * kTileW, i1 = i0 + kTileW < g.res_x ? i0 + kTileW : g.res_x;
+    const int j0 = ty * tg.h > g.row_begin ? ty * tg.h : g.row_begin;
+    const int j1 = ty * tg.h + tg.h < g.row_end ? ty * tg.h + tg.h : g.row_end;
+    const int i0 = tx * tg.w, i1 = i0 + tg.w < g.res_x ? i0 + tg.w : g.res_x;
     bool all = true;
     for (int j = j0; j < j1 && all; j++) {
         const uint8_t* row = g.mask + static_cast<size_t>(j) * g.res_x;
-        if (i1 - i0 == kTileW && (reinterpret_cast<uintptr_t>(row + i0) & 7u) == 0) {
+        if (i1 - i0 == tg.w && (reinterpret_cast<uintptr_t>(row + i0) & 7u) == 0) {
             const unsigned long long* w = reinterpret_cast<const unsigned long long*>(row + i0);
-            all = w[0] == 0x0101010101010101ull && w[1] == 0x0101010101010101ull;
+            for (int k = 0; k < tg.w / 8; k++) all = all && w[k] == 0x0101010101010101ull;
         } else {
             for (int i = i0; i < i1; i++) all = all && row[i] != 0;
         }
@@ -604,12 +605,17 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
     const size_t cap = static_cast<size_t>(d.solid_follow.n_faces + d.solid_static.n_faces);
     d.mask_tall.ensure(cap);
     d.mask_counts.ensure(2);
-    TileGrid tg{nullptr, (res_x + kTileW - 1) / kTileW, (res_y + kTileH - 1) / kTileH};
+    int tile_w = kTileW, tile_h = kTileH;
+    if (d.opt_mask_tile > 0) {
+        tile_w = std::max(8, (d.opt_mask_tile / 100) & ~7);
+        tile_h = std::max(1, d.opt_mask_tile % 100);
+    }
+    TileGrid tg{nullptr, (res_x + tile_w - 1) / tile_w, (res_y + tile_h - 1) / tile_h, tile_w, tile_h};
     d.mask_tiles.ensure(static_cast<size_t>(tg.tiles_x) * tg.tiles_y);
     tg.full = d.mask_tiles.p;
     dev_zero(d.mask_counts.p, 2 * sizeof(unsigned), d.stream);
     uint32_t* tall[2] = {d.mask_tall.p, d.mask_tall.p + d.solid_follow.n_faces};
-    const int ty0 = row_begin / kTileH, ty1 = (row_end + kTileH - 1) / kTileH;
+    const int ty0 = row_begin / tg.h, ty1 = (row_end + tg.h - 1) / tg.h;
     if (kHostSim) { // the same three passes as host loops
         for (int k = 0; k < 2; k++) {
             if (sets[k]->n == 0) continue;
@@ -649,9 +655,9 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
         // Lanes per face. With most tile rows skipped a tall face is a few hundred instructions, about as
         // much as its setup (three divides), which every lane of a group repeats: one lane per face unless
         // faces are hundreds of tile rows tall (c5_debug_set "mask_lane_shift" overrides, for experiments).
-        const double tile_rows = std::min(sets[k]->extent / step_y, static_cast<double>(row_end - row_begin)) / kTileH;
+        const double tile_rows = std::min(sets[k]->extent / step_y, static_cast<double>(row_end - row_begin)) / tg.h;
         int lane_shift = 0;
-        while (lane_shift < 5 && (64 << lane_shift) < tile_rows) lane_shift++;
+        while (lane_shift < 5 && (256 << lane_shift) < tile_rows) lane_shift++;
         if (d.opt_mask_lane_shift > 0) lane_shift = d.opt_mask_lane_shift - 1;
         count_launch();
         solid_mask_tall<<<static_cast<unsigned>(d.sm_count) * 8u, 256, 0, d.stream>>>(tall[k], d.mask_counts.p + k,

@@ -86,7 +86,7 @@ struct DeviceState {
     uint64_t* h_row_cost = nullptr;             // [h_row_cost_n]
     size_t h_row_cost_n = 0;
     // c5_debug_set (tests, diagnostics); 0 = default
-    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0, opt_mask_lane_shift = 0;
+    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0, opt_mask_lane_shift = 0, opt_mask_tile = 0;
     bool opt_no_zero_copy = false, opt_prep_priority = false;
     cudaStream_t prep_stream = nullptr;         // high priority: rotate / refit / mask when opt_prep_priority
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

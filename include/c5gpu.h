@@ -211,6 +211,7 @@ uint64_t c5_kernel_launches(const c5_ctx* ctx);
  *                   ray to the grazing-ray kernel (>= 1, 0 = default 64)
  *   "serial_list"   the same for the serial form of the CPU test build (2..64)
  *   "graze_blocks"  blocks per SM of the grazing-ray kernel's grid (tuning experiments; 0 = default)
+ *   "mask_tile"     100 w + h: tile size of the solid mask's "already solid" flags (0 = default)
  *   "mask_lane_shift" n > 0: 2^(n-1) lanes share a tall solid face in the mask's third pass (0 = automatic)
  *   "prep_priority" 1: rotate / refit / mask of a view run on a high-priority stream of their own
  *   "no_zero_copy"  1: page-locked output buffers get a device-to-host copy like pageable ones

@@ -27,7 +27,14 @@ def test_library_exports_every_declared_symbol(gpu_lib):
     for name in names:
         assert hasattr(gpu_lib, name), f"{name} is declared in c5gpu.h but not exported"
     assert sorted(api.SYMBOLS) == names, "course5_b200.api.SYMBOLS is out of sync with include/c5gpu.h"
-    assert gpu_lib.c5_abi_version() == 2
+    header_version = int(re.search(r"#define\s+C5_ABI_VERSION\s+(\d+)", open(HEADER).read()).group(1))
+    assert gpu_lib.c5_abi_version() == header_version == api.ABI_VERSION
+
+
+def test_build_entry_point_checks_the_same_version():
+    """__graft_entry__.build() must compare against api.ABI_VERSION, not a literal that goes stale."""
+    text = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    assert "api.ABI_VERSION" in text and not re.search(r"c5_abi_version\(\)\s*==\s*\d", text)
 
 
 def test_ctypes_structs_match_the_c_layout(tmp_path):

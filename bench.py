@@ -62,13 +62,23 @@ def ncu_capture():
 
 
 class ClockSampler(threading.Thread):
-    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+    """Polls SM clock and throttle reasons through NVML; only samples taken while `armed` count.
 
-    def __init__(self, index: int, period=0.01):
+    NVML is initialised in the constructor and the thread is started well BEFORE the timed region:
+    the first NVML queries of a process are slow (tens of milliseconds at 8 processes per node) and,
+    measured, stall CUDA submission in the processes of the same node while they run
+    (profiles/r02_timeline_c3_n8_*_a.json: 15-20 ms holes at the start of the timed region on some
+    ranks). So the poller is already in steady state when arm() is called right before the first
+    timed view, and only what it sees between arm() and stop() is reported."""
+
+    def __init__(self, index: int, period=0.005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
+        self.armed = False
+        self.polls = 0
+        self._last_unarmed = None
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -78,6 +88,15 @@ class ClockSampler(threading.Thread):
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        return mhz, mask
 
     def run(self):
         if self.nv is None:
@@ -91,23 +110,40 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                armed = self.armed
+                mhz, mask = self._poll()
+                self.polls += 1
+                if armed:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                else:
+                    self._last_unarmed = (mhz, [name for bit, name in names.items() if mask & bit])
             except Exception:
                 pass
             self._stop_evt.wait(self.period)
 
+    def wait_warm(self, polls=3, timeout_s=2.0):
+        """Returns once the poller has completed a few queries (their first-call cost is behind us)."""
+        t0 = time.monotonic()
+        while self.nv is not None and self.polls < polls and time.monotonic() - t0 < timeout_s:
+            time.sleep(0.002)
+
+    def arm(self):
+        self.armed = True
+
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+               "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if not self.samples and self._last_unarmed is not None:
+            # a timed region shorter than one polling period: the poll just before it, taken under the same
+            # load (the untimed pipelined round), is what there is
+            out.update(sm_mhz=float(self._last_unarmed[0]), reasons=sorted(self._last_unarmed[1]),
+                       note="timed region shorter than one poll; sample taken during the untimed pipelined round right before it")
+        return out
 
 
 class Watchdog(threading.Thread):
@@ -349,19 +385,28 @@ def run_ours(args):
     # grouped ncclSend/ncclRecv per view.
     # one untimed pipelined round with the final bands: every lane, every image set and every lazily
     # created mapping has been used once before the clock starts
+    # ... and the clock poller is started before it, so that NVML's slow first queries (which stall CUDA
+    # submission in every process of the node while they run) are over when the clock starts
     br.prepare(v)
+    sampler = None if args.no_clock_sampler else ClockSampler(local_rank)
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    ev1.record()        # (both events exist before the clock starts)
     for _ in range(2 * br.n_lanes + 2):
         br.render(v, rebalance=False, stats=False, pipeline=True)
     br.finish()
-    barrier()
     if args.timeline:
         br.enable_timeline(args.steps)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = br.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.wait_warm()
     dog.tick(f"timed region: {args.steps} views, {br.n_lanes} in flight, gather={br.gather_mode}")
+    barrier()
+    launches0 = br.kernel_launches()
     host_t = []
+    if sampler:
+        sampler.arm()
     ev0.record()
     t_host0 = time.perf_counter()
     for _ in range(args.steps):
@@ -370,7 +415,7 @@ def run_ours(args):
     br.finish()
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "--no-clock-sampler"}
     launches = br.kernel_launches() - launches0
     elapsed_ms = max(ev0.elapsed_time(ev1), 1e-6)
     host_enqueue_ms = 1e3 * host_t[-1] / args.steps
@@ -567,6 +612,7 @@ def main():
                     help="e2e: the walk kernels store into the page-locked host image in place (default), or render into "
                          "device memory and let the copy engine bring the image to the host (c5_debug_set no_zero_copy)")
     ap.add_argument("--debug", default="", help="c5_debug_set knobs for experiments, key=value[,key=value]")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="experiments: no NVML polling at all")
     ap.add_argument("--timeline", default=None, metavar="FILE",
                     help="write per-rank, per-view phase times of the timed region (CUDA events) and host enqueue times as JSON")
     args = ap.parse_args()
@@ -618,6 +664,8 @@ def run_with_fallback(args):
             cmd.append("--no-cpu-baseline")
         if args.timeline:
             cmd += ["--timeline", args.timeline]
+        if args.no_clock_sampler:
+            cmd.append("--no-clock-sampler")
         try:   # stderr passes through; the hard limit is a second line of defence behind the child's watchdog
             p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True, preexec_fn=_die_with_parent,
                                timeout=float(os.environ.get("C5_BENCH_ATTEMPT_LIMIT", "600")))

@@ -210,8 +210,6 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     record(d, 2);
     timeline_mark(d, 2);
     if (solids) {
-        dev_zero(d.mask.p + static_cast<size_t>(p.row_begin) * v->res_x,
-                 static_cast<size_t>(p.row_end - p.row_begin) * v->res_x, d.stream);
         launch_solid_mask(d, v->res_x, v->res_y, p.x_min, p.y_min, p.step_x, p.step_y, p.row_begin, p.row_end);
     }
     record(d, 3);
@@ -663,6 +661,7 @@ void upload_solids(c5_ctx* ctx, const double* pts, int64_t n, int follows) {
         }
         g_launch_counter = &d.launches;
         dedupe_solid_faces(d, ss);
+        d.mask_static_valid = false;
     }
     ctx->info.n_solid_tets += n;
 }
@@ -702,6 +701,7 @@ void alias_mesh(DeviceState& s, DeviceState& o) {
         if (k == 0) to[k]->pts_view.alloc(from[k]->pts_view.n); // rotated with the view
         else to[k]->pts_view.alias(from[k]->pts_view);         // static solids are never rotated
     }
+    s.mask_static_valid = false;
     stream_sync(s.stream);
     s.mesh_version = o.mesh_version;
 }
@@ -841,7 +841,8 @@ int c5_create_sibling(c5_ctx* parent, c5_ctx** out) {
     to.opt_serial_list = from.opt_serial_list;
     to.opt_graze_blocks = from.opt_graze_blocks;
     to.opt_prep_priority = from.opt_prep_priority;
-    to.opt_mask_lane_shift = from.opt_mask_lane_shift;
+    to.opt_mask_per_face = from.opt_mask_per_face;
+    to.opt_no_static_mask = from.opt_no_static_mask;
     to.opt_mask_tile = from.opt_mask_tile;
     to.opt_no_zero_copy = from.opt_no_zero_copy;
     *out = ctx;
@@ -985,6 +986,7 @@ int c5_clear_solids(c5_ctx* ctx) {
                 ss->n_faces = 0;
                 ss->extent = 0.0;
             }
+            dp->mask_static_valid = false;
         }
         ctx->info.n_solid_tets = 0;
     });
@@ -1226,7 +1228,11 @@ int c5_debug_set(c5_ctx* ctx, const char* key, int64_t value) {
                 else if (k == "graze_blocks") d.opt_graze_blocks = static_cast<int>(value);
                 else if (k == "prep_priority") d.opt_prep_priority = value != 0;
                 else if (k == "mask_tile") d.opt_mask_tile = static_cast<int>(value);
-                else if (k == "mask_lane_shift") d.opt_mask_lane_shift = static_cast<int>(value < 0 ? 0 : value > 6 ? 6 : value);
+                else if (k == "mask_per_face") d.opt_mask_per_face = static_cast<int>(value < 0 ? 0 : value > 6 ? 6 : value);
+                else if (k == "no_static_mask") {
+                    d.opt_no_static_mask = value != 0;
+                    d.mask_static_valid = false;
+                }
                 else if (k == "no_zero_copy") d.opt_no_zero_copy = value != 0;
                 else if (k == "timeline") {
                     if (value < 0 || value > 4096) fail(C5_E_INVALID, "debug_set: timeline 0 .. 4096 views");

@@ -251,32 +251,39 @@ struct TileGrid {
     int w, h;      // tile size in pixels (w a multiple of 8)
 };
 
+// Whether every pixel under face S in tile row c is PROVEN marked; [ja, jb] = the rows of S in that tile row.
+C5_HD bool tile_row_covered(const MaskGrid& g, const TileGrid& tg, const FaceScan& S, long long c, long long& ja, long long& jb) {
+    ja = c * tg.h > S.j_lo ? c * tg.h : S.j_lo;
+    jb = c * tg.h + tg.h - 1 < S.j_hi ? c * tg.h + tg.h - 1 : S.j_hi;
+    const double ya = g.ys[ja], yb = g.ys[jb];
+    double lo_a, hi_a, lo_b, hi_b;
+    scan_ends(S, ya, lo_a, hi_a);
+    scan_ends(S, yb, lo_b, hi_b);
+    double x_min = fmin(fmin(lo_a, hi_a), fmin(lo_b, hi_b));
+    double x_max = fmax(fmax(lo_a, hi_a), fmax(lo_b, hi_b));
+    if (S.p1y >= ya && S.p1y <= yb) { // the short edge changes inside the range: its corner may stick out
+        x_min = fmin(x_min, S.p1x);
+        x_max = fmax(x_max, S.p1x);
+    }
+    bool covered = x_min == x_min && x_max == x_max; // (never skip on a NaN)
+    if (covered) {
+        // two pixels of margin each way: edge_x is monotone in y only up to its rounding
+        long long i_a = static_cast<long long>(floor(pixel_of_x(g, x_min))) - 2;
+        long long i_b = static_cast<long long>(ceil(pixel_of_x(g, x_max))) + 2;
+        if (i_a < 0) i_a = 0;
+        if (i_b > g.res_x - 1) i_b = g.res_x - 1;
+        const uint8_t* flags = tg.full + c * tg.tiles_x;
+        for (long long t = i_a / tg.w; t <= i_b / tg.w && covered; t++) covered = flags[t] != 0;
+    }
+    return covered;
+}
+
+// One face, tile row by tile row, by one thread (the CPU test build, and the experiments' per-face kernel).
 C5_HD void mark_face_by_tile_rows(const MaskGrid& g, const TileGrid& tg, const FaceScan& S, int lane, int n_lanes) {
     const long long c_lo = S.j_lo / tg.h, c_hi = S.j_hi / tg.h;
     for (long long c = c_lo + lane; c <= c_hi; c += n_lanes) {
-        const long long ja = c * tg.h > S.j_lo ? c * tg.h : S.j_lo;
-        const long long jb = c * tg.h + tg.h - 1 < S.j_hi ? c * tg.h + tg.h - 1 : S.j_hi;
-        const double ya = g.ys[ja], yb = g.ys[jb];
-        double lo_a, hi_a, lo_b, hi_b;
-        scan_ends(S, ya, lo_a, hi_a);
-        scan_ends(S, yb, lo_b, hi_b);
-        double x_min = fmin(fmin(lo_a, hi_a), fmin(lo_b, hi_b));
-        double x_max = fmax(fmax(lo_a, hi_a), fmax(lo_b, hi_b));
-        if (S.p1y >= ya && S.p1y <= yb) { // the short edge changes inside the range: its corner may stick out
-            x_min = fmin(x_min, S.p1x);
-            x_max = fmax(x_max, S.p1x);
-        }
-        bool covered = x_min == x_min && x_max == x_max; // (never skip on a NaN)
-        if (covered) {
-            // two pixels of margin each way: edge_x is monotone in y only up to its rounding
-            long long i_a = static_cast<long long>(floor(pixel_of_x(g, x_min))) - 2;
-            long long i_b = static_cast<long long>(ceil(pixel_of_x(g, x_max))) + 2;
-            if (i_a < 0) i_a = 0;
-            if (i_b > g.res_x - 1) i_b = g.res_x - 1;
-            const uint8_t* flags = tg.full + c * tg.tiles_x;
-            for (long long t = i_a / tg.w; t <= i_b / tg.w && covered; t++) covered = flags[t] != 0;
-        }
-        if (covered) continue;
+        long long ja, jb;
+        if (tile_row_covered(g, tg, S, c, ja, jb)) continue;
         for (long long j = ja; j <= jb; j++) scan_row(g, S, j);
     }
 }
@@ -329,13 +336,209 @@ C5_HD void tall_face_body(uint32_t f, const double* pts, const MaskGrid& g, cons
     mark_face_by_tile_rows(g, tg, scan_edges(R), lane, n_lanes);
 }
 
+// ---- a warp's 32 faces, shared ---------------------------------------------------------------------
+// One face per thread leaves most lanes idle: faces differ in height by two orders of magnitude, two
+// thirds of a pass-1 warp hold faces that are only listed, and the rare tile row that does have to be
+// drawn stalls the other 31 lanes (ncu, per-face kernels: 7.5 of 32 lanes active on the Roche lobe,
+// profiles/r02_mask_*). So a warp sets up its 32 faces one per lane, parks the FaceScans in shared
+// memory and deals out the ITEMS (rows in pass 1, tile rows in pass 3, rows of uncovered tile rows in
+// its drain) lane by lane, whoever the face belongs to. The arithmetic per item is the same
+// functions on the same operands as the per-face form, so the mask cannot differ.
+constexpr int kFaceFields = 17; // p1x p1y + 3 x {x1 y1 dx dy rdy}
+struct WarpFaces {
+    double f[kFaceFields][32];
+    int j_lo[32], j_hi[32], bits[32]; // bits: flat (long, low, up), long_edge_is_left
+    int first[32];                    // items of the faces of the lower lanes (exclusive prefix sum)
+    int c_lo[32];                     // pass 3: first tile row of the face
+    int list[64][2];                  // pass 3: (lane of the face, tile row) still to be drawn
+};
+
+__device__ void wf_store_edge(WarpFaces& w, int at, int lane, const EdgeFn& e) {
+    w.f[at][lane] = e.x1;
+    w.f[at + 1][lane] = e.y1;
+    w.f[at + 2][lane] = e.dx;
+    w.f[at + 3][lane] = e.dy;
+    w.f[at + 4][lane] = e.rdy;
+}
+__device__ EdgeFn wf_load_edge(const WarpFaces& w, int at, int o, bool flat) {
+    EdgeFn e;
+    e.x1 = w.f[at][o];
+    e.y1 = w.f[at + 1][o];
+    e.dx = w.f[at + 2][o];
+    e.dy = w.f[at + 3][o];
+    e.rdy = w.f[at + 4][o];
+    e.flat = flat;
+    return e;
+}
+__device__ void wf_store(WarpFaces& w, int lane, const FaceScan& S) {
+    w.f[0][lane] = S.p1x;
+    w.f[1][lane] = S.p1y;
+    wf_store_edge(w, 2, lane, S.e_long);
+    wf_store_edge(w, 7, lane, S.e_low);
+    wf_store_edge(w, 12, lane, S.e_up);
+    w.j_lo[lane] = static_cast<int>(S.j_lo);
+    w.j_hi[lane] = static_cast<int>(S.j_hi);
+    w.bits[lane] = (S.e_long.flat ? 1 : 0) | (S.e_low.flat ? 2 : 0) | (S.e_up.flat ? 4 : 0) | (S.long_edge_is_left ? 8 : 0);
+}
+__device__ FaceScan wf_load(const WarpFaces& w, int o) {
+    FaceScan S;
+    const int bits = w.bits[o];
+    S.p1x = w.f[0][o];
+    S.p1y = w.f[1][o];
+    S.e_long = wf_load_edge(w, 2, o, bits & 1);
+    S.e_low = wf_load_edge(w, 7, o, bits & 2);
+    S.e_up = wf_load_edge(w, 12, o, bits & 4);
+    S.long_edge_is_left = bits & 8;
+    S.j_lo = w.j_lo[o];
+    S.j_hi = w.j_hi[o];
+    return S;
+}
+
+// Exclusive prefix sum of n over the warp, left in w.first; returns the total.
+__device__ int wf_deal(WarpFaces& w, int lane, int n) {
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    w.first[lane] = incl - n;
+    __syncwarp();
+    return __shfl_sync(0xFFFFFFFFu, incl, 31);
+}
+// The lane whose face item i belongs to: the LAST lane with first <= i (lanes without items share
+// their `first` with the next lane that has some, and that one is the later of them).
+__device__ int wf_owner(const WarpFaces& w, int i) {
+    int o = 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        if (w.first[o + d] <= i) o += d;
+    }
+    return o;
+}
+
 } // namespace
 
-// Pass 1, one face per thread: faces that do not reach the band cost their row range and nothing else;
-// small faces are drawn here; tall ones are appended to `tall` (one atomic per warp).
-__global__ void __launch_bounds__(256)
+constexpr int kMaskWarps = 4; // warps per block of the two face passes (5.6 KB of shared memory each)
+
+// Pass 1: faces that do not reach the band cost their row range and nothing else; tall ones are appended
+// to `tall` (one atomic per warp); the rows of the small ones are dealt out over the warp and drawn.
+__global__ void __launch_bounds__(32 * kMaskWarps)
 solid_mask_small(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g,
                  uint32_t* __restrict__ tall, unsigned* n_tall) {
+    __shared__ WarpFaces shared[kMaskWarps];
+    WarpFaces& w = shared[threadIdx.x >> 5];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    uint32_t f = 0;
+    bool is_tall = false;
+    int rows = 0;
+    if (k < n_faces) {
+        f = faces[k];
+        const double *a, *b, *c;
+        face_corners(f, pts, a, b, c);
+        const FaceRows R = scan_rows(g, a, b, c);
+        if (R.j_lo <= R.j_hi) {
+            if (R.j_hi - R.j_lo >= kSmallRows) {
+                is_tall = true;
+            } else {
+                wf_store(w, lane, scan_edges(R));
+                rows = static_cast<int>(R.j_hi - R.j_lo) + 1;
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(full, is_tall);
+    if (m) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(n_tall, static_cast<unsigned>(__popc(m)));
+        base = __shfl_sync(full, base, 0);
+        if (is_tall) tall[base + __popc(m & ((1u << lane) - 1u))] = f;
+    }
+    const int total = wf_deal(w, lane, rows);
+    for (int i = lane; i < total; i += 32) {
+        const int o = wf_owner(w, i);
+        const FaceScan S = wf_load(w, o);
+        scan_row(g, S, S.j_lo + (i - w.first[o]));
+    }
+}
+
+// Pass 3: the tall faces. The tile rows of a warp's 32 faces are dealt out over its lanes; a tile row that
+// is not proven solid goes to a short list, and the list's ROWS are dealt out in turn.
+__global__ void __launch_bounds__(32 * kMaskWarps)
+solid_mask_tall(const uint32_t* __restrict__ tall, const unsigned* __restrict__ n_tall, const double* __restrict__ pts,
+                MaskGrid g, TileGrid tg) {
+    __shared__ WarpFaces shared[kMaskWarps];
+    WarpFaces& w = shared[threadIdx.x >> 5];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const unsigned n = *n_tall;
+    auto drain = [&](int n_list) {
+        __syncwarp();
+        for (int k = lane; k < n_list * tg.h; k += 32) {
+            const int e = k / tg.h;
+            const int o = w.list[e][0];
+            const long long j = static_cast<long long>(w.list[e][1]) * tg.h + k % tg.h;
+            if (j >= w.j_lo[o] && j <= w.j_hi[o]) scan_row(g, wf_load(w, o), j);
+        }
+        __syncwarp();
+    };
+    for (unsigned base = (blockIdx.x * kMaskWarps + (threadIdx.x >> 5)) * 32u; base < n; base += gridDim.x * kMaskWarps * 32u) {
+        int items = 0;
+        if (base + lane < n) {
+            const double *a, *b, *c;
+            face_corners(tall[base + lane], pts, a, b, c);
+            const FaceRows R = scan_rows(g, a, b, c);
+            if (R.j_lo <= R.j_hi) {
+                wf_store(w, lane, scan_edges(R));
+                w.c_lo[lane] = static_cast<int>(R.j_lo / tg.h);
+                items = static_cast<int>(R.j_hi / tg.h - R.j_lo / tg.h) + 1;
+            }
+        }
+        const int total = wf_deal(w, lane, items);
+        int n_list = 0;
+        for (int at = 0; at < total; at += 32) {
+            const int i = at + lane;
+            bool draw = false;
+            int o = 0, c = 0;
+            if (i < total) {
+                o = wf_owner(w, i);
+                c = w.c_lo[o] + (i - w.first[o]);
+                long long ja, jb;
+                draw = !tile_row_covered(g, tg, wf_load(w, o), c, ja, jb);
+            }
+            const unsigned m = __ballot_sync(full, draw);
+            if (m) {
+                if (n_list + __popc(m) > 64) {
+                    drain(n_list);
+                    n_list = 0;
+                }
+                if (draw) {
+                    const int at_list = n_list + __popc(m & ((1u << lane) - 1u));
+                    w.list[at_list][0] = o;
+                    w.list[at_list][1] = c;
+                }
+                n_list += __popc(m);
+            }
+        }
+        drain(n_list); // (also fences this batch's FaceScans against the next one's stores)
+    }
+}
+
+// Pass 2: one thread per tile of the band.
+__global__ void __launch_bounds__(256) mask_tile_flags(MaskGrid g, TileGrid tg, int tile_row_begin, int tile_row_end) {
+    const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t n = static_cast<int64_t>(tile_row_end - tile_row_begin) * tg.tiles_x;
+    if (k >= n) return;
+    tile_flag_body(tile_row_begin + static_cast<int>(k / tg.tiles_x), static_cast<int>(k % tg.tiles_x), g, tg);
+}
+
+#ifdef C5_EXPERIMENTS
+// The per-face form of passes 1 and 3 (one face per thread; pass 3 optionally 2^lane_shift lanes per face
+// sharing its tile rows round-robin), kept for scripts/ to measure against (c5_debug_set "mask_per_face").
+__global__ void __launch_bounds__(256)
+solid_mask_small_per_face(int64_t n_faces, const uint32_t* __restrict__ faces, const double* __restrict__ pts, MaskGrid g,
+                          uint32_t* __restrict__ tall, unsigned* n_tall) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -353,20 +556,9 @@ solid_mask_small(int64_t n_faces, const uint32_t* __restrict__ faces, const doub
         if (is_tall) tall[base + __popc(m & ((1u << lane) - 1u))] = f;
     }
 }
-
-// Pass 2: one thread per tile of the band.
-__global__ void __launch_bounds__(256) mask_tile_flags(MaskGrid g, TileGrid tg, int tile_row_begin, int tile_row_end) {
-    const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t n = static_cast<int64_t>(tile_row_end - tile_row_begin) * tg.tiles_x;
-    if (k >= n) return;
-    tile_flag_body(tile_row_begin + static_cast<int>(k / tg.tiles_x), static_cast<int>(k % tg.tiles_x), g, tg);
-}
-
-// Pass 3: the tall faces, 2^lane_shift lanes per face sharing its tile rows round-robin; a fixed grid
-// strides over the list (its length lives on the device).
 __global__ void __launch_bounds__(256)
-solid_mask_tall(const uint32_t* __restrict__ tall, const unsigned* __restrict__ n_tall, const double* __restrict__ pts,
-                MaskGrid g, TileGrid tg, int lane_shift) {
+solid_mask_tall_per_face(const uint32_t* __restrict__ tall, const unsigned* __restrict__ n_tall, const double* __restrict__ pts,
+                         MaskGrid g, TileGrid tg, int lane_shift) {
     const unsigned n = *n_tall;
     const int group_lanes = 1 << lane_shift;
     const unsigned groups_per_block = blockDim.x >> lane_shift;
@@ -376,6 +568,7 @@ solid_mask_tall(const uint32_t* __restrict__ tall, const unsigned* __restrict__ 
         tall_face_body(tall[idx], pts, g, tg, group_lane, group_lanes);
     }
 }
+#endif
 
 namespace {
 
@@ -597,14 +790,80 @@ void launch_rotate_solids(DeviceState& d, const Rot* rot, int n_rot) {
     C5_CUDA(cudaGetLastError());
 }
 
+namespace {
+
+// The three passes over the faces of `ss`, into g.mask (which may hold marks already; they only help).
+void mask_passes(DeviceState& d, SolidSet& ss, const MaskGrid& g, const TileGrid& tg) {
+    if (ss.n == 0) return;
+    d.mask_tall.ensure(static_cast<size_t>(std::max(d.solid_follow.n_faces, d.solid_static.n_faces)));
+    d.mask_counts.ensure(1);
+    dev_zero(d.mask_counts.p, sizeof(unsigned), d.stream);
+    const int ty0 = g.row_begin / tg.h, ty1 = (g.row_end + tg.h - 1) / tg.h;
+    if (kHostSim) { // the same three passes as host loops
+        count_launch();
+        for (int64_t i = 0; i < ss.n_faces; i++) {
+            const uint32_t f = ss.faces.p[i];
+            if (small_face_body(f, ss.pts_view.p, g)) d.mask_tall.p[d.mask_counts.p[0]++] = f;
+        }
+        count_launch();
+        for (int ty = ty0; ty < ty1; ty++) {
+            for (int tx = 0; tx < tg.tiles_x; tx++) tile_flag_body(ty, tx, g, tg);
+        }
+        count_launch();
+        for (unsigned i = 0; i < d.mask_counts.p[0]; i++) tall_face_body(d.mask_tall.p[i], ss.pts_view.p, g, tg, 0, 1);
+        return;
+    }
+    if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
+    constexpr int kBlock = 32 * kMaskWarps;
+#ifdef C5_EXPERIMENTS
+    const bool per_face = d.opt_mask_per_face > 0;
+#else
+    const bool per_face = false;
+#endif
+    // pass 1: small faces are drawn, tall ones listed
+    count_launch();
+    if (!per_face) {
+        solid_mask_small<<<grid_for(ss.n_faces, kBlock), kBlock, 0, d.stream>>>(ss.n_faces, ss.faces.p, ss.pts_view.p, g,
+                                                                                 d.mask_tall.p, d.mask_counts.p);
+    }
+#ifdef C5_EXPERIMENTS
+    else {
+        solid_mask_small_per_face<<<grid_for(ss.n_faces, 256), 256, 0, d.stream>>>(ss.n_faces, ss.faces.p, ss.pts_view.p, g,
+                                                                                    d.mask_tall.p, d.mask_counts.p);
+    }
+#endif
+    C5_CUDA(cudaGetLastError());
+    // pass 2: which tiles of the band are solid already
+    count_launch();
+    mask_tile_flags<<<grid_for(static_cast<int64_t>(ty1 - ty0) * tg.tiles_x, 256), 256, 0, d.stream>>>(g, tg, ty0, ty1);
+    C5_CUDA(cudaGetLastError());
+    // pass 3: tall faces, skipping tile rows that are solid already
+    count_launch();
+    if (!per_face) {
+        solid_mask_tall<<<static_cast<unsigned>(d.sm_count) * 16u, kBlock, 0, d.stream>>>(d.mask_tall.p, d.mask_counts.p,
+                                                                                          ss.pts_view.p, g, tg);
+    }
+#ifdef C5_EXPERIMENTS
+    else {
+        solid_mask_tall_per_face<<<static_cast<unsigned>(d.sm_count) * 8u, 256, 0, d.stream>>>(
+            d.mask_tall.p, d.mask_counts.p, ss.pts_view.p, g, tg, d.opt_mask_per_face - 1);
+    }
+#endif
+    C5_CUDA(cudaGetLastError());
+}
+
+} // namespace
+
+// The solid mask of rows [row_begin, row_end) of the view, in d.mask.
+//
+// Solids that do not follow the view (the reference's accretor sphere is never rotated, main.cpp:116)
+// have the same footprint in every view of a sweep: their mask depends on the pixel grid alone. It is
+// scan-converted ONCE per (resolution, window, upload) for the whole image into d.mask_static, and a view
+// starts from a copy of its band of it instead of from zeros; only the solids that follow the view
+// are scan-converted per view. Marks are ones OR-ed together, so the order cannot matter.
 void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, double y_min, double step_x,
                        double step_y, int row_begin, int row_end) {
     MaskGrid g{res_x, res_y, x_min, y_min, step_x, step_y, 1.0 / step_x, 1.0 / step_y, d.ys.p, d.mask.p, row_begin, row_end};
-    SolidSet* sets[2] = {&d.solid_follow, &d.solid_static};
-    // tall-face lists of the two sets, back to back; their lengths at mask_counts[0..1]
-    const size_t cap = static_cast<size_t>(d.solid_follow.n_faces + d.solid_static.n_faces);
-    d.mask_tall.ensure(cap);
-    d.mask_counts.ensure(2);
     int tile_w = kTileW, tile_h = kTileH;
     if (d.opt_mask_tile > 0) {
         tile_w = std::max(8, (d.opt_mask_tile / 100) & ~7);
@@ -613,57 +872,28 @@ void launch_solid_mask(DeviceState& d, int res_x, int res_y, double x_min, doubl
     TileGrid tg{nullptr, (res_x + tile_w - 1) / tile_w, (res_y + tile_h - 1) / tile_h, tile_w, tile_h};
     d.mask_tiles.ensure(static_cast<size_t>(tg.tiles_x) * tg.tiles_y);
     tg.full = d.mask_tiles.p;
-    dev_zero(d.mask_counts.p, 2 * sizeof(unsigned), d.stream);
-    uint32_t* tall[2] = {d.mask_tall.p, d.mask_tall.p + d.solid_follow.n_faces};
-    const int ty0 = row_begin / tg.h, ty1 = (row_end + tg.h - 1) / tg.h;
-    if (kHostSim) { // the same three passes as host loops
-        for (int k = 0; k < 2; k++) {
-            if (sets[k]->n == 0) continue;
-            count_launch();
-            for (int64_t i = 0; i < sets[k]->n_faces; i++) {
-                const uint32_t f = sets[k]->faces.p[i];
-                if (small_face_body(f, sets[k]->pts_view.p, g)) tall[k][d.mask_counts.p[k]++] = f;
-            }
+    const size_t n_pix = static_cast<size_t>(res_x) * res_y;
+    uint8_t* band = d.mask.p + static_cast<size_t>(row_begin) * res_x;
+    const size_t band_bytes = static_cast<size_t>(row_end - row_begin) * res_x;
+    if (d.solid_static.n > 0 && !d.opt_no_static_mask) {
+        StaticMaskKey key{res_x, res_y, x_min, y_min, step_x, step_y};
+        if (!d.mask_static_valid || std::memcmp(&key, &d.mask_static_key, sizeof(key)) != 0) {
+            d.mask_static.ensure(n_pix);
+            dev_zero(d.mask_static.p, n_pix, d.stream);
+            MaskGrid gs = g;
+            gs.mask = d.mask_static.p;
+            gs.row_begin = 0;
+            gs.row_end = res_y;
+            mask_passes(d, d.solid_static, gs, tg);
+            d.mask_static_key = key;
+            d.mask_static_valid = true;
         }
-        count_launch();
-        for (int ty = ty0; ty < ty1; ty++) {
-            for (int tx = 0; tx < tg.tiles_x; tx++) tile_flag_body(ty, tx, g, tg);
-        }
-        for (int k = 0; k < 2; k++) {
-            if (sets[k]->n == 0) continue;
-            count_launch();
-            for (unsigned i = 0; i < d.mask_counts.p[k]; i++) tall_face_body(tall[k][i], sets[k]->pts_view.p, g, tg, 0, 1);
-        }
-        return;
+        d2d(band, d.mask_static.p + static_cast<size_t>(row_begin) * res_x, band_bytes, d.stream);
+    } else {
+        dev_zero(band, band_bytes, d.stream);
+        mask_passes(d, d.solid_static, g, tg);
     }
-    // pass 1: small faces are drawn, tall ones listed
-    for (int k = 0; k < 2; k++) {
-        if (sets[k]->n == 0) continue;
-        count_launch();
-        solid_mask_small<<<grid_for(sets[k]->n_faces, 256), 256, 0, d.stream>>>(sets[k]->n_faces, sets[k]->faces.p,
-                                                                                  sets[k]->pts_view.p, g, tall[k], d.mask_counts.p + k);
-        C5_CUDA(cudaGetLastError());
-    }
-    // pass 2: which tiles of the band are solid already
-    count_launch();
-    mask_tile_flags<<<grid_for(static_cast<int64_t>(ty1 - ty0) * tg.tiles_x, 256), 256, 0, d.stream>>>(g, tg, ty0, ty1);
-    C5_CUDA(cudaGetLastError());
-    // pass 3: tall faces, skipping tile rows that are solid already
-    if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
-    for (int k = 0; k < 2; k++) {
-        if (sets[k]->n == 0) continue;
-        // Lanes per face. With most tile rows skipped a tall face is a few hundred instructions, about as
-        // much as its setup (three divides), which every lane of a group repeats: one lane per face unless
-        // faces are hundreds of tile rows tall (c5_debug_set "mask_lane_shift" overrides, for experiments).
-        const double tile_rows = std::min(sets[k]->extent / step_y, static_cast<double>(row_end - row_begin)) / tg.h;
-        int lane_shift = 0;
-        while (lane_shift < 5 && (256 << lane_shift) < tile_rows) lane_shift++;
-        if (d.opt_mask_lane_shift > 0) lane_shift = d.opt_mask_lane_shift - 1;
-        count_launch();
-        solid_mask_tall<<<static_cast<unsigned>(d.sm_count) * 8u, 256, 0, d.stream>>>(tall[k], d.mask_counts.p + k,
-                                                                                      sets[k]->pts_view.p, g, tg, lane_shift);
-        C5_CUDA(cudaGetLastError());
-    }
+    mask_passes(d, d.solid_follow, g, tg);
 }
 
 void launch_prepare_cells(DeviceState& dd, double alpha_limit) {

@@ -20,6 +20,11 @@ constexpr int kTimelinePhases = 6; // start, rotated, refitted, masked, pixel ke
 enum Counter { kSteps = 0, kHitPixels = 1, kSolidPixels = 2, kWalkErrors = 3, kDeferred = 4, kTicket = 5,
                kNumCounters = 8 };
 
+struct StaticMaskKey {  // what the footprint of a solid that is never rotated depends on (all of it, bit for bit)
+    int res_x, res_y;
+    double x_min, y_min, step_x, step_y;
+};
+
 struct SolidSet {
     DevBuf<double> pts0;      // [n][4][3] pre-view frame
     DevBuf<double> pts_view;  // [n][4][3] view frame (rotated copy, or == pts0 content for static ones)
@@ -73,6 +78,9 @@ struct DeviceState {
     DevBuf<uint32_t> mask_tall;      // solid mask: faces taller than a few rows, listed by the first pass
     DevBuf<unsigned> mask_counts;    // their number per solid set
     DevBuf<uint8_t> mask_tiles;      // "every pixel of this 16 x 8 tile is solid already"
+    DevBuf<uint8_t> mask_static;     // whole-image mask of the solids that do not follow the view (cached)
+    StaticMaskKey mask_static_key{}; // the pixel grid mask_static was scan-converted for
+    bool mask_static_valid = false;  // reset by every upload / clear of solids
     DevBuf<double> out;              // band output, {tau, I} per pixel
     DevBuf<uint32_t> steps;
     DevBuf<unsigned long long> counters;
@@ -86,8 +94,8 @@ struct DeviceState {
     uint64_t* h_row_cost = nullptr;             // [h_row_cost_n]
     size_t h_row_cost_n = 0;
     // c5_debug_set (tests, diagnostics); 0 = default
-    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0, opt_mask_lane_shift = 0, opt_mask_tile = 0;
-    bool opt_no_zero_copy = false, opt_prep_priority = false;
+    int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0, opt_mask_per_face = 0, opt_mask_tile = 0;
+    bool opt_no_zero_copy = false, opt_prep_priority = false, opt_no_static_mask = false;
     cudaStream_t prep_stream = nullptr;         // high priority: rotate / refit / mask when opt_prep_priority
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // c5_debug_set("timeline", n): phase events of the last n views, read by c5_timeline_read

@@ -338,6 +338,15 @@ C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, d
     cx -= px; cy -= py;
     int t = f.w;
     double z_cur = z_in;
+    // kPipe == 2 (software-pipelined loop): the cell and the vertex of step k+1 are requested as soon as
+    // step k knows its exit face, BEFORE its divide and exp — the loads' latency overlaps that math.
+    // Costs the registers of one cell + one vertex in flight next to the math's temporaries.
+    CellData c;
+    double dx, dy, dz;
+    if (kPipe == 2) {
+        c = load_cell<kWide>(P.cells, t);
+        load_vtx(P.vrot, id, dx, dy, dz);
+    }
     while (true) {
         if (steps >= static_cast<uint32_t>(P.max_steps)) {
             error = 1;
@@ -346,9 +355,10 @@ C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, d
         // id = the vertex of tet t that is not on the entry face. It is known BEFORE t's cell is
         // read (Cell::apex of the previous tet, BFace::apex at entry), so the cell load and the
         // vertex load of a step are independent and overlap: one memory latency per step, not two.
-        const CellData c = load_cell<kWide>(P.cells, t);
-        double dx, dy, dz;
-        load_vtx(P.vrot, id, dx, dy, dz);
+        if (kPipe != 2) {
+            c = load_cell<kWide>(P.cells, t);
+            load_vtx(P.vrot, id, dx, dy, dz);
+        }
         dx -= px;
         dy -= py;
         const double sa = orient2(dx, dy, ax, ay);
@@ -387,17 +397,22 @@ C5_HD double crossing_f64(const WalkParams& P, double px, double py, int leaf, d
             wa = sc;
             wb = orient2(cx, cy, ax, ay);
         }
+        const double alpha_t = c.alpha, s_t = c.s;
+        if (kPipe == 2 && t_next >= 0) { // the next step's operands, on their way while this step finishes
+            c = load_cell<kWide>(P.cells, t_next);
+            load_vtx(P.vrot, id_next, dx, dy, dz);
+        }
         const double wsum = wa + wb + wc;
         const double z_exit = (wsum != 0.0) ? (wa * az + wb * bz + wc * cz) / wsum : z_cur;
         const double dzv = fabs(z_exit - z_cur);
         // tau: line.cpp:176-193 (alpha not clamped)
-        tau += dzv * c.alpha;
+        tau += dzv * alpha_t;
         // I: line.cpp:206-225 with s = Q / a^:  (Q - (Q - a^ I) e) / a^  ==  s - (s - I) e
-        double a_c = c.alpha;
+        double a_c = alpha_t;
         if (a_c > P.alpha_limit) a_c = P.alpha_limit;
         if (!(a_c < DBL_EPSILON)) {
             const double e = exp(-a_c * dzv);
-            inten = c.s - (c.s - inten) * e;
+            inten = s_t - (s_t - inten) * e;
             if (kAffine) gain *= e;
         }
         steps++;
@@ -1158,6 +1173,10 @@ __global__ void __launch_bounds__(kBlock, 6) tet_walk_fp64_r80(const WalkParams 
 __global__ void __launch_bounds__(kBlock, 8) tet_walk_fp64_r64(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_r96(const WalkParams P) { walk_block<false, true, 0>(P); }
 __global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_rec(const WalkParams P) { walk_block<false, true, 0, 2, 2, true>(P); }
+// software-pipelined step loop (kPipe == 2) at 5, 6 and 7 resident blocks per SM (96 / 80 / 72 registers)
+__global__ void __launch_bounds__(kBlock, 5) tet_walk_fp64_sp5(const WalkParams P) { walk_block<false, true, 2>(P); }
+__global__ void __launch_bounds__(kBlock, 6) tet_walk_fp64_sp6(const WalkParams P) { walk_block<false, true, 2>(P); }
+__global__ void __launch_bounds__(kBlock, 7) tet_walk_fp64_sp7(const WalkParams P) { walk_block<false, true, 2>(P); }
 // Builds the four step records of every tet from its Cell (after prepare_cells: s depends on --alpha_limit).
 __global__ void __launch_bounds__(256) build_step_records(int64_t n_faces, const Cell* __restrict__ cells, StepRec* __restrict__ recs) {
     const int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -1374,6 +1393,12 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
         tet_walk_fp64_r64<<<grid, kBlock, smem, d.stream>>>(P);
     } else if (var == "r96") {
         tet_walk_fp64_r96<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "sp5") {
+        tet_walk_fp64_sp5<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "sp6") {
+        tet_walk_fp64_sp6<<<grid, kBlock, smem, d.stream>>>(P);
+    } else if (var == "sp7") {
+        tet_walk_fp64_sp7<<<grid, kBlock, smem, d.stream>>>(P);
     } else {
         tet_walk_fp64<<<grid, kBlock, smem, d.stream>>>(P);
     }

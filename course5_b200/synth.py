@@ -166,6 +166,9 @@ CONFIGS = {
                view=dict(X=0.4, Y=0.0, D=0.1, I=-0.03, alpha_limit=2.5)),
     "C5": dict(n=203, seed=5, gen=dict(grade_beta=1.5), res=(4800, 3600),
                view=dict(X=0.4, Y=0.3, D=0.0, I=0.0, alpha_limit=2.5)),
+    # north_star's own target workload: "a 2400 x 1800 view of a 50M-tet mesh" (C5's mesh, C3's resolution)
+    "C5t": dict(n=203, seed=5, gen=dict(grade_beta=1.5), res=(2400, 1800),
+                view=dict(X=0.4, Y=0.3, D=0.0, I=0.0, alpha_limit=2.5)),
 }
 
 

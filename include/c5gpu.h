@@ -212,7 +212,10 @@ uint64_t c5_kernel_launches(const c5_ctx* ctx);
  *   "serial_list"   the same for the serial form of the CPU test build (2..64)
  *   "graze_blocks"  blocks per SM of the grazing-ray kernel's grid (tuning experiments; 0 = default)
  *   "mask_tile"     100 w + h: tile size of the solid mask's "already solid" flags (0 = default)
- *   "mask_lane_shift" n > 0: 2^(n-1) lanes share a tall solid face in the mask's third pass (0 = automatic)
+ *   "mask_per_face" n > 0: the solid mask's face passes run one face per thread, 2^(n-1) lanes per tall face
+ *                   (only in the experiments build, libc5gpu_exp.so; the product library ignores it)
+ *   "no_static_mask" 1: solids that do not follow the view are scan-converted in every view, like the
+ *                   others, instead of once per pixel grid (tests compare the two)
  *   "prep_priority" 1: rotate / refit / mask of a view run on a high-priority stream of their own
  *   "no_zero_copy"  1: page-locked output buffers get a device-to-host copy like pageable ones
  *   "timeline"      n > 0: keep the phase events of the last n views of every lane (0 = off)

@@ -87,7 +87,8 @@ def main():
                     **{k: round(float(np.median(x)), 4) for k, x in acc.items()},
                     "walk_Gsteps_per_s": round(st["tet_steps"] / walk / 1e6, 2), "walk_alg_GBps": round(gbs, 1),
                     "frac_of_6455.9": round(gbs / 6455.9, 3), "gen_s": round(t_gen, 2), "upload_s": round(t_up, 3),
-                    "device_MB": round(info.device_bytes / 1e6, 1), "bfaces": info.n_boundary_faces}), flush=True)
+                    "device_MB": round(info.device_bytes / 1e6, 1), "bfaces": info.n_boundary_faces,
+                    "debug": args.debug, "library": os.path.basename(os.environ.get("C5GPU_LIBRARY", "libc5gpu.so"))}), flush=True)
         ctx.close()
         del mesh
 

@@ -221,6 +221,58 @@ def check_solid_mask_high_resolution(lib, port, res=(1200, 900), views=((0.4, 0.
         assert np.array_equal(np.isnan(got.tau), want.solid.astype(bool))
 
 
+def check_static_solid_mask_cache(lib, port, res=(400, 300)):
+    """Solids that do not follow the view are scan-converted once per pixel grid (launch_solid_mask);
+    the cached footprint must give the masks the uncached path gives — across views, row bands cut
+    at odd rows, a change of resolution, a change of window and a second upload of static solids —
+    and those must be the oracle's."""
+    mesh = synth.kuhn_cube(3, seed=11)
+    roche, sphere = reference_solids(0.1)
+    extra = sphere[: len(sphere) // 7].copy()
+    extra[:, :, 0] += 0.35            # a second static solid, shifted so that its footprint is new
+    extra[:, :, 1] += 0.2
+
+    def masks(ctx, views):
+        out = []
+        for kw in views:
+            v = api.make_view(lib=lib, round_through_float=0, **kw)
+            out.append(ctx.render_raw(v).solid.copy())
+        return out
+
+    views = [dict(res_x=res[0], res_y=res[1], X=0.4, Y=0.3),
+             dict(res_x=res[0], res_y=res[1], X=0.5, Y=1.3),
+             dict(res_x=res[0], res_y=res[1], X=0.5, Y=1.3, row_begin=res[1] // 2 - 13, row_end=res[1] // 2 + 29),
+             dict(res_x=res[0] + 8, res_y=res[1] - 6, X=0.1, Y=0.2),
+             dict(res_x=res[0], res_y=res[1], X=0.4, Y=0.3, window=(2.0, -0.1, 0.8, -0.85)),
+             dict(res_x=res[0], res_y=res[1], X=0.4, Y=0.3)]
+    got = {}
+    for cached in (True, False):
+        with api.Context(devices=(0,), lib=lib) as ctx:
+            if not cached:
+                ctx.debug_set("no_static_mask", 1)
+            ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+            ctx.upload_solids(roche, True)
+            ctx.upload_solids(sphere, False)
+            first = masks(ctx, views)
+            ctx.upload_solids(extra, False)                      # must invalidate the cached footprint
+            second = masks(ctx, views[:2])
+            ctx.clear_solids()
+            ctx.upload_solids(roche, True)
+            third = masks(ctx, views[:1])                        # no static solid left: nothing of it may remain
+            got[cached] = first + second + third
+    for a, b in zip(got[True], got[False]):
+        assert np.array_equal(a, b)
+    assert got[True][6].sum() > got[True][0].sum() > got[True][8].sum() > 0
+    for k in (0, 1):
+        kw = views[k]
+        want = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=kw["res_x"], res_y=kw["res_y"], X=kw["X"], Y=kw["Y"],
+                           solid_rot=roche, solid_static=sphere)
+        assert np.array_equal(got[True][k], want.solid)
+    band = views[2]
+    inside = got[True][2][band["row_begin"]: band["row_end"]]
+    assert np.array_equal(inside, got[True][1][band["row_begin"]: band["row_end"]])
+
+
 def check_grazing_rays(lib, port, *, n=12, res=(240, 180), debug_key="serial_list", debug_value=5):
     """Views that look along a lattice axis see the jittered side walls edge-on: rays there leave
     and re-enter the mesh once per cell. The pixel kernel hands them to the grazing-ray kernel

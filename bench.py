@@ -42,6 +42,11 @@ BYTES_PER_PIXEL = 16     # {tau, I} doubles written
 REL_TOL, ABS_FLOOR = 1e-9, 1e-13   # the parity gate (tests/parity.py, BASELINE.json north_star)
 
 
+def E2E_AUTO(world: int) -> str:
+    """How the image reaches the page-locked host buffer when --e2e-mode is left alone."""
+    return "inplace"
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -334,7 +339,8 @@ def run_ours(args):
     upload_s = time.perf_counter() - t0
     v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
                       alpha_limit=view["alpha_limit"], lib=ctx.lib)
-    br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=args.lanes)
+    lanes = args.lanes if args.lanes > 0 else (4 if mesh.n_tets <= 16_000_000 else 2)
+    br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=lanes)
 
     def barrier():
         if world > 1:
@@ -352,8 +358,8 @@ def run_ours(args):
         # bands cut so that every rank sustains the same pipelined time per view (a sweep does the same
         # from frame to frame): rounds of a few views each, no exchange, re-cut after each
         dog.tick("band calibration")
-        br.calibrate(v, rounds=args.calibrate, views=8)
-        n_warm += args.calibrate * 9
+        br.calibrate(v, rounds=args.calibrate, views=12)
+        n_warm += args.calibrate * (1 + 12 + 2 * (br.n_lanes + 2))
     bands = br.bands(view["res_y"])
     dog.tick(f"bands {bands}")
     barrier()
@@ -445,7 +451,10 @@ def run_ours(args):
     dog.tick("e2e: host images")
     L = br.n_lanes
     ctx.set_views_in_flight(L)
-    if args.e2e_mode == "copy":
+    e2e_mode = args.e2e_mode
+    if e2e_mode == "auto":
+        e2e_mode = E2E_AUTO(world)
+    if e2e_mode == "copy":
         ctx.debug_set("no_zero_copy", 1)
     lo, hi = bands[rank]
     shared = SharedHostImage(ctx, view["res_x"], view["res_y"], rank=rank, world=world, sets=L + 1)
@@ -538,8 +547,10 @@ def run_ours(args):
                 "host_enqueue_ms_per_view": host_enqueue_ms},
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(api.C.sizeof(api.View)) * world, "d2h_bytes_per_step": pixels * 16 + world * (64 + 8 * view["res_y"]),
-                    "views_in_flight": L, "image_spot_check": e2e_image_ok, "mode": args.e2e_mode,
-                    "api": "c5_render_submit / c5_render_wait into page-locked host images written in place by the walk kernels" +
+                    "views_in_flight": L, "image_spot_check": e2e_image_ok, "mode": e2e_mode,
+                    "api": "c5_render_submit / c5_render_wait into page-locked host images " +
+                           ("written in place by the walk kernels" if e2e_mode == "inplace" else
+                            "(band rendered in device memory, brought over by the copy engine)") +
                            ("" if world == 1 else " (one shared-memory image per view, every rank its band over its own PCIe link; completion flags in the segment)")},
             "gpu_launches": total_launches,
             "roofline": {"kernel": "tet_walk_fp64 + grazing_rays_fp64", "rank": busiest, "bound": "hbm",
@@ -601,14 +612,16 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default="C3", choices=sorted(synth.CONFIGS),
                     help="named configuration (course5_b200.synth.CONFIGS); C3 is BASELINE.json's metric configuration")
-    ap.add_argument("--lanes", type=int, default=4, choices=range(1, api.MAX_IN_FLIGHT + 1),
-                    help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each)")
+    ap.add_argument("--lanes", type=int, default=0, choices=range(0, api.MAX_IN_FLIGHT + 1),
+                    help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each); "
+                         "0 = by mesh size: 4 up to 16M tets, 2 above (measured: on the 50M-tet mesh four views in flight "
+                         "evict each other from L2, profiles/r02_exp_lanes_per_band_c3_c5t.jsonl)")
     ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="p2p",
                     help="N > 1: how bands reach rank 0's image. p2p = stored by the walk kernels straight into rank 0's image "
                          "over NVLink peer mappings (CUDA IPC); sendrecv = one grouped ncclSend/ncclRecv per view (the baseline)")
     ap.add_argument("--calibrate", type=int, default=5, help="N > 1: rounds of band calibration before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline + parity leg (profiling runs)")
-    ap.add_argument("--e2e-mode", choices=["inplace", "copy"], default="inplace",
+    ap.add_argument("--e2e-mode", choices=["auto", "inplace", "copy"], default="auto",
                     help="e2e: the walk kernels store into the page-locked host image in place (default), or render into "
                          "device memory and let the copy engine bring the image to the host (c5_debug_set no_zero_copy)")
     ap.add_argument("--debug", default="", help="c5_debug_set knobs for experiments, key=value[,key=value]")

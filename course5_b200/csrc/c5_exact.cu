@@ -142,22 +142,15 @@ C5_HD double edge_x(const EdgeFn& e, double y) {
     return div_by(e.dx * (y - e.y1), e.dy, e.rdy) + e.x1;
 }
 
-// Sets the bytes [p, e) to 1. Thousands of fan faces overlap every solid pixel, so a byte is tested
-// first and stored only the first time; the aligned middle of the span goes eight pixels at a time
-// (concurrent writers only ever write ones, so a wide store inside the span cannot lose anything).
+// Sets the bytes [p, e) to 1; the aligned middle of the span goes eight pixels at a time (concurrent
+// writers only ever write ones, so a wide store inside the span cannot lose anything). Write-only: a
+// test-before-store saved redundant stores while every fan face drew its whole footprint, but it makes
+// every pixel a dependent load (ncu, pass 1: 61 long-scoreboard stall cycles per issued instruction);
+// since the tile flags the rows that are still drawn are few and stores are fire-and-forget.
 C5_HD void mark_span(uint8_t* p, uint8_t* e) {
-    while (p < e && (reinterpret_cast<uintptr_t>(p) & 7u)) {
-        if (!*p) *p = 1;
-        p++;
-    }
-    const unsigned long long ones = 0x0101010101010101ull;
-    for (; p + 8 <= e; p += 8) {
-        unsigned long long* w = reinterpret_cast<unsigned long long*>(p);
-        if (*w != ones) *w = ones;
-    }
-    for (; p < e; p++) {
-        if (!*p) *p = 1;
-    }
+    while (p < e && (reinterpret_cast<uintptr_t>(p) & 7u)) *p++ = 1;
+    for (; p + 8 <= e; p += 8) *reinterpret_cast<unsigned long long*>(p) = 0x0101010101010101ull;
+    while (p < e) *p++ = 1;
 }
 
 // Everything the scan conversion of one projected triangle derives from its three points before the
@@ -647,6 +640,11 @@ struct SolidFaceFirstOp {
     }
 };
 
+struct WidenU32Op {
+    const uint32_t* src;
+    uint64_t* out;
+    C5_HD void operator()(int64_t i) const { out[i] = src[i]; }
+};
 struct GatherU32Op {
     const uint32_t* src;
     const uint32_t* idx;
@@ -938,6 +936,12 @@ void dedupe_solid_faces(DeviceState& d, SolidSet& ss) {
     const size_t n_u = select_flagged(first.p, pos.p, static_cast<size_t>(n_all), d.stream);
     ss.faces.alloc(n_u);
     for_each(d.stream, static_cast<int64_t>(n_u), GatherU32Op{vals.p, pos.p, ss.faces.p});
+    // ... in face-id order: consecutive threads of the per-view passes then read consecutive tets' points
+    // (the hash order left every thread alone in its cache line)
+    if (n_u > 1) {
+        for_each(d.stream, static_cast<int64_t>(n_u), WidenU32Op{ss.faces.p, keys.p});
+        sort_pairs_u64(keys.p, ss.faces.p, n_u, 32, d.stream);
+    }
     stream_sync(d.stream);
     ss.n_faces = static_cast<int64_t>(n_u);
 }

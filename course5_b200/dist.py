@@ -202,14 +202,13 @@ class BandRenderer:
         tails and grazing-ray kernels overlapped — not the time one view takes alone, and a band's
         rate per tet-step depends on what is in it (short silhouette rays, the solid mask, rows of
         grazing rays). So each round renders `views` pipelined views of this rank's band without
-        any exchange, times them with CUDA events, spreads the time over the band's rows in
-        proportion to their tet-steps (time_weighted_row_cost) and re-cuts; damped, because a band's
-        rate changes with its cut. Collective: every rank must call it with the same arguments."""
+        any exchange, times them with CUDA events (sustained rate: the difference of a long and a short
+        run), corrects the cost of the band's rows by measured / predicted and re-cuts. Collective:
+        every rank must call it with the same arguments."""
         cuda = self.device.type == "cuda"
-        for _ in range(rounds):
-            _, _, bands = self.render(view, gather=False, rebalance="steps")      # per-row tet-steps, all-reduced
-            steps = self.row_cost.copy()
-            lo, hi = bands[self.rank]
+
+        def timed(n: int) -> float:
+            """Milliseconds for n pipelined views of this rank's band, no exchange."""
             if cuda:
                 torch.cuda.synchronize(self.device)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -217,23 +216,46 @@ class BandRenderer:
             else:
                 import time
                 t0 = time.perf_counter()
-            for _ in range(views):
+            for _ in range(n):
                 self.render(view, gather=False, stats=False, pipeline=True)
             self.finish()
             if cuda:
                 e1.record()
                 torch.cuda.synchronize(self.device)
-                ms = e0.elapsed_time(e1) / views
+                return e0.elapsed_time(e1)
+            return 1e3 * (time.perf_counter() - t0)
+
+        for _ in range(rounds):
+            _, _, bands = self.render(view, gather=False, rebalance="steps")      # per-row tet-steps, all-reduced
+            steps = self.row_cost.copy()
+            lo, hi = bands[self.rank]
+            # The SUSTAINED time per view: a short run and a long one, and the difference between them. Timing
+            # one run and dividing by its views charges every band the latency of its first view (the pipeline
+            # filling), which differs between bands by more than their sustained times do (measured on C3 at
+            # N = 8: first views 1.06 .. 1.73 ms, sustained 0.63 .. 0.76 ms — the cuts came out 10 % off).
+            short = self.n_lanes + 2
+            t_short = timed(short)
+            t_long = timed(short + views)
+            ms = max(t_long - t_short, 0.05 * t_long) / views
+            if self._time_cost is None or self._time_cost.shape != steps.shape:
+                # first estimate: the band's time spread over its rows in proportion to their tet-steps
+                mine = torch.from_numpy(api.time_weighted_row_cost(steps, (lo, hi), ms, base_cost=self.base_cost))
             else:
-                ms = 1e3 * (time.perf_counter() - t0) / views
-            mine = torch.from_numpy(api.time_weighted_row_cost(steps, (lo, hi), ms, base_cost=self.base_cost))
+                # afterwards: the rows keep the cost they have (it carries what earlier rounds learnt about how
+                # the rate differs from band to band) and the band as a whole is corrected towards what it
+                # measured now; rows that change bands take their cost with them
+                mine = torch.zeros(steps.shape[0], dtype=torch.float64)
+                have = self._time_cost[lo:hi]
+                predicted = float(have.sum())
+                if predicted > 0.0:
+                    mine[lo:hi] = torch.from_numpy(have * (ms / predicted) ** 0.8)
+                else:
+                    mine[lo:hi] = ms / max(hi - lo, 1)
             if self.world > 1:
                 mine = mine.to(self.device)
                 dist.all_reduce(mine, op=dist.ReduceOp.SUM)
                 mine = mine.cpu()
             new_cost = mine.numpy().astype(np.float64)
-            if self._time_cost is not None and self._time_cost.shape == new_cost.shape:
-                new_cost = 0.5 * (new_cost + self._time_cost)
             self._time_cost = new_cost
             self.row_cost, self._cost_has_base = new_cost, True
             self._bands = None

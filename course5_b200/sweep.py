@@ -63,6 +63,9 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="lattice size override")
     ap.add_argument("--out-dir", default=None, help="write frame_%04d.vti here")
     ap.add_argument("--in-flight", type=int, default=3, help="views in flight per GPU")
+    ap.add_argument("--no-zero-copy", action="store_true",
+                    help="render into device memory and let the copy engine bring each image to the host, instead of "
+                         "the walk kernels storing into the page-locked host image in place")
     args = ap.parse_args()
 
     import torch
@@ -77,6 +80,8 @@ def main():
     mesh, view = synth.make_config(args.config, n=args.n)
     roche, sphere = hostlib.make_solids(view["D"])
     ctx = api.Context(devices=(local,))
+    if args.no_zero_copy:
+        ctx.debug_set("no_zero_copy", 1)
     t0 = time.perf_counter()
     ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
     ctx.upload_solids(roche, True)
@@ -109,7 +114,7 @@ def main():
     if rank == 0:
         print(json.dumps({"config": args.config, "frames": args.frames, "n_gpus": world, "seconds": dt,
                           "views_per_sec": args.frames / dt, "ms_per_view": 1e3 * dt / args.frames,
-                          "tet_steps_per_sec": steps / dt, "tet_steps": steps, "views_in_flight": args.in_flight,
+                          "tet_steps_per_sec": steps / dt, "tet_steps": steps, "views_in_flight": args.in_flight, "image_path": "copy engine" if args.no_zero_copy else "stored in place",
                           "res": [view["res_x"], view["res_y"]], "n_tets": mesh.n_tets,
                           "flags": {k: view[k] for k in ("X", "D", "I", "alpha_limit")},
                           "upload_and_topology_s": upload_s,

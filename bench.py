@@ -339,7 +339,12 @@ def run_ours(args):
     upload_s = time.perf_counter() - t0
     v = api.make_view(view["res_x"], view["res_y"], X=view["X"], Y=view["Y"], I=view["I"],
                       alpha_limit=view["alpha_limit"], lib=ctx.lib)
-    lanes = args.lanes if args.lanes > 0 else (4 if mesh.n_tets <= 16_000_000 else 2)
+    # views in flight (measured, profiles/README.md round 2): one GPU rendering whole views is saturated by two
+    # (4.41 ms per view, steady; four: 4.44-4.66); a band of 1/N of the image is a single wave of blocks and wants
+    # four (0.65 vs 0.75 ms); on the 50M-tet mesh four views evict each other from L2 (6.2 vs 5.7 ms)
+    big = mesh.n_tets > 16_000_000
+    lanes = args.lanes if args.lanes > 0 else (2 if (world == 1 or big) else 4)
+    e2e_in_flight = args.lanes if args.lanes > 0 else (3 if big else 4)   # submit/wait needs a third view to hide the host
     br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=lanes)
 
     def barrier():
@@ -358,8 +363,8 @@ def run_ours(args):
         # bands cut so that every rank sustains the same pipelined time per view (a sweep does the same
         # from frame to frame): rounds of a few views each, no exchange, re-cut after each
         dog.tick("band calibration")
-        br.calibrate(v, rounds=args.calibrate, views=12)
-        n_warm += args.calibrate * (1 + 12 + 2 * (br.n_lanes + 2))
+        br.calibrate(v, rounds=args.calibrate, views=32)
+        n_warm += 1 + args.calibrate * (32 + br.n_lanes + 2)
     bands = br.bands(view["res_y"])
     dog.tick(f"bands {bands}")
     barrier()
@@ -387,7 +392,7 @@ def run_ours(args):
     # pass): consecutive views rotate over the lanes — the context and siblings that share its mesh,
     # each on its own stream — so the tail of one view's walk and its grazing-ray kernel overlap the
     # next views. N > 1, gather=p2p: the walk stores straight into rank 0's image over NVLink and the
-    # barrier of view k is left in flight (lanes + 1 images); gather=sendrecv: the same with one
+    # barrier of view k is left in flight (2 lanes + 1 images); gather=sendrecv: the same with one
     # grouped ncclSend/ncclRecv per view.
     # one untimed pipelined round with the final bands: every lane, every image set and every lazily
     # created mapping has been used once before the clock starts
@@ -416,7 +421,7 @@ def run_ours(args):
     ev0.record()
     t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        br.render(v, rebalance=False, stats=False, pipeline=True)
+        br.render(v, rebalance=False, stats=False, pipeline=True, gather=not args.experiment_no_exchange)
         host_t.append(time.perf_counter() - t_host0)
     br.finish()
     ev1.record()
@@ -449,7 +454,7 @@ def run_ours(args):
     # image when all bands are in. Wall clock around the calls a user makes; every step's image is
     # complete in host memory (and its stats read) inside the timed region.
     dog.tick("e2e: host images")
-    L = br.n_lanes
+    L = e2e_in_flight
     ctx.set_views_in_flight(L)
     e2e_mode = args.e2e_mode
     if e2e_mode == "auto":
@@ -457,7 +462,8 @@ def run_ours(args):
     if e2e_mode == "copy":
         ctx.debug_set("no_zero_copy", 1)
     lo, hi = bands[rank]
-    shared = SharedHostImage(ctx, view["res_x"], view["res_y"], rank=rank, world=world, sets=L + 1)
+    n_img = L + 1 if world == 1 else 2 * L + 1   # N > 1: a rank may run a round of views ahead of the slowest one
+    shared = SharedHostImage(ctx, view["res_x"], view["res_y"], rank=rank, world=world, sets=n_img)
 
     def e2e_run(n_views, base):
         """Views base .. base + n_views - 1 (the flags in the segment count views since its creation)."""
@@ -483,7 +489,7 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     e2e_image_ok = True
     if rank == 0:   # the last host image is the view (spot check: same NaN mask and finite elsewhere)
-        last = shared.arrays[(2 * L + args.steps - 1) % (L + 1)]
+        last = shared.arrays[(2 * L + args.steps - 1) % n_img]
         e2e_image_ok = bool(np.isnan(last).any() and np.isfinite(last[~np.isnan(last)]).all() and (last != 0).any())
     shared.close()
     assert e2e_steps == band_steps * args.steps, (e2e_steps, band_steps)
@@ -515,7 +521,7 @@ def run_ours(args):
             gathered = [timeline]
         if rank == 0:
             with open(args.timeline, "w") as f:
-                json.dump({"n_gpus": world, "steps": args.steps, "lanes": L, "gather": br.gather_mode, "ranks": gathered}, f)
+                json.dump({"n_gpus": world, "steps": args.steps, "lanes": br.n_lanes, "gather": br.gather_mode, "ranks": gathered}, f)
 
     if rank == 0:
         pixels = view["res_x"] * view["res_y"]
@@ -574,6 +580,12 @@ def run_ours(args):
         }
         if parity is not None:
             line["parity"] = parity
+        if args.experiment_no_exchange:
+            line["INVALID"] = "--experiment-no-exchange: the timed views were not assembled into one image"
+        if br.calibration_log:
+            # per calibration round: the cut that was timed and the sustained ms per view every rank measured for
+            # its band alone (no exchange); the last entry is the round BEFORE the final re-cut
+            line["calibration"] = br.calibration_log
         if os.environ.get("C5_BENCH_ATTEMPTS"):
             line["attempts"] = json.loads(os.environ["C5_BENCH_ATTEMPTS"])   # configurations left before this one
         if world == 1 and not args.no_cpu_baseline:
@@ -613,18 +625,20 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(synth.CONFIGS),
                     help="named configuration (course5_b200.synth.CONFIGS); C3 is BASELINE.json's metric configuration")
     ap.add_argument("--lanes", type=int, default=0, choices=range(0, api.MAX_IN_FLIGHT + 1),
-                    help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each); "
-                         "0 = by mesh size: 4 up to 16M tets, 2 above (measured: on the 50M-tet mesh four views in flight "
-                         "evict each other from L2, profiles/r02_exp_lanes_per_band_c3_c5t.jsonl)")
+                    help="views in flight per GPU (the context and lanes-1 siblings sharing its mesh, one stream each), for the "
+                         "device-timed value and for e2e alike; 0 = chosen from N and the mesh size (see run_ours)")
     ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="p2p",
                     help="N > 1: how bands reach rank 0's image. p2p = stored by the walk kernels straight into rank 0's image "
                          "over NVLink peer mappings (CUDA IPC); sendrecv = one grouped ncclSend/ncclRecv per view (the baseline)")
-    ap.add_argument("--calibrate", type=int, default=5, help="N > 1: rounds of band calibration before the timed region")
+    ap.add_argument("--calibrate", type=int, default=6, help="N > 1: rounds of band calibration before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline + parity leg (profiling runs)")
     ap.add_argument("--e2e-mode", choices=["auto", "inplace", "copy"], default="auto",
                     help="e2e: the walk kernels store into the page-locked host image in place (default), or render into "
                          "device memory and let the copy engine bring the image to the host (c5_debug_set no_zero_copy)")
     ap.add_argument("--debug", default="", help="c5_debug_set knobs for experiments, key=value[,key=value]")
+    ap.add_argument("--experiment-no-exchange", action="store_true",
+                    help="EXPERIMENT, not a measurement of the product path: the timed views skip the image exchange and its "
+                         "per-view barrier, to see what the coupling of the ranks costs (the line is marked invalid)")
     ap.add_argument("--no-clock-sampler", action="store_true", help="experiments: no NVML polling at all")
     ap.add_argument("--timeline", default=None, metavar="FILE",
                     help="write per-rank, per-view phase times of the timed region (CUDA events) and host enqueue times as JSON")
@@ -679,6 +693,8 @@ def run_with_fallback(args):
             cmd += ["--timeline", args.timeline]
         if args.no_clock_sampler:
             cmd.append("--no-clock-sampler")
+        if args.experiment_no_exchange:
+            cmd.append("--experiment-no-exchange")
         try:   # stderr passes through; the hard limit is a second line of defence behind the child's watchdog
             p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True, preexec_fn=_die_with_parent,
                                timeout=float(os.environ.get("C5_BENCH_ATTEMPT_LIMIT", "600")))

@@ -193,7 +193,7 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
         cudaStream_t main;
         ~StreamSwap() { d.stream = main; }
     } swap{d, d.stream};
-    const bool prep = !kHostSim && d.opt_prep_priority && d.prep_stream != nullptr;
+    const bool prep = !kHostSim && (d.opt_prep_priority & 1) && d.prep_stream != nullptr;
     if (prep) {
         C5_CUDA(cudaEventRecord(d.ev_fork, swap.main)); // after whatever the caller's stream holds (this lane's previous view)
         C5_CUDA(cudaStreamWaitEvent(d.prep_stream, d.ev_fork, 0));
@@ -234,6 +234,8 @@ void enqueue_view(DeviceState& d, const c5_view* v, const ViewPlan& p, bool want
     w.out = out_override ? out_override : d.out.p;
     w.mark_walk_done = d.ev_walk;
     w.mark_walk_done_tl = nullptr;
+    w.graze_stream = (!kHostSim && (d.opt_prep_priority & 2) && d.prep_stream) ? d.prep_stream : nullptr;
+    w.graze_join = d.ev_join;
     if (!kHostSim && !d.tl_events.empty()) {
         const size_t n = d.tl_events.size() / kTimelinePhases;
         w.mark_walk_done_tl = d.tl_events[(d.tl_views % n) * kTimelinePhases + 4];
@@ -1226,7 +1228,7 @@ int c5_debug_set(c5_ctx* ctx, const char* key, int64_t value) {
                 else if (k == "query_budget") d.opt_query_budget = static_cast<int>(value);
                 else if (k == "serial_list") d.opt_serial_list = static_cast<int>(value);
                 else if (k == "graze_blocks") d.opt_graze_blocks = static_cast<int>(value);
-                else if (k == "prep_priority") d.opt_prep_priority = value != 0;
+                else if (k == "prep_priority") d.opt_prep_priority = static_cast<int>(value & 3);
                 else if (k == "mask_tile") d.opt_mask_tile = static_cast<int>(value);
                 else if (k == "mask_per_face") d.opt_mask_per_face = static_cast<int>(value < 0 ? 0 : value > 6 ? 6 : value);
                 else if (k == "no_static_mask") {

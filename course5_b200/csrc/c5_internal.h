@@ -95,8 +95,9 @@ struct DeviceState {
     size_t h_row_cost_n = 0;
     // c5_debug_set (tests, diagnostics); 0 = default
     int opt_graze_list = 0, opt_query_budget = 0, opt_serial_list = 0, opt_graze_blocks = 0, opt_mask_per_face = 0, opt_mask_tile = 0;
-    bool opt_no_zero_copy = false, opt_prep_priority = false, opt_no_static_mask = false;
-    cudaStream_t prep_stream = nullptr;         // high priority: rotate / refit / mask when opt_prep_priority
+    bool opt_no_zero_copy = false, opt_no_static_mask = false;
+    int opt_prep_priority = 0;                  // bit 0: rotate / refit / mask, bit 1: the grazing-ray kernel, on prep_stream
+    cudaStream_t prep_stream = nullptr;         // high priority (see opt_prep_priority)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // c5_debug_set("timeline", n): phase events of the last n views, read by c5_timeline_read
     std::vector<cudaEvent_t> tl_events;         // [n][kTimelinePhases]
@@ -173,6 +174,8 @@ struct WalkLaunch {
     double* out; // {tau, I} per pixel of the band, x fastest
     cudaEvent_t mark_walk_done;    // recorded between the pixel kernel and the grazing-ray kernel (may be null)
     cudaEvent_t mark_walk_done_tl; // the same moment for the timeline ring (may be null)
+    cudaStream_t graze_stream;     // non-null: the grazing-ray kernel goes there (after mark_walk_done) and is joined back
+    cudaEvent_t graze_join;
 };
 void launch_walk(DeviceState& d, const WalkLaunch& w);
 

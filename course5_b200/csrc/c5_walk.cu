@@ -1417,12 +1417,21 @@ void launch_walk(DeviceState& d, const WalkLaunch& w) {
     if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
     const unsigned graze_grid = static_cast<unsigned>(d.sm_count) * static_cast<unsigned>(d.opt_graze_blocks > 0 ? d.opt_graze_blocks : kGrazeBlocksPerSm);
     count_launch();
+    cudaStream_t gs = d.stream;
+    if (w.graze_stream && w.mark_walk_done) { // c5_debug_set("prep_priority", 2): on the high-priority stream, still AFTER the pixel kernel
+        gs = w.graze_stream;
+        C5_CUDA(cudaStreamWaitEvent(gs, w.mark_walk_done, 0));
+    }
     if (f32) {
-        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
+        grazing_rays_fp32<<<graze_grid, 32 * kGrazeWarps, 0, gs>>>(P);
     } else {
-        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, d.stream>>>(P);
+        grazing_rays_fp64<<<graze_grid, 32 * kGrazeWarps, 0, gs>>>(P);
     }
     C5_CUDA(cudaGetLastError());
+    if (gs != d.stream) {
+        C5_CUDA(cudaEventRecord(w.graze_join, gs));
+        C5_CUDA(cudaStreamWaitEvent(d.stream, w.graze_join, 0));
+    }
 }
 
 } // namespace c5

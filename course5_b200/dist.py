@@ -52,7 +52,7 @@ class BandRenderer:
     """Renders row bands of successive views on this rank's device and assembles them on rank 0."""
 
     def __init__(self, ctx: api.Context, *, device: torch.device, rank: int, world: int,
-                 base_cost: float = 64.0, gather: str = "auto", lanes: int = 2):
+                 base_cost: float = 64.0, gather: str = "auto", lanes: int = 2, sets: int | None = None):
         self.ctx, self.device, self.rank, self.world = ctx, device, rank, world
         self.base_cost = base_cost
         if gather == "auto":
@@ -62,7 +62,11 @@ class BandRenderer:
         self.gather_mode = gather
         self.row_cost: np.ndarray | None = None
         self.n_lanes = max(1, int(lanes))
-        self.n_sets = self.n_lanes + 1     # view k + n_sets reuses view k's buffers (module docstring)
+        # view k + n_sets reuses view k's buffers (module docstring). lanes + 1 sets are the minimum; with that a
+        # lane's next view waits for EVERY rank to have finished the lane's previous one, so each view costs the
+        # slowest rank's time for it. A second round of sets lets a rank run a whole round of views ahead, and
+        # the view-to-view scatter of the ranks (+-10 % measured) averages out instead of adding up.
+        self.n_sets = max(self.n_lanes + 1, int(sets)) if sets else (2 * self.n_lanes + 1 if world > 1 else self.n_lanes + 1)
         self._band_buf = [None] * self.n_sets  # buffer sets: the exchange of one view may still be reading /
         self._image = [None] * self.n_sets     # writing its set while the next views fill the others
         self._peer = [None] * self.n_sets      # p2p: (device pointer of rank 0's image, bytes) per set
@@ -72,6 +76,7 @@ class BandRenderer:
         self._cost_has_base = False        # row_cost is measured time (the per-row constant is in it)
         self._flag = None
         self._time_cost = None             # calibrate(): last per-row time estimate (milliseconds)
+        self.calibration_log = []          # calibrate(): per round, the cut that was timed and what every rank sustained
         self._lanes = []                   # [(context, side stream)] on CUDA, created on first use
 
     # -- band cuts --------------------------------------------------------------------------------
@@ -202,53 +207,68 @@ class BandRenderer:
         tails and grazing-ray kernels overlapped — not the time one view takes alone, and a band's
         rate per tet-step depends on what is in it (short silhouette rays, the solid mask, rows of
         grazing rays). So each round renders `views` pipelined views of this rank's band without
-        any exchange, times them with CUDA events (sustained rate: the difference of a long and a short
-        run), corrects the cost of the band's rows by measured / predicted and re-cuts. Collective:
+        any exchange, times them with CUDA events (the clock starts once the pipeline is full), corrects the cost of the band's rows by measured / predicted and re-cuts. Collective:
         every rank must call it with the same arguments."""
         cuda = self.device.type == "cuda"
 
-        def timed(n: int) -> float:
-            """Milliseconds for n pipelined views of this rank's band, no exchange."""
+        def sustained(n: int, skip: int) -> float:
+            """Milliseconds per view over the last n of skip + n pipelined views of this rank's band, no
+            exchange. The clock starts when view number `skip` completes (an event on its lane's stream):
+            the pipeline is full by then. Timing a whole short run instead charges every band the latency
+            of its first view, which differs between bands by more than their sustained times do (C3 at
+            N = 8: first views 1.06 .. 1.73 ms, sustained 0.63 .. 0.76 ms)."""
             if cuda:
                 torch.cuda.synchronize(self.device)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
             else:
                 import time
-                t0 = time.perf_counter()
-            for _ in range(n):
+            for i in range(skip + n):
                 self.render(view, gather=False, stats=False, pipeline=True)
+                if i == skip - 1:
+                    if cuda:
+                        self._lane(self._count - 1)[1].record_event(e0)
+                    else:
+                        t0 = time.perf_counter()
             self.finish()
             if cuda:
                 e1.record()
                 torch.cuda.synchronize(self.device)
-                return e0.elapsed_time(e1)
-            return 1e3 * (time.perf_counter() - t0)
+                return e0.elapsed_time(e1) / n
+            return 1e3 * (time.perf_counter() - t0) / n
 
-        for _ in range(rounds):
-            _, _, bands = self.render(view, gather=False, rebalance="steps")      # per-row tet-steps, all-reduced
+        steps = None
+        if self._time_cost is None or self._time_cost.shape[0] != view.res_y:
+            self._time_cost = None
+            self.render(view, gather=False, rebalance="steps")      # per-row tet-steps, all-reduced; bands re-cut by them
             steps = self.row_cost.copy()
+        for _ in range(rounds):
+            # the cut that is timed is the cut the measurement is attributed to: nothing below changes it
+            # before the update at the end of the round (render(rebalance=False) leaves the cuts alone)
+            bands = self.bands(view.res_y)
             lo, hi = bands[self.rank]
-            # The SUSTAINED time per view: a short run and a long one, and the difference between them. Timing
-            # one run and dividing by its views charges every band the latency of its first view (the pipeline
-            # filling), which differs between bands by more than their sustained times do (measured on C3 at
-            # N = 8: first views 1.06 .. 1.73 ms, sustained 0.63 .. 0.76 ms — the cuts came out 10 % off).
-            short = self.n_lanes + 2
-            t_short = timed(short)
-            t_long = timed(short + views)
-            ms = max(t_long - t_short, 0.05 * t_long) / views
-            if self._time_cost is None or self._time_cost.shape != steps.shape:
+            ms = sustained(views, self.n_lanes + 2)
+            every = torch.zeros(self.world, dtype=torch.float64)
+            every[self.rank] = ms
+            if self.world > 1:
+                every = every.to(self.device)
+                dist.all_reduce(every, op=dist.ReduceOp.SUM)
+                every = every.cpu()
+            self.calibration_log.append({"bands": [list(b) for b in bands], "sustained_ms": [round(float(x), 4) for x in every]})
+            if self._time_cost is None:
                 # first estimate: the band's time spread over its rows in proportion to their tet-steps
                 mine = torch.from_numpy(api.time_weighted_row_cost(steps, (lo, hi), ms, base_cost=self.base_cost))
             else:
                 # afterwards: the rows keep the cost they have (it carries what earlier rounds learnt about how
                 # the rate differs from band to band) and the band as a whole is corrected towards what it
                 # measured now; rows that change bands take their cost with them
-                mine = torch.zeros(steps.shape[0], dtype=torch.float64)
+                mine = torch.zeros(view.res_y, dtype=torch.float64)
                 have = self._time_cost[lo:hi]
                 predicted = float(have.sum())
                 if predicted > 0.0:
-                    mine[lo:hi] = torch.from_numpy(have * (ms / predicted) ** 0.8)
+                    # decreasing gain: one measurement scatters by +-10 % (how the streams happen to interleave),
+                    # so later rounds average rather than chase it
+                    gain = max(0.35, 0.9 / (1 + 0.25 * max(0, len(self.calibration_log) - 2)))
+                    mine[lo:hi] = torch.from_numpy(have * (ms / predicted) ** gain)
                 else:
                     mine[lo:hi] = ms / max(hi - lo, 1)
             if self.world > 1:

@@ -216,7 +216,8 @@ uint64_t c5_kernel_launches(const c5_ctx* ctx);
  *                   (only in the experiments build, libc5gpu_exp.so; the product library ignores it)
  *   "no_static_mask" 1: solids that do not follow the view are scan-converted in every view, like the
  *                   others, instead of once per pixel grid (tests compare the two)
- *   "prep_priority" 1: rotate / refit / mask of a view run on a high-priority stream of their own
+ *   "prep_priority" bit 0: rotate / refit / mask of a view run on a high-priority stream of their own;
+ *                   bit 1: so does the grazing-ray kernel (still after the pixel kernel, by event)
  *   "no_zero_copy"  1: page-locked output buffers get a device-to-host copy like pageable ones
  *   "timeline"      n > 0: keep the phase events of the last n views of every lane (0 = off)
  * Unknown keys return C5_E_INVALID.

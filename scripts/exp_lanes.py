@@ -47,7 +47,7 @@ def main():
             st = c.render_device(v, outs[0].data_ptr(), s.cuda_stream)     # warm, and the band's step count
         for n_lanes in (int(x) for x in args.lanes.split(",")):
             times = []
-            for rep in range(3):
+            for rep in range(5):
                 torch.cuda.synchronize(dev)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -65,7 +65,7 @@ def main():
             print(json.dumps({"config": args.config, "view": [view["X"], view["Y"]], "rows": [lo, hi], "lanes": n_lanes,
                               "ms_per_view": round(ms, 4), "tet_steps": st["tet_steps"],
                               "Gsteps_per_s": round(st["tet_steps"] / ms / 1e6, 2),
-                              "one_view_ms_total": round(st["ms_total"], 4), "one_view_ms_graze": round(st["ms_graze"], 4),
+                              "reps_ms": [round(t, 4) for t in times], "one_view_ms_total": round(st["ms_total"], 4), "one_view_ms_graze": round(st["ms_graze"], 4),
                               "debug": debug}), flush=True)
     for c, _ in lanes[1:]:
         c.close()

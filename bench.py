@@ -345,7 +345,12 @@ def run_ours(args):
     big = mesh.n_tets > 16_000_000
     lanes = args.lanes if args.lanes > 0 else (2 if (world == 1 or big) else 4)
     e2e_in_flight = args.lanes if args.lanes > 0 else (3 if big else 4)   # submit/wait needs a third view to hide the host
-    br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=lanes)
+    # view groups (dist.py). Measured at N = 8 (profiles/r02_bench_*_n8_groups*.json): on C3 eight bands per view
+    # and two groups of four bands run at the same rate (0.717 vs 0.706 ms per view), so the plain row bands of
+    # the north_star stay; on the 50M-tet mesh the prologue every rank repeats (rotate + refit, 0.21 ms) and the
+    # lower rate of thin bands make two groups of four 1.4x faster (0.90 vs 1.26-1.35 ms), so big meshes use them.
+    groups = args.view_groups if args.view_groups > 0 else (world // 4 if (big and world >= 8 and world % 4 == 0) else 1)
+    br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=lanes, groups=groups)
 
     def barrier():
         if world > 1:
@@ -373,14 +378,17 @@ def run_ours(args):
     parity, parity_failed = None, False
     if world > 1:
         dog.tick("parity of the assembled image")
-        img_dev, _, _ = br.render(v, rebalance=False)
-        torch.cuda.synchronize(device)
-        barrier()
+        whole = ctx.render(v)[0] if rank == 0 else None
+        same, rows = True, np.zeros(0, dtype=np.int64)
+        for _ in range(br.groups):          # consecutive views go to consecutive view groups: every group once
+            img_dev, _, _ = br.render(v, rebalance=False)
+            torch.cuda.synchronize(device)
+            barrier()
+            if rank == 0:
+                got = img_dev.cpu().numpy()
+                same = same and bool(np.array_equal(got, whole, equal_nan=True))
+                rows = np.union1d(rows, np.where(~np.all((got == whole) | (np.isnan(got) & np.isnan(whole)), axis=(1, 2)))[0])
         if rank == 0:
-            whole, _ = ctx.render(v)
-            got = img_dev.cpu().numpy()
-            same = bool(np.array_equal(got, whole, equal_nan=True))
-            rows = np.where(~np.all((got == whole) | (np.isnan(got) & np.isnan(whole)), axis=(1, 2)))[0]
             parity = {"against": f"rank 0's own render of the whole view (bit for bit); one rank against oracle/_ref: "
                                  "the N = 1 line and tests/test_gpu_parity.py",
                       "assembled_image_equals_single_rank_render": same, "rows_that_differ": int(rows.size),
@@ -433,7 +441,7 @@ def run_ours(args):
     timeline = None
     if args.timeline:
         lanes_tl = br.timeline(ev0.cuda_event)
-        timeline = {"rank": rank, "band": list(bands[rank]), "host_enqueue_done_ms": [1e3 * t for t in host_t],
+        timeline = {"rank": rank, "view_group": br.group, "band": list(bands[br.band_index]), "host_enqueue_done_ms": [1e3 * t for t in host_t],
                     "phases": ["start", "rotated", "refitted", "mask", "pixel_kernel", "grazing_kernel"],
                     "lanes": [tl.tolist() for tl in lanes_tl], "elapsed_ms": elapsed_ms}
         br.enable_timeline(0)
@@ -441,7 +449,7 @@ def run_ours(args):
     dog.tick("statistics pass")
     walk_ms, stats_last = [], None
     for _ in range(3):
-        _, st, _ = br.render(v, rebalance=False)
+        _, st, _ = br.render(v, rebalance=False, gather=False)    # every rank its own band, no exchange
         walk_ms.append(st["ms_walk"])
         stats_last = st
     barrier()
@@ -461,38 +469,61 @@ def run_ours(args):
         e2e_mode = E2E_AUTO(world)
     if e2e_mode == "copy":
         ctx.debug_set("no_zero_copy", 1)
-    lo, hi = bands[rank]
-    n_img = L + 1 if world == 1 else 2 * L + 1   # N > 1: a rank may run a round of views ahead of the slowest one
+    lo, hi = bands[br.band_index]
+    G = br.groups
+    group_ranks = [list(range(g * br.per_group, (g + 1) * br.per_group)) for g in range(G)]
+    n_img = L + 1 if world == 1 else 2 * L * G + 1   # N > 1: a rank may run a round of views ahead of the slowest one
     shared = SharedHostImage(ctx, view["res_x"], view["res_y"], rank=rank, world=world, sets=n_img)
 
     def e2e_run(n_views, base):
-        """Views base .. base + n_views - 1 (the flags in the segment count views since its creation)."""
+        """Views base .. base + n_views - 1 (the flags in the segment count views since its creation). View k is
+        rendered by view group k % G; a rank has up to L of its own views in flight. Rank 0 takes every image, in
+        order, as soon as its bands are in — but waits for one only when it needs that image's set back, so that it
+        is no more tightly coupled to the slowest rank than the others are."""
         tickets = collections.deque()
-        steps_seen = 0
-        for k in range(n_views + L):
-            if k >= L:
-                kk = base + k - L
-                steps_seen += shared.complete_band(tickets.popleft(), kk)["tet_steps"]
-                if rank == 0:
-                    image = shared.wait_image(kk)      # complete in host memory here
-                    assert image.shape[0] == view["res_y"]
-                    shared.release(kk)
-            if k < n_views:
-                tickets.append(shared.submit_band(v, (lo, hi), base + k))
-        return steps_seen
+        steps_seen, own = 0, 0
+        end = base + n_views
+        taken = base                      # rank 0: images base .. taken - 1 have been taken and released
 
-    e2e_run(2 * L, 0)
+        def take(must_reach):
+            nonlocal taken
+            while taken < end:
+                who = group_ranks[taken % G]
+                if taken >= must_reach and int(shared._flags[who].min()) < taken + 1:
+                    return
+                image = shared.wait_image(taken, who)      # complete in host memory here
+                assert image.shape[0] == view["res_y"]
+                shared.release(taken)
+                taken += 1
+
+        for k in range(n_views + L * G):
+            if k >= L * G:
+                kk = base + k - L * G
+                if kk % G == br.group:
+                    steps_seen += shared.complete_band(tickets.popleft(), kk)["tet_steps"]
+                    own += 1
+            if k < n_views and (base + k) % G == br.group:
+                if rank == 0:
+                    take(base + k - n_img + 1)             # the set view base + k reuses must have been released
+                tickets.append(shared.submit_band(v, (lo, hi), base + k))
+            elif rank == 0:
+                take(base)                                 # whatever is ready
+        if rank == 0:
+            take(end)
+        return steps_seen, own
+
+    e2e_run(2 * L * G, 0)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = e2e_run(args.steps, 2 * L)
+    e2e_steps, e2e_own = e2e_run(args.steps, 2 * L * G)
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_image_ok = True
     if rank == 0:   # the last host image is the view (spot check: same NaN mask and finite elsewhere)
-        last = shared.arrays[(2 * L + args.steps - 1) % n_img]
+        last = shared.arrays[(2 * L * G + args.steps - 1) % n_img]
         e2e_image_ok = bool(np.isnan(last).any() and np.isfinite(last[~np.isnan(last)]).all() and (last != 0).any())
     shared.close()
-    assert e2e_steps == band_steps * args.steps, (e2e_steps, band_steps)
+    assert e2e_steps == band_steps * e2e_own, (e2e_steps, band_steps, e2e_own)
 
     dog.tick("reduce over ranks")
     t = torch.tensor([elapsed_ms, e2e_s * 1e3, float(np.mean(walk_ms)), host_enqueue_ms], dtype=torch.float64, device=device)
@@ -502,6 +533,7 @@ def run_ours(args):
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     elapsed_ms, e2e_ms, walk_ms_max, host_enqueue_ms = (float(x) for x in t.cpu())
     total_steps, total_launches = (int(x) for x in s.cpu())
+    total_steps //= br.groups            # every band is held by one rank of every view group
     # the roofline line describes the walk of the band with the most tet-steps (rank 0's may be empty)
     mine = torch.tensor([float(band_steps), float((hi - lo) * view["res_x"]), float(np.mean(walk_ms)),
                          float(stats_last["ms_graze"]), float(stats_last["ms_mask"]), float(stats_last["ms_total"])],
@@ -544,15 +576,18 @@ def run_ours(args):
             "tet_steps_per_view": total_steps,
             "config": config_dict(args.workload, mesh, view),
             "execution": {
-                "views_in_flight": br.n_lanes,
+                "views_in_flight": br.n_lanes, "view_groups": br.groups, "bands_per_view": br.per_group,
                 "walk": "pixel kernel, then the grazing-ray kernel on the same stream (no kernel waits for another)",
                 "parallelism": "single GPU" if world == 1 else
-                               f"{world} row bands (time-balanced), mesh replicated, " +
+                               (f"{world} row bands (time-balanced), mesh replicated, " if br.groups == 1 else
+                                f"{br.groups} view groups of {br.per_group} ranks take alternate views, each view in {br.per_group} row bands "
+                                "(time-balanced), mesh replicated, every image assembled in rank 0's memory, ") +
                                ("bands stored into rank 0's image over NVLink peer mappings by the walk kernels, one 4-byte all-reduce per view as the barrier"
                                 if br.gather_mode == "p2p" else "one grouped ncclSend/ncclRecv gather-v to rank 0 per view"),
                 "host_enqueue_ms_per_view": host_enqueue_ms},
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(api.C.sizeof(api.View)) * world, "d2h_bytes_per_step": pixels * 16 + world * (64 + 8 * view["res_y"]),
+                    "h2d_bytes_per_step": int(api.C.sizeof(api.View)) * br.per_group,
+                    "d2h_bytes_per_step": pixels * 16 + br.per_group * (64 + 8 * view["res_y"]),
                     "views_in_flight": L, "image_spot_check": e2e_image_ok, "mode": e2e_mode,
                     "api": "c5_render_submit / c5_render_wait into page-locked host images " +
                            ("written in place by the walk kernels" if e2e_mode == "inplace" else
@@ -630,7 +665,11 @@ def main():
     ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="p2p",
                     help="N > 1: how bands reach rank 0's image. p2p = stored by the walk kernels straight into rank 0's image "
                          "over NVLink peer mappings (CUDA IPC); sendrecv = one grouped ncclSend/ncclRecv per view (the baseline)")
-    ap.add_argument("--calibrate", type=int, default=6, help="N > 1: rounds of band calibration before the timed region")
+    ap.add_argument("--view-groups", type=int, default=0,
+                    help="N > 1: split the ranks into this many groups that render alternate views, each by N / groups row "
+                         "bands (1 = every rank a band of every view; 0 = 1, except one group per four ranks for meshes "
+                         "above 16M tets from N = 8 on)")
+    ap.add_argument("--calibrate", type=int, default=8, help="N > 1: rounds of band calibration before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline + parity leg (profiling runs)")
     ap.add_argument("--e2e-mode", choices=["auto", "inplace", "copy"], default="auto",
                     help="e2e: the walk kernels store into the page-locked host image in place (default), or render into "
@@ -686,7 +725,8 @@ def run_with_fallback(args):
                    C5_BENCH_ATTEMPTS=json.dumps(log))
         cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--workload", args.workload,
-               "--e2e-mode", args.e2e_mode, "--calibrate", str(args.calibrate), "--debug", args.debug]
+               "--e2e-mode", args.e2e_mode, "--calibrate", str(args.calibrate), "--debug", args.debug,
+               "--view-groups", str(args.view_groups)]
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
         if args.timeline:

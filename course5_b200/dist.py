@@ -27,6 +27,11 @@ rank derives the same cuts. Tet-steps are not quite time (a band of short silhou
 a lower rate than one of long central rays), so ``rebalance="time"`` additionally scales each
 band's row costs by the time that band actually took.
 
+View groups (``groups`` > 1): the ranks are split into groups of consecutive ranks, each group renders
+whole views by row bands and the groups take alternate views (view k belongs to group k % groups);
+every image is still assembled in rank 0's memory. ``groups=1`` is plain row bands, ``groups=world``
+one whole view per rank.
+
 Sweeps can pipeline: with ``pipeline=True`` the exchange (or barrier) of view k is left in flight
 while the next views render into the other buffer sets. With L views in flight per GPU ("lanes":
 the context and L-1 siblings sharing its mesh, each on its own stream) there are L+1 sets, and a
@@ -52,8 +57,22 @@ class BandRenderer:
     """Renders row bands of successive views on this rank's device and assembles them on rank 0."""
 
     def __init__(self, ctx: api.Context, *, device: torch.device, rank: int, world: int,
-                 base_cost: float = 64.0, gather: str = "auto", lanes: int = 2, sets: int | None = None):
+                 base_cost: float = 64.0, gather: str = "auto", lanes: int = 2, sets: int | None = None,
+                 groups: int = 1):
         self.ctx, self.device, self.rank, self.world = ctx, device, rank, world
+        # View groups: the ranks are split into `groups` groups of world / groups consecutive ranks; every
+        # group renders WHOLE views by row bands, and the groups take alternate views (view k belongs to group
+        # k % groups). groups = 1 is plain row bands (every rank a band of every view); groups = world is one
+        # whole view per rank (what sweep.py does). In between it trades bands per view for views per node: a
+        # 1/8 band is a single wave of blocks and sustains a lower rate than a 1/4 band (DESIGN.md §7).
+        # Whatever the groups, every image is assembled in rank 0's memory.
+        groups = max(1, int(groups))
+        if world % groups:
+            raise ValueError("groups must divide the number of ranks")
+        self.groups = groups
+        self.per_group = world // groups            # bands per view
+        self.group = rank // self.per_group         # the group this rank renders for
+        self.band_index = rank % self.per_group     # which band of the group's views
         self.base_cost = base_cost
         if gather == "auto":
             gather = "p2p" if (device.type == "cuda" and world > 1) else "sendrecv"
@@ -66,12 +85,14 @@ class BandRenderer:
         # lane's next view waits for EVERY rank to have finished the lane's previous one, so each view costs the
         # slowest rank's time for it. A second round of sets lets a rank run a whole round of views ahead, and
         # the view-to-view scatter of the ranks (+-10 % measured) averages out instead of adding up.
-        self.n_sets = max(self.n_lanes + 1, int(sets)) if sets else (2 * self.n_lanes + 1 if world > 1 else self.n_lanes + 1)
+        self.n_sets = max(self.n_lanes + 1, int(sets)) if sets else (2 * self.n_lanes * self.groups + 1 if world > 1 else self.n_lanes + 1)
         self._band_buf = [None] * self.n_sets  # buffer sets: the exchange of one view may still be reading /
         self._image = [None] * self.n_sets     # writing its set while the next views fill the others
         self._peer = [None] * self.n_sets      # p2p: (device pointer of rank 0's image, bytes) per set
         self._pending = {}                 # view number -> requests of its exchange / barrier
         self._count = 0
+        self._own_count = 0                # views this rank has rendered itself (lanes rotate over these)
+        self._aux = None                   # stream for the barriers of views that belong to other groups
         self._bands = None                 # cached cut, valid until the row costs change
         self._cost_has_base = False        # row_cost is measured time (the per-row constant is in it)
         self._flag = None
@@ -85,9 +106,9 @@ class BandRenderer:
             return self._bands[1]
         if self.row_cost is None or self.row_cost.shape[0] != res_y:
             cost = np.ones(res_y)          # first view: equal heights
-            cut = api.balanced_bands(cost, self.world)
+            cut = api.balanced_bands(cost, self.per_group)
         else:
-            cut = api.balanced_bands(self.row_cost, self.world, base_cost=0.0 if self._cost_has_base else self.base_cost)
+            cut = api.balanced_bands(self.row_cost, self.per_group, base_cost=0.0 if self._cost_has_base else self.base_cost)
         self._bands = (res_y, cut)
         return cut
 
@@ -186,6 +207,8 @@ class BandRenderer:
         cur = torch.cuda.current_stream(self.device)
         for _, s in self._lanes:
             cur.wait_stream(s)
+        if self._aux is not None:
+            cur.wait_stream(self._aux)
 
     def prepare(self, view: api.View):
         """Everything a pipelined run of `view`-sized images creates lazily, created now: the lanes and,
@@ -245,9 +268,9 @@ class BandRenderer:
             # the cut that is timed is the cut the measurement is attributed to: nothing below changes it
             # before the update at the end of the round (render(rebalance=False) leaves the cuts alone)
             bands = self.bands(view.res_y)
-            lo, hi = bands[self.rank]
+            lo, hi = bands[self.band_index]
             ms = sustained(views, self.n_lanes + 2)
-            every = torch.zeros(self.world, dtype=torch.float64)
+            every = torch.zeros(self.world, dtype=torch.float64)   # (with view groups, several ranks time the same band)
             every[self.rank] = ms
             if self.world > 1:
                 every = every.to(self.device)
@@ -267,7 +290,7 @@ class BandRenderer:
                 if predicted > 0.0:
                     # decreasing gain: one measurement scatters by +-10 % (how the streams happen to interleave),
                     # so later rounds average rather than chase it
-                    gain = max(0.35, 0.9 / (1 + 0.25 * max(0, len(self.calibration_log) - 2)))
+                    gain = max(0.25, 0.9 / (1 + 0.25 * max(0, len(self.calibration_log) - 2)))
                     mine[lo:hi] = torch.from_numpy(have * (ms / predicted) ** gain)
                 else:
                     mine[lo:hi] = ms / max(hi - lo, 1)
@@ -275,7 +298,7 @@ class BandRenderer:
                 mine = mine.to(self.device)
                 dist.all_reduce(mine, op=dist.ReduceOp.SUM)
                 mine = mine.cpu()
-            new_cost = mine.numpy().astype(np.float64)
+            new_cost = mine.numpy().astype(np.float64) / self.groups   # mean over the ranks that hold the same band
             self._time_cost = new_cost
             self.row_cost, self._cost_has_base = new_cost, True
             self._bands = None
@@ -299,14 +322,26 @@ class BandRenderer:
         self._count += 1
         par = k % self.n_sets
         bands = self.bands(view.res_y)
-        lo, hi = bands[self.rank]
+        lo, hi = bands[self.band_index]
+        # view groups: an assembled view belongs to ONE group; a local render (gather=False) is everybody's
+        view_group = k % self.groups
+        mine = (not gather) or view_group == self.group
         v = api.View.from_buffer_copy(view)
         v.row_begin, v.row_end = lo, hi
         p2p = self.gather_mode == "p2p" and self.world > 1 and gather
         if p2p:
             self._peer_image(view, par)     # (re)creates the mapping outside the lane stream if needed
-        ctx, lane_stream = self._lane(k)
+        if mine:
+            ctx, lane_stream = self._lane(self._own_count)
+            self._own_count += 1
+        else:   # only this view's barrier is enqueued here: on a stream of its own, the lanes are not held up
+            ctx = self.ctx
+            self._lane(0)
+            if self._aux is None and self.device.type == "cuda":
+                self._aux = torch.cuda.Stream(self.device)
+            lane_stream = self._aux
 
+        st = {}
         if lane_stream is not None:
             # what the caller enqueued so far (e.g. its reads of older images) comes first
             lane_stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -320,43 +355,53 @@ class BandRenderer:
             # follows it, k - n_sets + 1 (module docstring)
             self._drain(k - self.n_sets + 1)
             if p2p:
-                base = self._peer[par][0]
-                st = ctx.render_device(v, base + lo * view.res_x * 16, stream, stats=stats)
-                # barrier: when it completes on a rank's stream, every rank's band of this view is in
+                if mine:
+                    base = self._peer[par][0]
+                    st = ctx.render_device(v, base + lo * view.res_x * 16, stream, stats=stats)
+                # barrier: when it completes on a rank's stream, every band of this view is in
                 if self._flag is None:
                     self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
                 self._pending[k] = [dist.all_reduce(self._flag, async_op=True)]
             else:
                 self._buffers(view, hi - lo, par)
-                if self.rank == 0 and gather:
+                if self.rank == 0 and gather and mine:
                     target = self._image[par][lo * view.res_x * 2: hi * view.res_x * 2]
                 else:
                     target = self._band_buf[par][: (hi - lo) * view.res_x * 2]
-                st = ctx.render_device(v, target.data_ptr(), stream, stats=stats)
+                if mine:
+                    st = ctx.render_device(v, target.data_ptr(), stream, stats=stats)
                 if self.world > 1 and gather:
                     ops = []
                     if self.rank == 0:
-                        for r in range(1, self.world):
-                            rlo, rhi = bands[r]
+                        for b in range(self.per_group):
+                            r = view_group * self.per_group + b
+                            if r == 0:
+                                continue    # rank 0's own band is in place already
+                            rlo, rhi = bands[b]
                             ops.append(dist.P2POp(dist.irecv, self._image[par][rlo * view.res_x * 2: rhi * view.res_x * 2], r))
-                    else:
+                    elif mine:
                         ops.append(dist.P2POp(dist.isend, target, 0))
-                    self._pending[k] = list(dist.batch_isend_irecv(ops))
+                    if ops:
+                        self._pending[k] = list(dist.batch_isend_irecv(ops))
             if not pipeline:
                 self._drain(k)
         if not pipeline and lane_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(lane_stream)
 
         if rebalance:
-            steps = torch.from_numpy(ctx.last_row_cost(view.res_y).astype(np.float64))
+            # a local render is done by every rank: each band then arrives once per group
+            share = 1.0 if gather else 1.0 / self.groups
+            steps = torch.zeros(view.res_y, dtype=torch.float64)
+            if mine:
+                steps = torch.from_numpy(ctx.last_row_cost(view.res_y).astype(np.float64)) * share
             both = torch.zeros((2, view.res_y), dtype=torch.float64)
             both[0] = steps
-            if rebalance == "time" and self.world > 1:
+            if rebalance == "time" and self.world > 1 and mine:
                 # spread the time this band took over its rows in proportion to their tet-steps (plus
                 # the per-row constant): bands whose rays run at a lower rate, or that carry the solid
                 # mask, get proportionally fewer rows next time
                 both[1] = torch.from_numpy(api.time_weighted_row_cost(
-                    steps.numpy(), (lo, hi), float(st["ms_mask"] + st["ms_walk"]), base_cost=self.base_cost))
+                    steps.numpy(), (lo, hi), float(st["ms_mask"] + st["ms_walk"]) * share, base_cost=self.base_cost))
             if self.world > 1:
                 both = both.to(self.device)
                 dist.all_reduce(both, op=dist.ReduceOp.SUM)
@@ -458,9 +503,11 @@ class SharedHostImage:
         self._flags[self.rank] = k + 1
         return st
 
-    def wait_image(self, k: int) -> np.ndarray:
-        """Rank 0: image of view k once every rank's band is in."""
-        self._spin(lambda: int(self._flags[: self.world].min()) >= k + 1, f"the bands of view {k}")
+    def wait_image(self, k: int, ranks=None) -> np.ndarray:
+        """Rank 0: image of view k once the band of every rank (or of `ranks`, the view group that rendered
+        this view) is in."""
+        who = list(range(self.world)) if ranks is None else list(ranks)
+        self._spin(lambda: int(self._flags[who].min()) >= k + 1, f"the bands of view {k}")
         return self.arrays[k % self.sets]
 
     def release(self, k: int):

@@ -118,3 +118,53 @@ def test_two_ranks_assemble_the_same_image(built, tmp_path):
     # first view: equal heights; second view: cut by the first view's per-row cost
     assert r["bands0"][0][1] == 45
     assert r["bands1"][0][1] != 45 or True
+
+
+def _group_worker(rank, world, port, out_path, groups):
+    """View groups: `groups` groups of world / groups ranks take alternate views, each view by row bands."""
+    sys.path.insert(0, ROOT)
+    from course5_b200 import api, synth
+    from course5_b200.dist import BandRenderer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = api.load_library(os.path.join(ROOT, "tests", "hostsim", "libc5hostsim.so"))
+    mesh = synth.kuhn_cube(6, seed=73)
+    ctx = api.Context(lib=lib)
+    ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+    br = BandRenderer(ctx, device=torch.device("cpu"), rank=rank, world=world, base_cost=1.0, lanes=2, groups=groups)
+    assert br.per_group == world // groups and br.group == rank // br.per_group
+    views = [api.make_view(96, 72, X=0.4, Y=Y, lib=lib) for Y in (0.2, 0.9, 1.3, 0.5, 1.7)]
+    results = {}
+    rendered = 0
+    for k, v in enumerate(views):                      # synchronous, bands re-cut by steps after every view
+        image, st, bands = br.render(v)
+        assert len(bands) == br.per_group and bands[0][0] == 0 and bands[-1][1] == 72
+        rendered += bool(st)                           # stats only from the group the view belonged to
+        if rank == 0:
+            results[f"img{k}"] = image.numpy().copy()
+    n_mine = len([k for k in range(len(views)) if k % groups == br.group])
+    assert rendered == n_mine, (rank, rendered, n_mine)
+    cal = br.calibrate(views[1], rounds=2, views=3)    # every rank renders here, whatever its group
+    assert len(cal) == br.per_group and cal[0][0] == 0 and cal[-1][1] == 72
+    assert len(br.calibration_log) == 2 and len(br.calibration_log[0]["sustained_ms"]) == world
+    imgs = [br.render(v, stats=False, pipeline=True)[0] for v in views]    # pipelined: 2 lanes * groups * 2 + 1 sets
+    br.finish()
+    if rank == 0:
+        for k, v in enumerate(views):
+            results[f"pipe{k}"] = imgs[k].numpy().copy()
+            results[f"full{k}"] = ctx.render(v)[0]
+        np.savez(out_path, **results)
+    br.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,groups", [(4, 2), (2, 2)])
+def test_view_groups_assemble_every_view_on_rank_zero(built, tmp_path, world, groups):
+    out = str(tmp_path / "groups.npz")
+    mp.spawn(_group_worker, args=(world, _free_port(), out, groups), nprocs=world, join=True)
+    r = np.load(out)
+    for k in range(5):
+        assert np.array_equal(r[f"img{k}"], r[f"full{k}"], equal_nan=True), f"view {k} (group {k % groups})"
+        assert np.array_equal(r[f"pipe{k}"], r[f"full{k}"], equal_nan=True), f"pipelined view {k}"

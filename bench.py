@@ -316,6 +316,8 @@ def run_ours(args):
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    from course5_b200.dist import bind_to_device_numa_node
+    numa = {"bound": False, "note": "--no-numa-bind"} if args.no_numa_bind else bind_to_device_numa_node(local_rank)
     dog = Watchdog(rank, limit_s=float(os.environ.get("C5_BENCH_STALL_LIMIT", "150" if world == 1 else "90")))
     dog.start()
     dog.tick("init process group" if world > 1 else "single process")
@@ -584,7 +586,8 @@ def run_ours(args):
                                 "(time-balanced), mesh replicated, every image assembled in rank 0's memory, ") +
                                ("bands stored into rank 0's image over NVLink peer mappings by the walk kernels, one 4-byte all-reduce per view as the barrier"
                                 if br.gather_mode == "p2p" else "one grouped ncclSend/ncclRecv gather-v to rank 0 per view"),
-                "host_enqueue_ms_per_view": host_enqueue_ms},
+                "host_enqueue_ms_per_view": host_enqueue_ms,
+                "numa": numa},
             "e2e": {"value": e2e_value, "unit": "tet-steps/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(api.C.sizeof(api.View)) * br.per_group,
                     "d2h_bytes_per_step": pixels * 16 + br.per_group * (64 + 8 * view["res_y"]),
@@ -678,6 +681,8 @@ def main():
     ap.add_argument("--experiment-no-exchange", action="store_true",
                     help="EXPERIMENT, not a measurement of the product path: the timed views skip the image exchange and its "
                          "per-view barrier, to see what the coupling of the ranks costs (the line is marked invalid)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not restrict each rank to the CPUs (and so the memory) of its GPU's NUMA node")
     ap.add_argument("--no-clock-sampler", action="store_true", help="experiments: no NVML polling at all")
     ap.add_argument("--timeline", default=None, metavar="FILE",
                     help="write per-rank, per-view phase times of the timed region (CUDA events) and host enqueue times as JSON")
@@ -733,6 +738,8 @@ def run_with_fallback(args):
             cmd += ["--timeline", args.timeline]
         if args.no_clock_sampler:
             cmd.append("--no-clock-sampler")
+        if args.no_numa_bind:
+            cmd.append("--no-numa-bind")
         if args.experiment_no_exchange:
             cmd.append("--experiment-no-exchange")
         try:   # stderr passes through; the hard limit is a second line of defence behind the child's watchdog

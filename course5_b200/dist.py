@@ -421,6 +421,38 @@ class BandRenderer:
         return image, st, bands
 
 
+def bind_to_device_numa_node(device_index: int) -> dict:
+    """Restricts this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that host
+    memory it touches first — page-locked images, its rows of a shared image — is allocated on that
+    node: N GPUs writing results into host memory then load every socket's memory controllers
+    instead of the one the launcher happened to start on. Returns what it did; a box without NUMA
+    information (one node, or sysfs hidden) is left alone."""
+    import os
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/numa_node") as f:
+            node = int(f.read().strip())
+        info.update(pci=bdf, numa_node=node)
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus))
+    except Exception as e:       # no sysfs, no permission, not Linux: nothing to do
+        info["note"] = f"{type(e).__name__}: {e}"
+    return info
+
+
 def _tensor_from_pointer(ptr: int, n_doubles: int, device: torch.device) -> torch.Tensor:
     """A float64 tensor view of library-owned device memory (no copy, no ownership)."""
     class _Cai:
@@ -473,6 +505,14 @@ class SharedHostImage:
         # done[r] = views rank r has completed; released = views rank 0 has handed back
         self._flags = np.ndarray((world + 1,), dtype=np.int64, buffer=self._shm.buf, offset=self.sets * image_bytes)
         self._pinned = np.ndarray((self.sets * res_y, res_x, 2), dtype=np.float64, buffer=self._shm.buf)
+        # first touch: every rank writes zeros into an equal share of the rows of every image before anyone pins
+        # the segment, so those pages live on the NUMA node of the process that will write most of them
+        # (bind_to_device_numa_node); row bands move with the calibration, the share stays close to them
+        if world > 1:
+            r0, r1 = res_y * rank // world, res_y * (rank + 1) // world
+            for a in self.arrays:
+                a[r0:r1] = 0.0
+            dist.barrier()
         ctx.host_register(self._pinned)
         self._registered = True
 

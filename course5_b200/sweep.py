@@ -73,6 +73,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    from .dist import bind_to_device_numa_node
+    numa = bind_to_device_numa_node(local)       # page-locked images on the GPU's own NUMA node
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -117,7 +119,7 @@ def main():
                           "tet_steps_per_sec": steps / dt, "tet_steps": steps, "views_in_flight": args.in_flight, "image_path": "copy engine" if args.no_zero_copy else "stored in place",
                           "res": [view["res_x"], view["res_y"]], "n_tets": mesh.n_tets,
                           "flags": {k: view[k] for k in ("X", "D", "I", "alpha_limit")},
-                          "upload_and_topology_s": upload_s,
+                          "upload_and_topology_s": upload_s, "numa": numa,
                           "includes": "per view: rotate + BVH refit + solid mask + walk + grazing rays + image to page-locked "
                                       "host memory (c5_render_submit / c5_render_wait), whole sweep wall clock, max over ranks"
                                       + ("; + .vti write" if args.out_dir else "")}))

@@ -100,3 +100,55 @@ def test_two_gpus_one_image(gpu_lib, tmp_path):
     assert not bad, f"(image, rows that differ, first, last): {bad}; bands: {bands}"
     for mode in ("p2p", "sendrecv"):
         assert r[f"{mode}_bands0"][0][1] == 180                    # first view: equal heights
+
+
+def _group_worker(rank, world, port, out_path):
+    """View groups on real GPUs: two groups of one rank each take alternate views; every image is assembled
+    in rank 0's memory, by stores over NVLink (p2p) and by the grouped send/recv."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from course5_b200 import api, synth
+    from course5_b200.dist import BandRenderer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    device = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    mesh = synth.kuhn_cube(20, seed=74)
+    ctx = api.Context(devices=(rank,))
+    ctx.upload_mesh(mesh.points, mesh.tets, mesh.alpha, mesh.q)
+    views = [api.make_view(400, 300, X=0.4, Y=Y) for Y in (0.2, 0.9, 1.4, 0.6, 1.1)]
+    results = {}
+    if rank == 0:
+        for k, v in enumerate(views):
+            results[f"full{k}"] = ctx.render(v)[0]
+    for mode in ("p2p", "sendrecv"):
+        br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=mode, lanes=2, groups=world)
+        br.prepare(views[0])
+        imgs = [br.render(v, stats=False, pipeline=True)[0] for v in views]
+        br.finish()
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        if rank == 0:
+            for k in range(len(views)):
+                results[f"{mode}{k}"] = imgs[k].cpu().numpy().copy()
+        dist.barrier()
+        br.close()
+    if rank == 0:
+        np.savez(out_path, **results)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_view_groups_on_two_gpus(gpu_lib, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    out = str(tmp_path / "groups.npz")
+    mp.spawn(_group_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = np.load(out)
+    for mode in ("p2p", "sendrecv"):
+        for k in range(5):
+            assert np.array_equal(r[f"{mode}{k}"], r[f"full{k}"], equal_nan=True), f"{mode}: view {k} (rendered by rank {k % 2})"

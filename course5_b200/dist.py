@@ -249,7 +249,7 @@ class BandRenderer:
                 self.render(view, gather=False, stats=False, pipeline=True)
                 if i == skip - 1:
                     if cuda:
-                        self._lane(self._count - 1)[1].record_event(e0)
+                        self._lane(self._own_count - 1)[1].record_event(e0)      # the lane that view went to
                     else:
                         t0 = time.perf_counter()
             self.finish()

@@ -317,6 +317,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     from course5_b200.dist import bind_to_device_numa_node
+    all_cpus = os.sched_getaffinity(0)        # the cpu_baseline leg gets every core back
     numa = {"bound": False, "note": "--no-numa-bind"} if args.no_numa_bind else bind_to_device_numa_node(local_rank)
     dog = Watchdog(rank, limit_s=float(os.environ.get("C5_BENCH_STALL_LIMIT", "150" if world == 1 else "90")))
     dog.start()
@@ -631,6 +632,7 @@ def run_ours(args):
             vraw = api.View.from_buffer_copy(v)
             vraw.round_through_float = 0
             ours = ctx.render_raw(vraw)
+            os.sched_setaffinity(0, all_cpus)
             r = time_reference(mesh, view, steps=1, warmup=0, raw=True, keep_image=True)
             line["cpu_baseline"] = {
                 "value": r["value"], "unit": "tet-steps/s", "cores": r["cores"], "kind": r["kind"],

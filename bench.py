@@ -348,11 +348,12 @@ def run_ours(args):
     big = mesh.n_tets > 16_000_000
     lanes = args.lanes if args.lanes > 0 else (2 if (world == 1 or big) else 4)
     e2e_in_flight = args.lanes if args.lanes > 0 else (3 if big else 4)   # submit/wait needs a third view to hide the host
-    # view groups (dist.py). Measured at N = 8 (profiles/r02_bench_*_n8_groups*.json): on C3 eight bands per view
-    # and two groups of four bands run at the same rate (0.717 vs 0.706 ms per view), so the plain row bands of
-    # the north_star stay; on the 50M-tet mesh the prologue every rank repeats (rotate + refit, 0.21 ms) and the
-    # lower rate of thin bands make two groups of four 1.4x faster (0.90 vs 1.26-1.35 ms), so big meshes use them.
-    groups = args.view_groups if args.view_groups > 0 else (world // 4 if (big and world >= 8 and world % 4 == 0) else 1)
+    # view groups (dist.py). Measured at N = 8, 20 timed views (profiles/r02_bench_*_n8_groups*.json): on C3 eight
+    # bands per view, two groups of four and four groups of two run within 4 % of each other (0.717 / 0.706 / 0.688
+    # ms per view), so the plain row bands of the north_star stay; on the 50M-tet mesh the prologue every rank
+    # repeats (rotate + refit, 0.21 ms) and the lower rate of thin bands make the groups much faster (C5t: 1.26-1.35
+    # ms as eight bands, 0.90 as 2 x 4, 0.82 as 4 x 2), so big meshes render two bands per view.
+    groups = args.view_groups if args.view_groups > 0 else (world // 2 if (big and world >= 8 and world % 2 == 0) else 1)
     br = BandRenderer(ctx, device=device, rank=rank, world=world, gather=args.gather, lanes=lanes, groups=groups)
 
     def barrier():
@@ -672,7 +673,7 @@ def main():
                          "over NVLink peer mappings (CUDA IPC); sendrecv = one grouped ncclSend/ncclRecv per view (the baseline)")
     ap.add_argument("--view-groups", type=int, default=0,
                     help="N > 1: split the ranks into this many groups that render alternate views, each by N / groups row "
-                         "bands (1 = every rank a band of every view; 0 = 1, except one group per four ranks for meshes "
+                         "bands (1 = every rank a band of every view; 0 = 1, except N / 2 groups of two ranks for meshes "
                          "above 16M tets from N = 8 on)")
     ap.add_argument("--calibrate", type=int, default=8, help="N > 1: rounds of band calibration before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline + parity leg (profiling runs)")

@@ -347,7 +347,9 @@ def run_ours(args):
     # four (0.65 vs 0.75 ms); on the 50M-tet mesh four views evict each other from L2 (6.2 vs 5.7 ms)
     big = mesh.n_tets > 16_000_000
     lanes = args.lanes if args.lanes > 0 else (2 if (world == 1 or big) else 4)
-    e2e_in_flight = args.lanes if args.lanes > 0 else (3 if big else 4)   # submit/wait needs a third view to hide the host
+    # e2e: the host submits a view only when an earlier one has come back, so short views (bands) need more in
+    # flight to keep every lane's queue fed: N = 8, 0.91 ms per view with eight against 1.0 with four
+    e2e_in_flight = args.e2e_in_flight or (args.lanes if args.lanes > 0 else (3 if big else 4 if world == 1 else api.MAX_IN_FLIGHT))
     # view groups (dist.py). Measured at N = 8, 20 timed views (profiles/r02_bench_*_n8_groups*.json): on C3 eight
     # bands per view, two groups of four and four groups of two run within 4 % of each other (0.717 / 0.706 / 0.688
     # ms per view), so the plain row bands of the north_star stay; on the 50M-tet mesh the prologue every rank
@@ -671,6 +673,8 @@ def main():
     ap.add_argument("--gather", choices=["auto", "p2p", "sendrecv"], default="p2p",
                     help="N > 1: how bands reach rank 0's image. p2p = stored by the walk kernels straight into rank 0's image "
                          "over NVLink peer mappings (CUDA IPC); sendrecv = one grouped ncclSend/ncclRecv per view (the baseline)")
+    ap.add_argument("--e2e-in-flight", type=int, default=0, choices=range(0, api.MAX_IN_FLIGHT + 1),
+                    help="e2e: views in flight per GPU through c5_render_submit / c5_render_wait (0 = --lanes, or 4; 3 on big meshes)")
     ap.add_argument("--view-groups", type=int, default=0,
                     help="N > 1: split the ranks into this many groups that render alternate views, each by N / groups row "
                          "bands (1 = every rank a band of every view; 0 = 1, except N / 2 groups of two ranks for meshes "
@@ -734,7 +738,7 @@ def run_with_fallback(args):
         cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--gather", a["gather"], "--lanes", str(a["lanes"]), "--workload", args.workload,
                "--e2e-mode", args.e2e_mode, "--calibrate", str(args.calibrate), "--debug", args.debug,
-               "--view-groups", str(args.view_groups)]
+               "--view-groups", str(args.view_groups), "--e2e-in-flight", str(args.e2e_in_flight)]
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
         if args.timeline:

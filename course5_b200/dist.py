@@ -34,12 +34,12 @@ one whole view per rank.
 
 Sweeps can pipeline: with ``pipeline=True`` the exchange (or barrier) of view k is left in flight
 while the next views render into the other buffer sets. With L views in flight per GPU ("lanes":
-the context and L-1 siblings sharing its mesh, each on its own stream) there are L+1 sets, and a
-rank starts view k+L+1 (which reuses view k's set) only after barrier k+1 has completed. Rank 0 enqueues barrier
-k+1 inside ``render(k+1)``, so the contract for the consumer of rank 0's image is: whatever reads
-image k must be finished, or enqueued on the current stream, BEFORE ``render(k+1)`` is called;
-the peers cannot overwrite it earlier, and a fast rank may still run one whole view ahead of the
-slowest one.
+the context and L-1 siblings sharing its mesh, each on its own stream) and G view groups there are
+S = 2 L G + 1 sets (L + 1 would do; the second round lets a rank run a round of views ahead of the
+slowest one), and a rank starts view k+S (which reuses view k's set) only after barrier k+1 has
+completed. Rank 0 enqueues barrier k+1 inside ``render(k+1)``, so the contract for the consumer of
+rank 0's image is: whatever reads image k must be finished, or enqueued on the current stream,
+BEFORE ``render(k+1)`` is called; the peers cannot overwrite it earlier.
 """
 from __future__ import annotations
 

@@ -6,9 +6,13 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <atomic>
+#include <cstdlib>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
+#include <unistd.h>
 #include <zlib.h>
 
 namespace c5host {
@@ -26,29 +30,42 @@ const char kB64[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456
 
 // One self-contained base64 stream (padded): VTK encodes the block table and the data separately.
 std::string base64(const unsigned char* p, std::size_t n) {
-    std::string out;
-    out.reserve((n + 2) / 3 * 4);
+    std::string out((n + 2) / 3 * 4, '=');
+    char* o = &out[0];
     std::size_t i = 0;
-    for (; i + 2 < n; i += 3) {
+    for (; i + 2 < n; i += 3, o += 4) {
         const unsigned v = (p[i] << 16) | (p[i + 1] << 8) | p[i + 2];
-        out += kB64[v >> 18];
-        out += kB64[(v >> 12) & 63];
-        out += kB64[(v >> 6) & 63];
-        out += kB64[v & 63];
+        o[0] = kB64[v >> 18];
+        o[1] = kB64[(v >> 12) & 63];
+        o[2] = kB64[(v >> 6) & 63];
+        o[3] = kB64[v & 63];
     }
     if (i + 1 == n) {
         const unsigned v = p[i] << 16;
-        out += kB64[v >> 18];
-        out += kB64[(v >> 12) & 63];
-        out += "==";
+        o[0] = kB64[v >> 18];
+        o[1] = kB64[(v >> 12) & 63];
     } else if (i + 2 == n) {
         const unsigned v = (p[i] << 16) | (p[i + 1] << 8);
-        out += kB64[v >> 18];
-        out += kB64[(v >> 12) & 63];
-        out += kB64[(v >> 6) & 63];
-        out += '=';
+        o[0] = kB64[v >> 18];
+        o[1] = kB64[(v >> 12) & 63];
+        o[2] = kB64[(v >> 6) & 63];
     }
     return out;
+}
+
+// Threads for the block compressor: the blocks of VTK's compressed layout are independent zlib streams, so a
+// 69 MB frame (66 blocks) is deflated by as many cores as there are, and the bytes written do not depend on how
+// many took part. C5_VTI_THREADS overrides (1 = the serial path; tests compare the two).
+unsigned compressor_threads(std::uint64_t n_blocks) {
+    unsigned n = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("C5_VTI_THREADS")) {
+        const long v = std::strtol(e, nullptr, 10);
+        if (v > 0) n = static_cast<unsigned>(v);
+    }
+    if (n == 0) n = 1;
+    if (n > 32) n = 32;
+    if (n > n_blocks) n = static_cast<unsigned>(n_blocks);
+    return n == 0 ? 1 : n;
 }
 
 // Decodes ONE padded base64 stream starting at p (stops after its padding or at a non-alphabet byte);
@@ -114,7 +131,17 @@ void write_vti(const std::string& filename, const double* image, std::size_t res
                  compress ? " compressor=\"vtkZLibDataCompressor\"" : "", ex, ey, ex, ey, b64 ? "base64" : "raw");
     if (!compress) {
         std::fwrite(&n_bytes, sizeof(n_bytes), 1, fp);
-        if (std::fwrite(image, 1, n_bytes, fp) != n_bytes) throw std::runtime_error("short write to " + filename);
+        // the pixels go straight from the caller's buffer to the file descriptor: stdio would copy 69 MB through its
+        // own buffer first
+        std::fflush(fp);
+        const char* at = reinterpret_cast<const char*>(image);
+        std::uint64_t left = n_bytes;
+        while (left > 0) {
+            const ssize_t w = ::write(fileno(fp), at, left > (1u << 30) ? (1u << 30) : left);
+            if (w <= 0) throw std::runtime_error("short write to " + filename);
+            at += w;
+            left -= static_cast<std::uint64_t>(w);
+        }
     } else {
         // VTK compressed block layout: [n_blocks][block_size][last_block_size][compressed sizes...] data...
         const std::uint64_t block = 1u << 20;
@@ -126,16 +153,31 @@ void write_vti(const std::string& filename, const double* image, std::size_t res
         header[1] = block;
         header[2] = (last == block) ? 0 : last;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(image);
-        for (std::uint64_t b = 0; b < n_blocks; b++) {
-            const uLong in_size = static_cast<uLong>(b + 1 == n_blocks ? last : block);
-            uLongf out_size = compressBound(in_size);
-            packed[b].resize(out_size);
-            if (compress2(packed[b].data(), &out_size, src + b * block, in_size, Z_BEST_SPEED) != Z_OK) {
-                throw std::runtime_error("zlib failed while writing " + filename);
+        std::atomic<std::uint64_t> next{0};
+        std::atomic<bool> failed{false};
+        auto deflate_blocks = [&] {   // blocks are handed out one at a time: the last, short one does not unbalance anyone
+            for (std::uint64_t b = next.fetch_add(1); b < n_blocks && !failed.load(); b = next.fetch_add(1)) {
+                const uLong in_size = static_cast<uLong>(b + 1 == n_blocks ? last : block);
+                uLongf out_size = compressBound(in_size);
+                packed[b].resize(out_size);
+                if (compress2(packed[b].data(), &out_size, src + b * block, in_size, Z_BEST_SPEED) != Z_OK) {
+                    failed.store(true);
+                    return;
+                }
+                packed[b].resize(out_size);
+                header[3 + b] = out_size;
             }
-            packed[b].resize(out_size);
-            header[3 + b] = out_size;
+        };
+        const unsigned n_threads = compressor_threads(n_blocks);
+        if (n_threads <= 1) {
+            deflate_blocks();
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < n_threads; t++) pool.emplace_back(deflate_blocks);
+            deflate_blocks();
+            for (auto& t : pool) t.join();
         }
+        if (failed.load()) throw std::runtime_error("zlib failed while writing " + filename);
         if (!b64) {
             std::fwrite(header.data(), sizeof(std::uint64_t), header.size(), fp);
             for (const auto& p : packed) std::fwrite(p.data(), 1, p.size(), fp);

@@ -222,6 +222,23 @@ def test_vti_writer_against_the_vtk_xml_format(host, tmp_path, mode):
     assert 'WholeExtent="0 52 0 36 0 0"' in head
 
 
+@pytest.mark.parametrize("b64", [False, True])
+def test_vti_block_compressor_threads_do_not_change_the_file(host, tmp_path, b64, monkeypatch):
+    """The compressed blocks are independent zlib streams: deflated by one thread or by many, the file
+    is the same, byte for byte (vti_writer.cpp compressor_threads)."""
+    rng = np.random.default_rng(5)
+    img = rng.normal(size=(700, 500, 2)).round(3)        # 5.6 MB: six blocks, the last one short
+    img[3, 4] = np.nan
+    files = []
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("C5_VTI_THREADS", threads)
+        path = str(tmp_path / f"t{threads}.vti")
+        host.write_vti(path, img, compress=True, base64=b64)
+        files.append(open(path, "rb").read())
+    assert files[0] == files[1] == files[2]
+    assert np.array_equal(_decode_vti_independently(str(tmp_path / "t16.vti")), img, equal_nan=True)
+
+
 def test_cli_matches_the_reference_contract(host):
     r, text, v = host.parse_cli(["-f", "a.vtk", "-d", "b.vti", "-j16", "-x", "2400", "-y", "1800",
                                  "--alpha_limit", "3.0", "-X", "0.5"])       # readme.md:40

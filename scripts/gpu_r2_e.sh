@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL: the mask_lane_shift knob belonged to the per-face mask kernels, which now live only in the experiments
+# build (c5_debug_set "mask_per_face"); kept as the record of the command behind profiles/r02_exp_mask_tile_skip_lanes.jsonl.
 # ONE GPU: solid mask passes — lanes per tall face, per-kernel times (ncu launch list).
 set -u
 mkdir -p gpurun_out

@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL: the walk_smem_kb knob this run used was removed after the measurement (profiles/r02_exp_walk_block_cap_by_smem.jsonl);
+# it ran at commit 'Negative result recorded: capping the pixel kernel...'^ and is kept as the record of the command.
 # ONE GPU: does the pixel kernel filling every SM keep the other lanes' prologues out? Cap its blocks per SM.
 set -u
 mkdir -p gpurun_out

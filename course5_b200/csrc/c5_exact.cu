@@ -337,6 +337,7 @@ C5_HD void tall_face_body(uint32_t f, const double* pts, const MaskGrid& g, cons
 // memory and deals out the ITEMS (rows in pass 1, tile rows in pass 3, rows of uncovered tile rows in
 // its drain) lane by lane, whoever the face belongs to. The arithmetic per item is the same
 // functions on the same operands as the per-face form, so the mask cannot differ.
+#define C5_HDN __host__ __device__ // (not force-inlined, unlike C5_HD)
 constexpr int kFaceFields = 17; // p1x p1y + 3 x {x1 y1 dx dy rdy}
 struct WarpFaces {
     double f[kFaceFields][32];
@@ -346,14 +347,14 @@ struct WarpFaces {
     int list[64][2];                  // pass 3: (lane of the face, tile row) still to be drawn
 };
 
-__device__ void wf_store_edge(WarpFaces& w, int at, int lane, const EdgeFn& e) {
+C5_HDN void wf_store_edge(WarpFaces& w, int at, int lane, const EdgeFn& e) {
     w.f[at][lane] = e.x1;
     w.f[at + 1][lane] = e.y1;
     w.f[at + 2][lane] = e.dx;
     w.f[at + 3][lane] = e.dy;
     w.f[at + 4][lane] = e.rdy;
 }
-__device__ EdgeFn wf_load_edge(const WarpFaces& w, int at, int o, bool flat) {
+C5_HDN EdgeFn wf_load_edge(const WarpFaces& w, int at, int o, bool flat) {
     EdgeFn e;
     e.x1 = w.f[at][o];
     e.y1 = w.f[at + 1][o];
@@ -363,7 +364,7 @@ __device__ EdgeFn wf_load_edge(const WarpFaces& w, int at, int o, bool flat) {
     e.flat = flat;
     return e;
 }
-__device__ void wf_store(WarpFaces& w, int lane, const FaceScan& S) {
+C5_HDN void wf_store(WarpFaces& w, int lane, const FaceScan& S) {
     w.f[0][lane] = S.p1x;
     w.f[1][lane] = S.p1y;
     wf_store_edge(w, 2, lane, S.e_long);
@@ -373,7 +374,7 @@ __device__ void wf_store(WarpFaces& w, int lane, const FaceScan& S) {
     w.j_hi[lane] = static_cast<int>(S.j_hi);
     w.bits[lane] = (S.e_long.flat ? 1 : 0) | (S.e_low.flat ? 2 : 0) | (S.e_up.flat ? 4 : 0) | (S.long_edge_is_left ? 8 : 0);
 }
-__device__ FaceScan wf_load(const WarpFaces& w, int o) {
+C5_HDN FaceScan wf_load(const WarpFaces& w, int o) {
     FaceScan S;
     const int bits = w.bits[o];
     S.p1x = w.f[0][o];
@@ -401,7 +402,7 @@ __device__ int wf_deal(WarpFaces& w, int lane, int n) {
 }
 // The lane whose face item i belongs to: the LAST lane with first <= i (lanes without items share
 // their `first` with the next lane that has some, and that one is the later of them).
-__device__ int wf_owner(const WarpFaces& w, int i) {
+C5_HDN int wf_owner(const WarpFaces& w, int i) {
     int o = 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -797,18 +798,98 @@ void mask_passes(DeviceState& d, SolidSet& ss, const MaskGrid& g, const TileGrid
     d.mask_counts.ensure(1);
     dev_zero(d.mask_counts.p, sizeof(unsigned), d.stream);
     const int ty0 = g.row_begin / tg.h, ty1 = (g.row_end + tg.h - 1) / tg.h;
-    if (kHostSim) { // the same three passes as host loops
+    if (kHostSim) {
+        // The same three passes on the host, organised the way the kernels are: 32 faces at a time in a
+        // WarpFaces, their items dealt out one by one (wf_owner / wf_load), uncovered tile rows through the
+        // 64-entry list and its drain. What the CPU tests cannot reach is only the warp plumbing itself
+        // (shuffles, ballots); the item -> (face, row) arithmetic is the kernels' own.
+        static WarpFaces w;
         count_launch();
-        for (int64_t i = 0; i < ss.n_faces; i++) {
-            const uint32_t f = ss.faces.p[i];
-            if (small_face_body(f, ss.pts_view.p, g)) d.mask_tall.p[d.mask_counts.p[0]++] = f;
+        unsigned& n_tall = d.mask_counts.p[0];
+        for (int64_t base = 0; base < ss.n_faces; base += 32) {
+            int total = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                int rows = 0;
+                if (base + lane < ss.n_faces) {
+                    const uint32_t f = ss.faces.p[base + lane];
+                    const double *a, *b, *c;
+                    face_corners(f, ss.pts_view.p, a, b, c);
+                    const FaceRows R = scan_rows(g, a, b, c);
+                    if (R.j_lo <= R.j_hi) {
+                        if (R.j_hi - R.j_lo >= kSmallRows) {
+                            d.mask_tall.p[n_tall++] = f;
+                        } else {
+                            wf_store(w, lane, scan_edges(R));
+                            rows = static_cast<int>(R.j_hi - R.j_lo) + 1;
+                        }
+                    }
+                }
+                w.first[lane] = total;
+                total += rows;
+            }
+            for (int i = 0; i < total; i++) {
+                const int o = wf_owner(w, i);
+                const FaceScan S = wf_load(w, o);
+                scan_row(g, S, S.j_lo + (i - w.first[o]));
+            }
         }
         count_launch();
         for (int ty = ty0; ty < ty1; ty++) {
             for (int tx = 0; tx < tg.tiles_x; tx++) tile_flag_body(ty, tx, g, tg);
         }
         count_launch();
-        for (unsigned i = 0; i < d.mask_counts.p[0]; i++) tall_face_body(d.mask_tall.p[i], ss.pts_view.p, g, tg, 0, 1);
+        auto drain = [&](int n_list) {
+            for (int k = 0; k < n_list * tg.h; k++) {
+                const int e = k / tg.h;
+                const int o = w.list[e][0];
+                const long long j = static_cast<long long>(w.list[e][1]) * tg.h + k % tg.h;
+                if (j >= w.j_lo[o] && j <= w.j_hi[o]) scan_row(g, wf_load(w, o), j);
+            }
+        };
+        for (unsigned base = 0; base < n_tall; base += 32) {
+            int total = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                int items = 0;
+                if (base + lane < n_tall) {
+                    const double *a, *b, *c;
+                    face_corners(d.mask_tall.p[base + lane], ss.pts_view.p, a, b, c);
+                    const FaceRows R = scan_rows(g, a, b, c);
+                    if (R.j_lo <= R.j_hi) {
+                        wf_store(w, lane, scan_edges(R));
+                        w.c_lo[lane] = static_cast<int>(R.j_lo / tg.h);
+                        items = static_cast<int>(R.j_hi / tg.h - R.j_lo / tg.h) + 1;
+                    }
+                }
+                w.first[lane] = total;
+                total += items;
+            }
+            int n_list = 0;
+            for (int at = 0; at < total; at += 32) {   // one round of the warp: 32 items, then the list bookkeeping
+                int found[32][2], m = 0;
+                for (int i = at; i < total && i < at + 32; i++) {
+                    const int o = wf_owner(w, i);
+                    const int c = w.c_lo[o] + (i - w.first[o]);
+                    long long ja, jb;
+                    if (!tile_row_covered(g, tg, wf_load(w, o), c, ja, jb)) {
+                        found[m][0] = o;
+                        found[m][1] = c;
+                        m++;
+                    }
+                }
+                if (m) {
+                    if (n_list + m > 64) {
+                        drain(n_list);
+                        n_list = 0;
+                    }
+                    for (int k = 0; k < m; k++) {
+                        w.list[n_list + k][0] = found[k][0];
+                        w.list[n_list + k][1] = found[k][1];
+                    }
+                    n_list += m;
+                }
+            }
+            drain(n_list);
+        }
         return;
     }
     if (d.sm_count == 0) C5_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));

@@ -273,6 +273,23 @@ def check_static_solid_mask_cache(lib, port, res=(400, 300)):
     assert np.array_equal(inside, got[True][1][band["row_begin"]: band["row_end"]])
 
 
+def check_solid_mask_tile_sizes(lib, port, res=(320, 240), tiles=(801, 804, 1608, 3216, 6499)):
+    """The mask must not depend on the size of the "tile already solid" flags (c5_debug_set "mask_tile" =
+    100 w + h): one-row tiles make every row of a tall face an item of its own (hundreds of items per
+    warp, the 64-entry list of rows still to be drawn overflows and is drained in the middle of a batch),
+    huge tiles are never full, so every tall face is drawn in full."""
+    mesh = synth.kuhn_cube(3, seed=12)
+    solids = reference_solids(0.1)
+    kw = dict(X=0.45, Y=0.8)
+    want = port.render(mesh.tet_points(), mesh.alpha, mesh.q, res_x=res[0], res_y=res[1],
+                       solid_rot=solids[0], solid_static=solids[1], **kw)
+    assert want.solid.sum() > 500
+    for tile in tiles:
+        for cached in (0, 1):
+            got = render_raw(lib, mesh, res[0], res[1], solids=solids, debug={"mask_tile": tile, "no_static_mask": 1 - cached}, **kw)
+            assert np.array_equal(got.solid, want.solid), f"mask_tile={tile}, static footprint cached={cached}"
+
+
 def check_grazing_rays(lib, port, *, n=12, res=(240, 180), debug_key="serial_list", debug_value=5):
     """Views that look along a lattice axis see the jittered side walls edge-on: rays there leave
     and re-enter the mesh once per cell. The pixel kernel hands them to the grazing-ray kernel

@@ -90,6 +90,10 @@ def test_solid_mask_high_resolution(hostsim_lib, port):
     rc.check_solid_mask_high_resolution(hostsim_lib, port, res=(800, 600), views=((0.4, 0.3, 0.0),))
 
 
+def test_solid_mask_tile_sizes(hostsim_lib, port):
+    rc.check_solid_mask_tile_sizes(hostsim_lib, port)
+
+
 def test_static_solid_mask_cache(hostsim_lib, port):
     rc.check_static_solid_mask_cache(hostsim_lib, port)
 

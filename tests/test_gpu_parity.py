@@ -342,6 +342,14 @@ def test_solid_mask_high_resolution(gpu_lib, port):
     rc.check_solid_mask_high_resolution(gpu_lib, port, res=(2400, 1800))
 
 
+def test_solid_mask_tile_sizes(gpu_lib, port):
+    rc.check_solid_mask_tile_sizes(gpu_lib, port, res=(800, 600))
+
+
+def test_static_solid_mask_cache(gpu_lib, port):
+    rc.check_static_solid_mask_cache(gpu_lib, port)
+
+
 def test_search_budget(gpu_lib, port):
     rc.check_search_budget(gpu_lib, port, n=20, res=(400, 300))
 

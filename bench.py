@@ -348,8 +348,8 @@ def run_ours(args):
     big = mesh.n_tets > 16_000_000
     lanes = args.lanes if args.lanes > 0 else (2 if (world == 1 or big) else 4)
     # e2e: the host submits a view only when an earlier one has come back, so short views (bands) need more in
-    # flight to keep every lane's queue fed: N = 8, 0.91 ms per view with eight against 1.0 with four
-    e2e_in_flight = args.e2e_in_flight or (args.lanes if args.lanes > 0 else (3 if big else 4 if world == 1 else api.MAX_IN_FLIGHT))
+    # flight to keep every lane's queue fed: N = 8, 0.91 ms per view with eight against 1.0 with four (N = 4: no gain)
+    e2e_in_flight = args.e2e_in_flight or (args.lanes if args.lanes > 0 else (3 if big else api.MAX_IN_FLIGHT if world >= 8 else 4))
     # view groups (dist.py). Measured at N = 8, 20 timed views (profiles/r02_bench_*_n8_groups*.json): on C3 eight
     # bands per view, two groups of four and four groups of two run within 4 % of each other (0.717 / 0.706 / 0.688
     # ms per view), so the plain row bands of the north_star stay; on the 50M-tet mesh the prologue every rank
